@@ -1,0 +1,267 @@
+// Self-attention core of nn.MultiheadAttention for the MDM encoder (reference: model/mdm.py:107-114, :284;
+// no key-padding mask -- `src_key_padding_mask` is commented out there), head dim 128, S <= 208 keys:
+//
+//   O[s, :] = softmax_j( Q[s,:] . K[j,:] / sqrt(128) ) V[j, :]
+//
+// One CTA per (sequence, head, 128-query tile).  Both contractions run on tcgen05 tensor cores:
+//   S = Q K^T   : A = Q tile (smem, K-major), B = K tile (smem, K-major), D = 128 x 208 fp32 in TMEM
+//   O = P V     : A = P (bf16, written into TMEM by the softmax warps, aliasing S), B = V (smem, MN-major),
+//                 D = 128 x 128 fp32 in TMEM
+// Q, K and V are read straight out of the QKV projection's [tokens, 3*H*128] bf16 planes with TMA
+// (no head-split or transpose kernels).  With nsplit = 3 every product uses the hi/lo bf16 split
+// (X_lo*Y_hi + X_hi*Y_lo + X_hi*Y_hi), P included, so the result is fp32-accurate.
+//
+// warp 0: TMA producer   warp 1: MMA issuer (+TMEM alloc)   warps 2..5: softmax + output (thread = query row)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cmdi {
+
+namespace {
+
+constexpr int kHeadDim = 128;
+constexpr int kQTile = 128;
+constexpr int kKeyPad = kAttnKeyPad;            // 208 = 13 * 16
+constexpr int kQBlockBytes = kQTile * 128;      // 64 dh-columns of 128 queries
+constexpr int kKVBlockBytes = kKeyPad * 128;    // 64 dh-columns of 208 keys  (26 swizzle atoms)
+constexpr int kQPlane = 2 * kQBlockBytes;       // 32768
+constexpr int kKVPlane = 2 * kKVBlockBytes;     // 53248
+constexpr int kOffQHi = 0, kOffQLo = kQPlane;
+constexpr int kOffKHi = 2 * kQPlane, kOffKLo = kOffKHi + kKVPlane;
+constexpr int kOffVHi = kOffKLo + kKVPlane;
+constexpr int kOffVLo = kOffKHi;                // V_lo reuses the K region once S is complete
+constexpr int kSmemTiles = kOffVHi + kKVPlane;  // 225280
+constexpr int kThreads = 192;
+// TMEM columns
+constexpr uint32_t kColS = 0, kColPHi = 0, kColPLo = 208, kColO = 320, kTmemCols = 512;
+
+struct __align__(8) AttnBarriers {
+  uint64_t qk_full, vhi_full, vlo_full, s_full, p_full, o_full;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
+                 const __grid_constant__ CUtensorMap map_kv_hi, const __grid_constant__ CUtensorMap map_kv_lo,
+                 const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(smem + kSmemTiles);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qtile = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
+  const int S = p.seq_len;
+  const bool split = (p.nsplit == 3);
+  const int row0 = seq * S;  // first token row of this sequence
+  const int q_col = head * kHeadDim;
+  const int k_col = p.num_heads * kHeadDim + head * kHeadDim;
+  const int v_col = 2 * p.num_heads * kHeadDim + head * kHeadDim;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q_hi);
+    tma_prefetch_desc(&map_kv_hi);
+    mbar_init(&bars->qk_full, 1);
+    mbar_init(&bars->vhi_full, 1);
+    mbar_init(&bars->vlo_full, 1);
+    mbar_init(&bars->s_full, 1);
+    mbar_init(&bars->p_full, 128);
+    mbar_init(&bars->o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    tmem_alloc(&bars->tmem_base, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp_idx == 0) {
+    if (lane == 0) {
+      // Q + K
+      mbar_arrive_expect_tx(&bars->qk_full, (split ? 2 : 1) * (kQPlane + kKVPlane));
+      for (int j = 0; j < 2; ++j) {
+        tma_load_2d(smem + kOffQHi + j * kQBlockBytes, &map_q_hi, &bars->qk_full, q_col + j * 64, row0 + qtile * kQTile);
+        tma_load_2d(smem + kOffKHi + j * kKVBlockBytes, &map_kv_hi, &bars->qk_full, k_col + j * 64, row0);
+        if (split) {
+          tma_load_2d(smem + kOffQLo + j * kQBlockBytes, &map_q_lo, &bars->qk_full, q_col + j * 64, row0 + qtile * kQTile);
+          tma_load_2d(smem + kOffKLo + j * kKVBlockBytes, &map_kv_lo, &bars->qk_full, k_col + j * 64, row0);
+        }
+      }
+      // V_hi (own buffer, lands while S is being computed)
+      mbar_arrive_expect_tx(&bars->vhi_full, kKVPlane);
+      for (int j = 0; j < 2; ++j)
+        tma_load_2d(smem + kOffVHi + j * kKVBlockBytes, &map_kv_hi, &bars->vhi_full, v_col + j * 64, row0);
+      if (split) {
+        // V_lo overwrites K once the S MMAs have consumed it
+        mbar_wait(&bars->s_full, 0);
+        mbar_arrive_expect_tx(&bars->vlo_full, kKVPlane);
+        for (int j = 0; j < 2; ++j)
+          tma_load_2d(smem + kOffVLo + j * kKVBlockBytes, &map_kv_lo, &bars->vlo_full, v_col + j * 64, row0);
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx == 1) {
+    if (lane == 0) {
+      const uint32_t sbase = smem_u32(smem);
+      // ---------------- S = Q K^T ----------------
+      constexpr uint32_t idesc_s = make_idesc_bf16(kQTile, kKeyPad, 0);
+      mbar_wait(&bars->qk_full, 0);
+      tc_fence_after();
+      uint32_t accum = 0;
+      const int nterms = split ? 3 : 1;
+      for (int term = 0; term < nterms; ++term) {
+        // split order: Q_lo*K_hi, Q_hi*K_lo, Q_hi*K_hi ; fast mode: Q_hi*K_hi
+        const uint32_t qo = (split && term == 0) ? kOffQLo : kOffQHi;
+        const uint32_t ko = (split && term == 1) ? kOffKLo : kOffKHi;
+        for (int j = 0; j < 2; ++j) {
+          const uint64_t da = make_desc_kmajor_sw128(sbase + qo + j * kQBlockBytes);
+          const uint64_t db = make_desc_kmajor_sw128(sbase + ko + j * kKVBlockBytes);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            umma_ss(tmem_base + kColS, desc_advance(da, kk * 32), desc_advance(db, kk * 32), idesc_s, accum);
+            accum = 1;
+          }
+        }
+      }
+      umma_commit(&bars->s_full);
+      // ---------------- O = P V ----------------
+      constexpr uint32_t idesc_o = make_idesc_bf16(kQTile, kHeadDim, 1);
+      mbar_wait(&bars->p_full, 0);
+      mbar_wait(&bars->vhi_full, 0);
+      tc_fence_after();
+      const uint64_t dv_hi = make_desc_mnmajor_sw128(sbase + kOffVHi, kKVBlockBytes);
+      accum = 0;
+      if (split) {
+#pragma unroll 1
+        for (int ks = 0; ks < kKeyPad / 16; ++ks) {
+          umma_ts(tmem_base + kColO, tmem_base + kColPLo + ks * 8, desc_advance(dv_hi, ks * 2048), idesc_o, accum);
+          accum = 1;
+        }
+      }
+#pragma unroll 1
+      for (int ks = 0; ks < kKeyPad / 16; ++ks) {
+        umma_ts(tmem_base + kColO, tmem_base + kColPHi + ks * 8, desc_advance(dv_hi, ks * 2048), idesc_o, accum);
+        accum = 1;
+      }
+      if (split) {
+        mbar_wait(&bars->vlo_full, 0);
+        tc_fence_after();
+        const uint64_t dv_lo = make_desc_mnmajor_sw128(sbase + kOffVLo, kKVBlockBytes);
+#pragma unroll 1
+        for (int ks = 0; ks < kKeyPad / 16; ++ks)
+          umma_ts(tmem_base + kColO, tmem_base + kColPHi + ks * 8, desc_advance(dv_lo, ks * 2048), idesc_o, 1u);
+      }
+      umma_commit(&bars->o_full);
+    }
+    __syncwarp();
+  } else {
+    // ---------------- softmax (thread = query row) ----------------
+    const int lane_group = warp_idx & 3;
+    const int row = lane_group * 32 + lane;
+    const int qpos = qtile * kQTile + row;
+    const uint32_t trow = tmem_base + ((uint32_t)(lane_group * 32) << 16);
+    const float c_scale = 0.08838834764831845f * 1.4426950408889634f;  // 1/sqrt(128) * log2(e)
+
+    mbar_wait(&bars->s_full, 0);
+    tc_fence_after();
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < kKeyPad / 16; ++c) {
+      uint32_t v[16];
+      tmem_ld16(trow + kColS + c * 16, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (c * 16 + j < S) mx = fmaxf(mx, __uint_as_float(v[j]));
+    }
+    const float mc = mx * c_scale;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < kKeyPad / 16; ++c) {
+      uint32_t v[16];
+      tmem_ld16(trow + kColS + c * 16, v);
+      tmem_ld_wait();
+      uint32_t ph[8], pl[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = c * 16 + j * 2;
+        const float p0 = (col < S) ? exp2f(fmaf(__uint_as_float(v[j * 2]), c_scale, -mc)) : 0.f;
+        const float p1 = (col + 1 < S) ? exp2f(fmaf(__uint_as_float(v[j * 2 + 1]), c_scale, -mc)) : 0.f;
+        sum += p0 + p1;
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(p0, h0, l0);
+        split_bf16(p1, h1, l1);
+        ph[j] = pack_bf16x2(h0, h1);
+        pl[j] = pack_bf16x2(l0, l1);
+      }
+      // P_hi aliases S: columns [8c, 8c+8) were consumed in iterations <= c
+      tmem_st8(trow + kColPHi + c * 8, ph);
+      if (split) tmem_st8(trow + kColPLo + c * 8, pl);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(&bars->p_full);
+
+    // ---------------- output ----------------
+    mbar_wait(&bars->o_full, 0);
+    tc_fence_after();
+    const float inv = 1.0f / sum;
+    const bool valid = qpos < S;
+    const size_t orow = (size_t)(row0 + qpos) * p.ld_out + head * kHeadDim;
+#pragma unroll 1
+    for (int c = 0; c < kHeadDim / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(trow + kColO + c * 32, v);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(__uint_as_float(v[g * 8 + q * 2]) * inv, h0, l0);
+            split_bf16(__uint_as_float(v[g * 8 + q * 2 + 1]) * inv, h1, l1);
+            hw[q] = pack_bf16x2(h0, h1);
+            lw[q] = pack_bf16x2(l0, l1);
+          }
+          st_global_v4(p.out_hi + orow + c * 32 + g * 8, hw[0], hw[1], hw[2], hw[3]);
+          if (p.nsplit_out == 3) st_global_v4(p.out_lo + orow + c * 32 + g * 8, lw[0], lw[1], lw[2], lw[3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_attention(const CUtensorMap& q_hi, const CUtensorMap& q_lo, const CUtensorMap& kv_hi,
+                             const CUtensorMap& kv_lo, const AttnParams& p, cudaStream_t stream) {
+  if (p.seq_len > kKeyPad || p.seq_len < 1 || (p.nsplit != 1 && p.nsplit != 3)) {
+    set_last_error("launch_attention: unsupported seq_len=%d nsplit=%d", p.seq_len, p.nsplit);
+    return cudaErrorInvalidValue;
+  }
+  const size_t smem = 1024 + kSmemTiles + sizeof(AttnBarriers);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((p.seq_len + kQTile - 1) / kQTile, p.num_heads, p.num_seqs);
+  attention_kernel<<<grid, kThreads, smem, stream>>>(q_hi, q_lo, kv_hi, kv_lo, p);
+  return cudaGetLastError();
+}
+
+}  // namespace cmdi

@@ -1,0 +1,125 @@
+// Kernel-level C-ABI entry points used by the parity tests (declared in include/condmdi_b200.h).
+// They stage fp32 inputs into the bf16 hi/lo planes the kernels consume, build the TMA descriptors,
+// launch the production kernel and hand back fp32 results.
+#include <cstring>
+#include <vector>
+
+#include "../../include/condmdi_b200.h"
+#include "kernels.h"
+
+using namespace cmdi;
+
+namespace {
+
+#define CK(expr)                                                                   \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return 1;                                                                    \
+    }                                                                              \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) {
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) e = cudaMemset(p, 0, bytes);
+    return e;
+  }
+  template <class T>
+  T* as() {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+int num_sms_of_current_device() {
+  int dev = 0, n = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+
+}  // namespace
+
+extern "C" int cmdi_test_linear(const float* A, const float* W, const float* bias, const float* residual, float* C, int M,
+                                int N, int K, int act, int precision, int block_n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int Kp = round_up(K, 8), Mp = round_up(M, 128), Np = round_up(N, block_n);
+  DevBuf a_hi, a_lo, w_hi, w_lo;
+  CK(a_hi.alloc((size_t)Mp * Kp * 2));
+  CK(a_lo.alloc((size_t)Mp * Kp * 2));
+  CK(w_hi.alloc((size_t)Np * Kp * 2));
+  CK(w_lo.alloc((size_t)Np * Kp * 2));
+  CK(launch_split_planes(A, M, K, K, a_hi.as<__nv_bfloat16>(), a_lo.as<__nv_bfloat16>(), Kp, stream));
+  CK(launch_split_planes(W, N, K, K, w_hi.as<__nv_bfloat16>(), w_lo.as<__nv_bfloat16>(), Kp, stream));
+  CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+  if (make_tmap_bf16_2d(&ma_hi, a_hi.p, Mp, Kp, Kp, 64, 128)) return 1;
+  if (make_tmap_bf16_2d(&ma_lo, a_lo.p, Mp, Kp, Kp, 64, 128)) return 1;
+  if (make_tmap_bf16_2d(&mw_hi, w_hi.p, Np, Kp, Kp, 64, block_n)) return 1;
+  if (make_tmap_bf16_2d(&mw_lo, w_lo.p, Np, Kp, Kp, 64, block_n)) return 1;
+  LinearParams p{};
+  p.M = M; p.N = N; p.K = K; p.nsplit = precision;
+  p.bias = bias; p.residual = residual; p.ld_res = N;
+  p.act = act; p.rowmap = ROWMAP_IDENTITY;
+  p.out_f32 = C; p.ld_f32 = N;
+  p.nsplit_out = precision;
+  CK(launch_linear(ma_hi, ma_lo, mw_hi, mw_lo, p, block_n, num_sms_of_current_device(), stream));
+  CK(cudaStreamSynchronize(stream));  // staging buffers are freed on return
+  return 0;
+}
+
+extern "C" int cmdi_test_layernorm(const float* v, const float* gamma, const float* beta, float* out, int rows,
+                                   void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CK(launch_layernorm512(v, gamma, beta, 1e-5f, rows, out, nullptr, nullptr, stream));
+  return 0;
+}
+
+extern "C" int cmdi_test_attention(const float* qkv, float* O, int num_seqs, int S, int H, int precision, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (S > kAttnKeyPad) {
+    set_last_error("cmdi_test_attention: S=%d exceeds %d", S, kAttnKeyPad);
+    return 1;
+  }
+  const int rows = num_seqs * S;
+  const int rows_p = round_up(rows, 128) + 256;  // tiles of the last sequence read past its end
+  const int ld = 3 * H * 128, ldo = H * 128;
+  DevBuf q_hi, q_lo, o_hi, o_lo;
+  CK(q_hi.alloc((size_t)rows_p * ld * 2));
+  CK(q_lo.alloc((size_t)rows_p * ld * 2));
+  CK(o_hi.alloc((size_t)rows_p * ldo * 2));
+  CK(o_lo.alloc((size_t)rows_p * ldo * 2));
+  CK(launch_split_planes(qkv, rows, ld, ld, q_hi.as<__nv_bfloat16>(), q_lo.as<__nv_bfloat16>(), ld, stream));
+  CUtensorMap mq_hi, mq_lo, mkv_hi, mkv_lo;
+  if (make_tmap_bf16_2d(&mq_hi, q_hi.p, rows_p, ld, ld, 64, 128)) return 1;
+  if (make_tmap_bf16_2d(&mq_lo, q_lo.p, rows_p, ld, ld, 64, 128)) return 1;
+  if (make_tmap_bf16_2d(&mkv_hi, q_hi.p, rows_p, ld, ld, 64, kAttnKeyPad)) return 1;
+  if (make_tmap_bf16_2d(&mkv_lo, q_lo.p, rows_p, ld, ld, 64, kAttnKeyPad)) return 1;
+  AttnParams p{};
+  p.num_seqs = num_seqs; p.seq_len = S; p.num_heads = H; p.nsplit = precision; p.nsplit_out = 3;
+  p.out_hi = o_hi.as<__nv_bfloat16>(); p.out_lo = o_lo.as<__nv_bfloat16>(); p.ld_out = ldo;
+  CK(launch_attention(mq_hi, mq_lo, mkv_hi, mkv_lo, p, stream));
+  // O = hi + lo (fp32) for the test
+  {
+    std::vector<uint16_t> hh((size_t)rows * ldo), hl((size_t)rows * ldo);
+    std::vector<float> ho((size_t)rows * ldo);
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaMemcpy(hh.data(), o_hi.p, hh.size() * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hl.data(), o_lo.p, hl.size() * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < ho.size(); ++i) {
+      uint32_t a = (uint32_t)hh[i] << 16, b = (uint32_t)hl[i] << 16;
+      float fa, fb;
+      memcpy(&fa, &a, 4);
+      memcpy(&fb, &b, 4);
+      ho[i] = fa + fb;
+    }
+    CK(cudaMemcpy(O, ho.data(), ho.size() * 4, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}

@@ -1,0 +1,436 @@
+// Row-wise and elementwise kernels of the sampling path (HBM/L2-bound; coalesced, vectorised).
+//
+//   layernorm512           nn.TransformerEncoderLayer norm1/norm2 (post-norm)      mdm.py:107-114
+//   token_rows             timestep(+text) token + PE[0]                           mdm.py:245-251,279-280
+//   small_linear           TimestepEmbedder MLP / embed_text, once per loop        mdm.py:345-353,248-251
+//   diffusion_step         p_mean_variance tail + p_sample / ddim_sample           gaussian_diffusion.py:352-534,656-713,1358-1416
+//                          + ClassifierFreeSampleModel combine                     cfg_sampler.py:25-35
+//                          + keyframe imputation blend                             gaussian_diffusion.py:427-435
+//   layout converters      reference [B,D,1,L] <-> frame-major [B*L, D_pad]
+//
+// The step kernel uses explicit non-contracted fp32 intrinsics (__fmul_rn/__fadd_rn) in the
+// reference's operation order so that, given the same denoiser output, it is bit-identical to
+// the PyTorch CPU reference.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cmdi {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over rows of 512 fp32: one warp per row, 16 values per lane (4 x float4, coalesced)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restrict__ v, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps, int rows,
+                                                           float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
+                                                           __nv_bfloat16* __restrict__ out_lo) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* src = reinterpret_cast<const float4*>(v + (size_t)row * 512);
+  float4 x[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = src[i * 32 + lane];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+  const float mean = warp_sum(s) * (1.0f / 512.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / 512.0f) + eps);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + col));
+    float4 y;
+    y.x = (x[i].x - mean) * rstd * g.x + bb.x;
+    y.y = (x[i].y - mean) * rstd * g.y + bb.y;
+    y.z = (x[i].z - mean) * rstd * g.z + bb.z;
+    y.w = (x[i].w - mean) * rstd * g.w + bb.w;
+    if (out_f32) reinterpret_cast<float4*>(out_f32 + (size_t)row * 512)[i * 32 + lane] = y;
+    if (out_hi) {
+      __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+      split_bf16(y.x, h0, l0); split_bf16(y.y, h1, l1); split_bf16(y.z, h2, l2); split_bf16(y.w, h3, l3);
+      uint2 hw = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+      *reinterpret_cast<uint2*>(out_hi + (size_t)row * 512 + col) = hw;
+      if (out_lo) {
+        uint2 lw = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+        *reinterpret_cast<uint2*>(out_lo + (size_t)row * 512 + col) = lw;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 linear on CUDA cores: one warp per output element, K split across lanes
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ in, const float* __restrict__ W,
+                                                           const float* __restrict__ bias, float* __restrict__ out, int rows,
+                                                           int N, int K, int act) {
+  const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= (long long)rows * N) return;
+  const int r = (int)(w / N), n = (int)(w % N);
+  const float* a = in + (size_t)r * K;
+  const float* b = W + (size_t)n * K;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s = fmaf(a[k], b[k], s);
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (bias) s += bias[n];
+    if (act == 2) s = s / (1.0f + expf(-s));  // SiLU
+    out[(size_t)r * N + n] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conditioning token rows
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) token_rows_kernel(const TokenParams p) {
+  const int seq = blockIdx.x;
+  const int t = *p.step_ptr;
+  const int col = threadIdx.x * 4;
+  float4 e = *reinterpret_cast<const float4*>(p.temb_table + (size_t)t * 512 + col);
+  if (p.cond_proj) {
+    // emb += embed_text(mask_cond(enc_text))   (mdm.py:250; uncond -> embed_text(0) = bias)
+    const float* c = (seq < p.n_cond_seqs) ? p.cond_proj + (size_t)seq * 512 : p.uncond_proj;
+    const float4 cv = *reinterpret_cast<const float4*>(c + col);
+    e.x += cv.x; e.y += cv.y; e.z += cv.z; e.w += cv.w;
+  }
+  const float4 pe = *reinterpret_cast<const float4*>(p.pe0 + col);
+  e.x += pe.x; e.y += pe.y; e.z += pe.z; e.w += pe.w;
+  const size_t row = (size_t)seq * p.seq_len;
+  *reinterpret_cast<float4*>(p.x_f32 + row * 512 + col) = e;
+  __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+  split_bf16(e.x, h0, l0); split_bf16(e.y, h1, l1); split_bf16(e.z, h2, l2); split_bf16(e.w, h3, l3);
+  *reinterpret_cast<uint2*>(p.x_hi + row * 512 + col) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+  if (p.x_lo) *reinterpret_cast<uint2*>(p.x_lo + row * 512 + col) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011) + Box-Muller: counter = (element index / 4, sample, stream, 0)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// standard normal for flat element index `idx` of sample `sample` on stream `stream_id`
+__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned long long stream_id,
+                                               unsigned long long sample, unsigned long long idx) {
+  const uint4 ctr = make_uint4((uint32_t)(idx >> 2), (uint32_t)sample, (uint32_t)stream_id,
+                               (uint32_t)((idx >> 34) | ((sample >> 32) << 8) | ((stream_id >> 32) << 20)));
+  const uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const int lane = (int)(idx & 3);
+  const uint32_t a = (lane & 2) ? r.z : r.x;
+  const uint32_t b = (lane & 2) ? r.w : r.y;
+  const float rad = sqrtf(-2.0f * logf(u01(a)));
+  float sn, cs;
+  sincospif(2.0f * u01(b), &sn, &cs);
+  return rad * ((lane & 1) ? sn : cs);
+}
+
+__global__ void fill_normal_ref_kernel(float* out, int B, size_t per_sample, unsigned long long seed,
+                                       unsigned long long stream_id, unsigned long long sample_offset) {
+  const size_t total = (size_t)B * per_sample;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / per_sample, e = i - b * per_sample;
+    out[i] = philox_normal(seed, stream_id, sample_offset + b, e);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// diffusion step. grid: (ceil(L/32), ceil(D_pad/32), B); block 32x8. Each block owns a 32(l) x 32(c)
+// tile: frame-major operands are read/written with c fastest, the reference-layout noise tape with
+// l fastest, through a padded smem tile.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) diffusion_step_kernel(const StepParams p) {
+  __shared__ float s_noise[32][33];
+  const int b = blockIdx.z;
+  const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int t = *p.step_ptr;
+
+  // ---- noise tile (reference layout [b][c][l], l contiguous) ----
+  const bool want_noise = true;  // the reference draws noise at every step, including t == 0
+  if (want_noise) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + ty + i * 8, l = l0 + tx;
+      float nz = 0.f;
+      if (c < p.D && l < p.L) {
+        const size_t e = (size_t)c * p.L + l;
+        nz = p.noise_ref ? p.noise_ref[(size_t)b * p.D * p.L + e]
+                         : philox_normal(p.seed, (unsigned long long)(t + 1), p.sample_offset + b, e);
+      }
+      s_noise[ty + i * 8][tx] = nz;
+    }
+  }
+  __syncthreads();
+
+  // ---- per-step scalars (fp32, gathered exactly like _extract_into_tensor(...).float()) ----
+  const float coef1 = p.tab.post_coef1[t], coef2 = p.tab.post_coef2[t];
+  const float logvar = p.tab.post_logvar[t];
+  const float nonzero = (t != 0) ? 1.0f : 0.0f;
+  const float text_scale = p.cfg ? p.text_scale[b] : 0.f;
+  const bool do_impute = p.impute && (t >= p.stop_imputation_at);
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int l = l0 + ty + i * 8, c = c0 + tx;
+    if (l >= p.L || c >= p.D_pad) continue;
+    const size_t idx = ((size_t)b * p.L + l) * p.D_pad + c;
+    float xn = 0.f, x0 = 0.f;
+    if (c < p.D) {
+      // model output (+ classifier-free guidance: out_uncond + scale * (out - out_uncond), cfg_sampler.py:35)
+      float out = p.model_out[idx];
+      if (p.cfg) {
+        const float u = p.model_out[idx + (size_t)p.B * p.L * p.D_pad];
+        out = __fadd_rn(u, __fmul_rn(text_scale, __fsub_rn(out, u)));
+      }
+      // imputation: (hat_x * ~M) + (x_obs * M)   (gaussian_diffusion.py:435)
+      if (do_impute) {
+        const float m = p.obs_mask[idx] ? 1.0f : 0.0f;
+        out = __fadd_rn(__fmul_rn(out, 1.0f - m), __fmul_rn(p.x_obs[idx], m));
+      }
+      x0 = out;  // START_X, no clipping (:513-515)
+      const float xt = p.x_t[idx];
+      const float noise = s_noise[tx][ty + i * 8];
+      if (p.sampler == 0) {
+        // mean = coef1*x0 + coef2*x_t (:338-342); sample = mean + nonzero*exp(0.5*logvar)*noise (:710-711)
+        const float mean = __fadd_rn(__fmul_rn(coef1, x0), __fmul_rn(coef2, xt));
+        const float sd = expf(__fmul_rn(0.5f, logvar));
+        xn = __fadd_rn(mean, __fmul_rn(__fmul_rn(nonzero, sd), noise));
+      } else {
+        // ddim_sample_with_grad (:1397-1412)
+        const float r1 = p.tab.sqrt_recip_acp[t], r2 = p.tab.sqrt_recipm1_acp[t];
+        const float ab = p.tab.acp[t], abp = p.tab.acp_prev[t];
+        const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(r1, xt), x0), r2);
+        const float sigma = __fmul_rn(__fmul_rn(p.eta, sqrtf(__fdiv_rn(1.0f - abp, 1.0f - ab))),
+                                      sqrtf(__fsub_rn(1.0f, __fdiv_rn(ab, abp))));
+        const float mean_pred = __fadd_rn(__fmul_rn(x0, sqrtf(abp)),
+                                          __fmul_rn(sqrtf(__fsub_rn(__fsub_rn(1.0f, abp), __fmul_rn(sigma, sigma))), eps));
+        xn = __fadd_rn(mean_pred, __fmul_rn(__fmul_rn(nonzero, sigma), noise));
+      }
+    }
+    p.x_next[idx] = xn;
+    __nv_bfloat16 h, lo;
+    split_bf16(xn, h, lo);
+    p.x_next_hi[idx] = h;
+    if (p.x_next_lo) p.x_next_lo[idx] = lo;
+    if (p.pred_xstart) p.pred_xstart[idx] = x0;
+  }
+
+  // ---- advance the device-side step counter once every block has read it ----
+  if (p.advance) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (tx == 0 && ty == 0) {
+      const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+      unsigned int* counter = reinterpret_cast<unsigned int*>(p.step_ptr + 1);
+      const unsigned int prev = atomicAdd(counter, 1u);
+      is_last = (prev == total - 1);
+      if (is_last) {
+        *counter = 0;
+        *p.step_ptr = t - 1;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout converters (32x32 smem tile transposes)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ref_to_frames_kernel(const float* __restrict__ ref, int B, int D, int L, int D_pad,
+                                                            float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
+                                                            __nv_bfloat16* __restrict__ out_lo) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + i * 8, l = l0 + tx;
+    tile[ty + i * 8][tx] = (c < D && l < L) ? ref[((size_t)b * D + c) * L + l] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int l = l0 + ty + i * 8, c = c0 + tx;
+    if (l >= L || c >= D_pad) continue;
+    const float v = tile[tx][ty + i * 8];
+    const size_t idx = ((size_t)b * L + l) * D_pad + c;
+    if (out_f32) out_f32[idx] = v;
+    if (out_hi) {
+      __nv_bfloat16 h, lo;
+      split_bf16(v, h, lo);
+      out_hi[idx] = h;
+      if (out_lo) out_lo[idx] = lo;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) frames_to_ref_kernel(const float* __restrict__ frames, int B, int D, int L, int D_pad,
+                                                            float* __restrict__ ref) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int l = l0 + ty + i * 8, c = c0 + tx;
+    tile[ty + i * 8][tx] = (l < L && c < D) ? frames[((size_t)b * L + l) * D_pad + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + i * 8, l = l0 + tx;
+    if (c < D && l < L) ref[((size_t)b * D + c) * L + l] = tile[tx][ty + i * 8];
+  }
+}
+
+__global__ void __launch_bounds__(256) mask_to_frames_kernel(const uint8_t* __restrict__ ref_mask,
+                                                             const uint8_t* __restrict__ y_mask, int B, int D, int L,
+                                                             int D_pad, uint8_t* __restrict__ out) {
+  __shared__ uint8_t tile[32][33];
+  const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + i * 8, l = l0 + tx;
+    uint8_t m = 0;
+    if (c < D && l < L) {
+      // (inpainting_mask * y.mask.float()).bool()   (gaussian_diffusion.py:406-409, :432-433)
+      m = ref_mask[((size_t)b * D + c) * L + l] != 0;
+      if (y_mask) m = m && (y_mask[(size_t)b * L + l] != 0);
+    }
+    tile[ty + i * 8][tx] = m;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int l = l0 + ty + i * 8, c = c0 + tx;
+    if (l < L && c < D_pad) out[((size_t)b * L + l) * D_pad + c] = tile[tx][ty + i * 8];
+  }
+}
+
+__global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float a, float b, float* __restrict__ out,
+                             size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __fadd_rn(__fmul_rn(a, x[i]), __fmul_rn(b, y[i]));
+}
+
+__global__ void set_int_kernel(int* p, int v) {
+  p[0] = v;
+  p[1] = 0;  // block-arrival counter used by diffusion_step_kernel
+}
+
+__global__ void split_planes_kernel(const float* __restrict__ in, int rows, int cols, int ld_in, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, int ld_out) {
+  const size_t total = (size_t)rows * ld_out;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / ld_out;
+    const int c = (int)(i - r * ld_out);
+    const float v = (c < cols) ? in[r * ld_in + c] : 0.f;
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+inline int grid_for(size_t n, int block) {
+  size_t g = (n + block - 1) / block;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+cudaError_t launch_layernorm512(const float* v, const float* gamma, const float* beta, float eps, int rows, float* out_f32,
+                                __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream) {
+  layernorm512_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(v, gamma, beta, eps, rows, out_f32, out_hi, out_lo);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_small_linear(const float* in, const float* W, const float* bias, float* out, int rows, int N, int K,
+                                int act, cudaStream_t stream) {
+  const long long warps = (long long)rows * N;
+  small_linear_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(in, W, bias, out, rows, N, K, act);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_token_rows(const TokenParams& p, cudaStream_t stream) {
+  token_rows_kernel<<<p.num_seqs, 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_diffusion_step(const StepParams& p, cudaStream_t stream) {
+  dim3 grid((p.L + 31) / 32, (p.D_pad + 31) / 32, p.B), block(32, 8);
+  diffusion_step_kernel<<<grid, block, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ref_to_frames(const float* ref, int B, int D, int L, int D_pad, float* out_f32, __nv_bfloat16* out_hi,
+                                 __nv_bfloat16* out_lo, cudaStream_t stream) {
+  dim3 grid((L + 31) / 32, (D_pad + 31) / 32, B), block(32, 8);
+  ref_to_frames_kernel<<<grid, block, 0, stream>>>(ref, B, D, L, D_pad, out_f32, out_hi, out_lo);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_frames_to_ref(const float* frames, int B, int D, int L, int D_pad, float* ref, cudaStream_t stream) {
+  dim3 grid((L + 31) / 32, (D + 31) / 32, B), block(32, 8);
+  frames_to_ref_kernel<<<grid, block, 0, stream>>>(frames, B, D, L, D_pad, ref);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mask_to_frames(const uint8_t* ref_mask, const uint8_t* y_mask, int B, int D, int L, int D_pad, uint8_t* out,
+                                  cudaStream_t stream) {
+  dim3 grid((L + 31) / 32, (D_pad + 31) / 32, B), block(32, 8);
+  mask_to_frames_kernel<<<grid, block, 0, stream>>>(ref_mask, y_mask, B, D, L, D_pad, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_axpby(const float* x, const float* y, float a, float b, float* out, size_t n, cudaStream_t stream) {
+  axpby_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, y, a, b, out, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill_normal_ref(float* out, int B, size_t per_sample, unsigned long long seed, unsigned long long stream_id,
+                                   unsigned long long sample_offset, cudaStream_t stream) {
+  fill_normal_ref_kernel<<<grid_for((size_t)B * per_sample, 256), 256, 0, stream>>>(out, B, per_sample, seed, stream_id,
+                                                                                  sample_offset);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_set_int(int* p, int v, cudaStream_t stream) {
+  set_int_kernel<<<1, 1, 0, stream>>>(p, v);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_split_planes(const float* in, int rows, int cols, int ld_in, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                                int ld_out, cudaStream_t stream) {
+  split_planes_kernel<<<grid_for((size_t)rows * ld_out, 256), 256, 0, stream>>>(in, rows, cols, ld_in, hi, lo, ld_out);
+  return cudaGetLastError();
+}
+
+}  // namespace cmdi

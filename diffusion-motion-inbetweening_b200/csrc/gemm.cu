@@ -1,0 +1,328 @@
+// Linear layers of the MDM denoiser on tcgen05 tensor cores (sm_100a).
+//
+//   C[M,N] = epilogue( A[M,K] * W[N,K]^T )
+//
+// covers, per denoiser pass (reference: model/mdm.py):
+//   frame embed   InputProcess.poseEmbedding      mdm.py:362,368-371   (+ positional encoding :332-335)
+//   QKV / out-proj of nn.MultiheadAttention       mdm.py:107-114
+//   FFN linear1 (+ exact GELU) / linear2          mdm.py:107-114
+//   output head   OutputProcess.poseFinal         mdm.py:405,412
+//
+// Numerics. The reference is fp32 end to end and the parity gate is rtol 1e-3 / atol 1e-4, which
+// plain bf16 (or tf32) operands do not meet.  Operands are therefore kept as
+// two bf16 planes (hi = bf16(v), lo = bf16(v - hi)) and a product is accumulated in fp32 TMEM as
+//   A_hi*W_hi + A_hi*W_lo + A_lo*W_hi            (nsplit = 3, error ~2^-17 per product)
+// or just A_hi*W_hi (nsplit = 1, "fast" mode).  All three terms hit the same accumulator, so the
+// split costs tensor-pipe time only; the A/W tiles are fetched once per k-block.
+//
+// Structure: persistent CTAs (one per SM), warp-specialised:
+//   warp 0      TMA producer   (one lane)  : global -> 128B-swizzled smem ring, mbarrier expect_tx
+//   warp 1      MMA issuer     (one lane)  : tcgen05.mma kind::f16, M=128, N=BLOCK_N, K=16 per instruction
+//   warps 2..9  epilogue                   : tcgen05.ld -> bias / PE / residual / GELU -> fp32 + bf16 planes
+// The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps
+// the MMAs of tile i+1.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cmdi {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kNumEpiWarps = 8;
+constexpr int kNumThreads = 64 + kNumEpiWarps * 32;
+constexpr int kMaxStages = 8;
+constexpr int kSmemLimit = 232448;  // 227 KB
+constexpr int kABytes = kBlockM * kBlockK * 2;
+
+struct __align__(8) PipeBarriers {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kNumThreads, 1)
+linear_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+              const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+              const LinearParams p, const int num_stages, const int num_m_blocks, const int num_n_blocks) {
+  constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // 256 or 512 (power of two)
+  static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int nplanes = (p.nsplit == 3) ? 2 : 1;
+  const uint32_t stage_bytes = nplanes * (kABytes + kBBytes);
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + (size_t)num_stages * stage_bytes);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = num_m_blocks * num_n_blocks;
+  const int num_k_blocks = (p.K + kBlockK - 1) / kBlockK;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_w_hi);
+    if (nplanes == 2) {
+      tma_prefetch_desc(&map_a_lo);
+      tma_prefetch_desc(&map_w_lo);
+    }
+    for (int s = 0; s < num_stages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->tmem_full[s], 1);
+      mbar_init(&bars->tmem_empty[s], kNumEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    tmem_alloc(&bars->tmem_base, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp_idx == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n_blocks;
+        const int n_blk = tile % num_n_blocks;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          uint8_t* sb = sa + nplanes * kABytes;
+          mbar_arrive_expect_tx(&bars->full[stage], stage_bytes);
+          tma_load_2d(sa, &map_a_hi, &bars->full[stage], kb * kBlockK, m_blk * kBlockM);
+          tma_load_2d(sb, &map_w_hi, &bars->full[stage], kb * kBlockK, n_blk * BLOCK_N);
+          if (nplanes == 2) {
+            tma_load_2d(sa + kABytes, &map_a_lo, &bars->full[stage], kb * kBlockK, m_blk * kBlockM);
+            tma_load_2d(sb + kBBytes, &map_w_lo, &bars->full[stage], kb * kBlockK, n_blk * BLOCK_N);
+          }
+          if (++stage == num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx == 1) {
+    // ====================================== MMA issuer ======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + nplanes * kABytes;
+          const uint64_t da_hi = make_desc_kmajor_sw128(sa);
+          const uint64_t db_hi = make_desc_kmajor_sw128(sb);
+          if (nplanes == 2) {
+            const uint64_t da_lo = make_desc_kmajor_sw128(sa + kABytes);
+            const uint64_t db_lo = make_desc_kmajor_sw128(sb + kBBytes);
+            // small cross terms first, the dominant hi*hi term last
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_ss(d_tmem, desc_advance(da_lo, k * kUmmaK * 2), desc_advance(db_hi, k * kUmmaK * 2), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_ss(d_tmem, desc_advance(da_hi, k * kUmmaK * 2), desc_advance(db_lo, k * kUmmaK * 2), idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_ss(d_tmem, desc_advance(da_hi, k * kUmmaK * 2), desc_advance(db_hi, k * kUmmaK * 2), idesc, 1u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_ss(d_tmem, desc_advance(da_hi, k * kUmmaK * 2), desc_advance(db_hi, k * kUmmaK * 2), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&bars->empty[stage]);  // smem slot is free once these MMAs have read it
+          if (++stage == num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================================= epilogue =======================================
+    const int epi = warp_idx - 2;
+    const int lane_group = warp_idx & 3;  // TMEM lanes this warp may touch: 32*lane_group ..
+    const int col_part = epi >> 2;        // which half of the tile's columns
+    constexpr int kColsPerPart = BLOCK_N / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n_blocks;
+      const int n_blk = tile % num_n_blocks;
+      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      tc_fence_after();
+
+      const int a_row = m_blk * kBlockM + lane_group * 32 + lane;
+      bool valid = a_row < p.M;
+      long long out_row = a_row;
+      int pos = 0;  // sequence position for the positional-encoding add
+      if (p.rowmap == ROWMAP_FRAMES_TO_SEQ) {
+        const int b = a_row / p.frames;
+        const int l = a_row - b * p.frames;
+        out_row = (long long)b * (p.frames + 1) + l + 1;
+        pos = l + 1;
+      } else if (p.rowmap == ROWMAP_SEQ_TO_FRAMES) {
+        const int S = p.frames + 1;
+        const int b = a_row / S;
+        const int s = a_row - b * S;
+        valid = valid && (s > 0);
+        out_row = (long long)b * p.frames + (s - 1);
+      }
+
+#pragma unroll 1
+      for (int c = 0; c < kColsPerPart / 32; ++c) {
+        const int col_in_tile = col_part * kColsPerPart + c * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem_addr(tmem_base, lane_group * 32, acc * BLOCK_N + col_in_tile), v);
+        tmem_ld_wait();
+        const int n0 = n_blk * BLOCK_N + col_in_tile;
+        if (valid && n0 < p.N) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int n = n0 + g * 4;
+            if (n < p.N) {
+              if (p.bias) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                f[g * 4 + 0] += bv.x; f[g * 4 + 1] += bv.y; f[g * 4 + 2] += bv.z; f[g * 4 + 3] += bv.w;
+              }
+              if (p.pos_enc) {
+                const float4 pv = __ldg(reinterpret_cast<const float4*>(p.pos_enc + (size_t)pos * p.N + n));
+                f[g * 4 + 0] += pv.x; f[g * 4 + 1] += pv.y; f[g * 4 + 2] += pv.z; f[g * 4 + 3] += pv.w;
+              }
+              if (p.residual) {
+                const float4 rv = *reinterpret_cast<const float4*>(p.residual + (size_t)out_row * p.ld_res + n);
+                f[g * 4 + 0] += rv.x; f[g * 4 + 1] += rv.y; f[g * 4 + 2] += rv.z; f[g * 4 + 3] += rv.w;
+              }
+              if (p.act == 1) {
+                f[g * 4 + 0] = gelu_erf(f[g * 4 + 0]); f[g * 4 + 1] = gelu_erf(f[g * 4 + 1]);
+                f[g * 4 + 2] = gelu_erf(f[g * 4 + 2]); f[g * 4 + 3] = gelu_erf(f[g * 4 + 3]);
+              }
+            }
+          }
+          const int ncopies = (p.dup_row_offset > 0) ? 2 : 1;
+          for (int cp = 0; cp < ncopies; ++cp) {
+            const long long orow = out_row + (long long)cp * p.dup_row_offset;
+            if (p.out_f32) {
+              float* dst = p.out_f32 + (size_t)orow * p.ld_f32 + n0;
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                if (n0 + g * 4 < p.N) st_global_v4f(dst + g * 4, f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+            }
+            if (p.out_hi) {
+              __nv_bfloat16* dh = p.out_hi + (size_t)orow * p.ld_bf + n0;
+              __nv_bfloat16* dl = (p.nsplit_out == 3) ? p.out_lo + (size_t)orow * p.ld_bf + n0 : nullptr;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (n0 + g * 8 < p.N) {
+                  uint32_t hw[4], lw[4];
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    split_bf16(f[g * 8 + q * 2], h0, l0);
+                    split_bf16(f[g * 8 + q * 2 + 1], h1, l1);
+                    hw[q] = pack_bf16x2(h0, h1);
+                    lw[q] = pack_bf16x2(l0, l1);
+                  }
+                  st_global_v4(dh + g * 8, hw[0], hw[1], hw[2], hw[3]);
+                  if (dl) st_global_v4(dl + g * 8, lw[0], lw[1], lw[2], lw[3]);
+                }
+              }
+            }
+          }
+        }
+      }
+      // accumulator buffer drained -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int BLOCK_N>
+cudaError_t launch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                        const CUtensorMap& w_lo, const LinearParams& p, int num_sms, cudaStream_t stream) {
+  constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  const int nplanes = (p.nsplit == 3) ? 2 : 1;
+  const int stage_bytes = nplanes * (kABytes + kBBytes);
+  int num_stages = (kSmemLimit - 1024 - (int)sizeof(PipeBarriers)) / stage_bytes;
+  if (num_stages > kMaxStages) num_stages = kMaxStages;
+  const size_t smem = 1024 + (size_t)num_stages * stage_bytes + sizeof(PipeBarriers);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(linear_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int num_m_blocks = (p.M + kBlockM - 1) / kBlockM;
+  const int num_n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m_blocks * num_n_blocks;
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  linear_kernel<BLOCK_N><<<grid, kNumThreads, smem, stream>>>(a_hi, a_lo, w_hi, w_lo, p, num_stages, num_m_blocks,
+                                                            num_n_blocks);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_linear(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                          const CUtensorMap& w_lo, const LinearParams& p, int block_n, int num_sms,
+                          cudaStream_t stream) {
+  if (p.N % 8 != 0 || (p.nsplit != 1 && p.nsplit != 3)) {
+    set_last_error("launch_linear: N must be a multiple of 8 and nsplit 1 or 3 (N=%d nsplit=%d)", p.N, p.nsplit);
+    return cudaErrorInvalidValue;
+  }
+  if (block_n == 256) return launch_impl<256>(a_hi, a_lo, w_hi, w_lo, p, num_sms, stream);
+  if (block_n == 128) return launch_impl<128>(a_hi, a_lo, w_hi, w_lo, p, num_sms, stream);
+  set_last_error("launch_linear: unsupported block_n %d", block_n);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace cmdi

@@ -1,0 +1,160 @@
+// Host-visible launch interface of the sm_100a kernels (internal to the shared library).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cmdi {
+
+// ----------------------------------------------------------------------------------------------
+// linear layer: C[M,N] = epilogue(A[M,K] * W[N,K]^T)      (gemm.cu)
+// ----------------------------------------------------------------------------------------------
+enum RowMap : int {
+  ROWMAP_IDENTITY = 0,
+  ROWMAP_FRAMES_TO_SEQ = 1,  // A row b*L + l      -> out row b*(L+1) + l + 1   (frame embed, mdm.py:279)
+  ROWMAP_SEQ_TO_FRAMES = 2,  // A row b*(L+1) + s  -> out row b*L + s - 1, s=0 dropped (mdm.py:284 "[1:]")
+};
+
+struct LinearParams {
+  int M;       // valid A rows
+  int N;       // valid output columns
+  int K;       // reduction extent (any value; tail k-block is zero-filled by TMA)
+  int nsplit;  // 1: A_hi*W_hi            (bf16)
+               // 3: + A_hi*W_lo + A_lo*W_hi   (bf16x3, ~fp32 accuracy)
+  const float* bias;      // [N] or null
+  const float* residual;  // fp32 [rows, ld_res], indexed by OUTPUT row; or null
+  int ld_res;
+  const float* pos_enc;  // fp32 [L+1, N] table added per output sequence position (ROWMAP_FRAMES_TO_SEQ); or null
+  int act;               // 0 none, 1 exact erf GELU
+  int rowmap;            // RowMap
+  int frames;            // L for the two sequence row maps
+  int dup_row_offset;    // >0: also store every output row at (row + dup_row_offset)  (CFG: cond + uncond copies)
+  float* out_f32;        // fp32 [rows, ld_f32] or null
+  int ld_f32;
+  __nv_bfloat16* out_hi;  // bf16 planes [rows, ld_bf] or null
+  __nv_bfloat16* out_lo;  // written only when nsplit_out == 3
+  int ld_bf;
+  int nsplit_out;  // 1 or 3: whether the consumer of out_hi/out_lo wants the lo plane
+};
+
+// block_n: 128 or 256. Tensor maps: bf16 row-major, box {64, 128} for A and {64, block_n} for W, 128B swizzle.
+cudaError_t launch_linear(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                          const CUtensorMap& w_lo, const LinearParams& p, int block_n, int num_sms,
+                          cudaStream_t stream);
+
+// ----------------------------------------------------------------------------------------------
+// self-attention core: O = softmax(Q K^T / sqrt(dh)) V per (sequence, head)      (attention.cu)
+// ----------------------------------------------------------------------------------------------
+struct AttnParams {
+  int num_seqs;   // sequences (B, or 2B under CFG)
+  int seq_len;    // S = L+1 (<= 208)
+  int num_heads;  // H, head dim fixed at 128
+  int nsplit;     // 1 or 3 (as above, applied to both Q K^T and P V)
+  int nsplit_out;
+  __nv_bfloat16* out_hi;  // [num_seqs*seq_len (+pad), H*128]
+  __nv_bfloat16* out_lo;
+  int ld_out;
+};
+// qkv maps: bf16 [rows, 3*H*128] row-major planes (hi, lo); box {64, 128} for Q, {64, 208} for K and V.
+cudaError_t launch_attention(const CUtensorMap& q_hi, const CUtensorMap& q_lo, const CUtensorMap& kv_hi,
+                             const CUtensorMap& kv_lo, const AttnParams& p, cudaStream_t stream);
+constexpr int kAttnKeyPad = 208;
+
+// ----------------------------------------------------------------------------------------------
+// elementwise / row kernels      (elementwise.cu)
+// ----------------------------------------------------------------------------------------------
+// y = LayerNorm(v) * gamma + beta over rows of 512; writes fp32 and bf16 planes.
+cudaError_t launch_layernorm512(const float* v, const float* gamma, const float* beta, float eps, int rows, float* out_f32,
+                                __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream);
+
+// fp32 CUDA-core linear for the tiny per-loop tables: out[r, n] = act(in[r,:] . W[n,:] + b[n])
+// act: 0 none, 2 SiLU
+cudaError_t launch_small_linear(const float* in, const float* W, const float* bias, float* out, int rows, int N, int K,
+                                int act, cudaStream_t stream);
+
+// Conditioning token rows of the sequence buffer (mdm.py:245-251, :279-280):
+//   x[seq*S + 0, :] = temb[step_t, :] + (cond_proj[seq % B] if seq < n_cond_seqs else uncond_bias) + pe[0, :]
+struct TokenParams {
+  const float* temb_table;  // [T, 512] time_embed(pe[timestep_map[t]]) for every sampler step t
+  const int* step_ptr;      // device: current sampler step index t
+  const float* cond_proj;   // [B, 512] embed_text(cond) (bias included) or null (no_cond)
+  const float* uncond_proj; // [512] embed_text(0) = bias, or null
+  const float* pe0;         // [512]
+  int num_seqs;             // total sequences
+  int n_cond_seqs;          // first n use cond_proj[seq], the rest use uncond_proj
+  int seq_len;
+  float* x_f32;             // [num_seqs*seq_len, 512]
+  __nv_bfloat16* x_hi;
+  __nv_bfloat16* x_lo;
+};
+cudaError_t launch_token_rows(const TokenParams& p, cudaStream_t stream);
+
+// Diffusion step (gaussian_diffusion.py:352-534, :656-713, :1358-1416) on frame-major state [B*L, D_pad].
+struct StepTables {            // device pointers, each [T] fp32, indexed by sampler step t
+  const float* post_coef1;     // posterior_mean_coef1
+  const float* post_coef2;     // posterior_mean_coef2
+  const float* post_logvar;    // posterior_log_variance_clipped
+  const float* sqrt_recip_acp;    // sqrt(1/alphas_cumprod)
+  const float* sqrt_recipm1_acp;  // sqrt(1/alphas_cumprod - 1)
+  const float* acp;               // alphas_cumprod
+  const float* acp_prev;          // alphas_cumprod_prev
+};
+struct StepParams {
+  StepTables tab;
+  int* step_ptr;            // device: current step t; decremented by the kernel's last block when advance != 0
+  int advance;
+  int B, L, D, D_pad;
+  int sampler;              // 0 = ancestral DDPM (p_sample), 1 = DDIM (ddim_sample_with_grad, cond_fn=None)
+  float eta;                // DDIM
+  const float* model_out;   // [B*L (x2 when cfg), D_pad] raw denoiser output(s); uncond half at +B*L rows
+  int cfg;                  // 1: out = u + s[b]*(c - u)
+  const float* text_scale;  // [B]
+  const float* x_t;         // [B*L, D_pad]
+  // imputation (gaussian_diffusion.py:427-435): applied when impute != 0 and t >= stop_imputation_at
+  int impute;
+  int stop_imputation_at;
+  const float* x_obs;          // [B*L, D_pad] frame-major
+  const uint8_t* obs_mask;     // [B*L, D_pad] frame-major, already AND-ed with y.mask
+  // noise
+  const float* noise_ref;      // reference layout [B, D, 1, L] for this step, or null -> in-kernel Philox
+  unsigned long long seed;     // Philox key
+  unsigned long long sample_offset;  // global index of local sample 0 (multi-GPU: results independent of sharding)
+  // outputs
+  float* x_next;               // [B*L, D_pad]
+  __nv_bfloat16* x_next_hi;
+  __nv_bfloat16* x_next_lo;
+  float* pred_xstart;          // [B*L, D_pad] or null
+};
+cudaError_t launch_diffusion_step(const StepParams& p, cudaStream_t stream);
+
+// layout converters between the reference layout [B, D, 1, L] and frame-major [B*L, D_pad]
+cudaError_t launch_ref_to_frames(const float* ref, int B, int D, int L, int D_pad, float* out_f32, __nv_bfloat16* out_hi,
+                                 __nv_bfloat16* out_lo, cudaStream_t stream);
+cudaError_t launch_frames_to_ref(const float* frames, int B, int D, int L, int D_pad, float* ref, cudaStream_t stream);
+// mask: ref-layout bool bytes [B, D, 1, L] AND y_mask [B, L] (or null) -> frame-major bytes
+cudaError_t launch_mask_to_frames(const uint8_t* ref_mask, const uint8_t* y_mask, int B, int D, int L, int D_pad,
+                                  uint8_t* out, cudaStream_t stream);
+// q_sample (gaussian_diffusion.py:311-328) in reference layout: out = a*x0 + b*noise
+cudaError_t launch_axpby(const float* x, const float* y, float a, float b, float* out, size_t n, cudaStream_t stream);
+// standard normal fill (Philox4x32-10 + Box-Muller), value at flat index i of sample s depends on (seed, stream_id, s, i) only
+cudaError_t launch_fill_normal_ref(float* out, int B, size_t per_sample, unsigned long long seed,
+                                   unsigned long long stream_id, unsigned long long sample_offset, cudaStream_t stream);
+cudaError_t launch_set_int(int* p, int v, cudaStream_t stream);
+
+// fp32 [rows, cols] -> bf16 planes [rows, ld] (zero padded columns)
+cudaError_t launch_split_planes(const float* in, int rows, int cols, int ld_in, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                                int ld_out, cudaStream_t stream);
+
+// ----------------------------------------------------------------------------------------------
+// TMA descriptor creation (tma_host.cu)
+// ----------------------------------------------------------------------------------------------
+// bf16 row-major [rows, cols] with row pitch ld elements; box {box_cols (=64), box_rows}; 128 B swizzle.
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                      uint32_t box_rows);
+
+void set_last_error(const char* fmt, ...);
+const char* get_last_error();
+
+}  // namespace cmdi

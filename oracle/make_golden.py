@@ -1,0 +1,207 @@
+"""TEST INFRASTRUCTURE -- pins the oracle against the UNMODIFIED reference and writes tests/golden/*.npz.
+
+Run in the build container (needs /root/reference):   python -m oracle.make_golden
+
+For every piece of the hot path it (1) runs the reference's own code on CPU on seeded inputs, (2) runs the
+restatement in oracle/condmdi_oracle.py on the same inputs, (3) asserts they agree, and (4) stores the
+REFERENCE's output as a fixture.  Weights are not stored (70 MB): they are regenerated from a seed by
+`condmdi_oracle.random_state_dict` and loaded into the reference model with load_state_dict.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import condmdi_oracle as O  # noqa: E402
+from oracle import reference_harness as RH  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+B, D, L = 2, 263, 196
+
+
+def close(a, b, tol, what):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    err = (a - b).abs().max().item()
+    print(f"  {what}: max|ref - oracle| = {err:.3e}")
+    assert err <= tol, (what, err)
+
+
+def ref_model_with(sd, text):
+    m = RH.build_reference_model(seed=0, text=text)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    return m
+
+
+def golden_schedules():
+    print("schedules")
+    ref = RH.import_reference()
+    out = {}
+    for name, resp in (("full", ""), ("ddim50", "ddim50"), ("ddim100", "ddim100"), ("sect", "10,15,20")):
+        d = RH.build_reference_diffusion(resp)
+        t = O.make_tables(resp)
+        assert d.timestep_map == t.timestep_map
+        for f in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+                  "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_variance",
+                  "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2"):
+            r, o = getattr(d, f), getattr(t, f)
+            assert np.array_equal(r, o), (name, f)  # float64, same op order -> bit-identical
+            out[f"{name}.{f}"] = r
+        out[f"{name}.timestep_map"] = np.array(d.timestep_map, dtype=np.int64)
+    for sched in (None, "first-half", "last-half", "exponential", "sigmoid", "half-sigmoid"):
+        r = ref.editing_util.get_gradient_schedule(sched, 1000)
+        assert np.array_equal(r, O.get_gradient_schedule(sched, 1000))
+        out[f"grad.{sched}"] = r
+    np.savez_compressed(os.path.join(GOLDEN, "schedules.npz"), **out)
+
+
+def golden_masks():
+    print("keyframe masks")
+    ref = RH.import_reference()
+    out = {}
+    data = torch.zeros(4, D, 1, L)
+    lengths = torch.tensor([196, 120, 57, 5])
+    out["lengths"] = lengths.numpy()
+    for mode, Ts in (("benchmark_sparse", (1, 5, 10, 15, 20)), ("benchmark_clip", (10, 20, 30)), ("uncond", (5,))):
+        for T in Ts:
+            if mode == "benchmark_clip" and T > 5:
+                ls = torch.tensor([196, 120, 57, 40])
+            else:
+                ls = lengths
+            for fm in ("pos_rot_vel", "pos", "pos_rot"):
+                r, rj = ref.editing_util.get_keyframes_mask(data, ls, edit_mode=mode, trans_length=T, feature_mode=fm,
+                                                            get_joint_mask=True)
+                o, oj = O.get_keyframes_mask(data, ls, edit_mode=mode, trans_length=T, feature_mode=fm, get_joint_mask=True)
+                assert torch.equal(r, o) and torch.equal(rj, oj), (mode, T, fm)
+                key = f"{mode}.{T}.{fm}"
+                out[key + ".lengths"] = ls.numpy()
+                out[key + ".bits"] = np.packbits(r.numpy().reshape(-1))
+                out[key + ".sums"] = r.sum(dim=(1, 2, 3)).numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "masks.npz"), **out)
+    print("  sums sparse T=5:", out["benchmark_sparse.5.pos_rot_vel.sums"])
+
+
+def golden_model_and_sampler():
+    ref = RH.import_reference()
+    out = {}
+    gi = O.golden_inputs()
+    x, cond, x_obs, tape, scale, lengths, y_mask, kf_mask = (gi[k] for k in (
+        "x", "cond", "x_obs", "tape", "text_scale", "lengths", "y_mask", "kf_mask"))
+    # inputs are regenerated from the seed by O.golden_inputs(); a checksum pins them
+    out["inputs.checksum"] = np.array([float(x.double().sum()), float(tape.double().sum()), float(cond.double().sum())])
+
+    # ---------------- denoiser forward, no_cond ----------------
+    print("MDM.forward (no_cond)")
+    sd = O.random_state_dict(seed=7, text=False)
+    m = ref_model_with(sd, text=False)
+    t_model = torch.tensor([999, 37])
+    with torch.no_grad():
+        r = m(x, t_model, y={})
+    o = O.mdm_forward(sd, x, t_model)
+    close(r, o, 2e-5, "forward no_cond")
+    out["fwd_nocond.t"] = t_model.numpy()
+    out["fwd_nocond.out"] = r.numpy()
+
+    # ---------------- denoiser forward, text / uncond / CFG ----------------
+    print("MDM.forward (text), ClassifierFreeSampleModel.forward")
+    sdt = O.random_state_dict(seed=7, text=True)
+    mt = ref_model_with(sdt, text=True)
+    mt._synthetic_text_emb = cond
+    t_model = torch.tensor([500, 500])
+    with torch.no_grad():
+        r_c = mt(x, t_model, y={"text": ["a", "b"]})
+        r_u = mt(x, t_model, y={"text": ["a", "b"], "uncond": True})
+        cfgm = ref.cfg_sampler.ClassifierFreeSampleModel(mt)
+        r_cfg = cfgm(x, t_model, y={"text": ["a", "b"], "text_scale": scale})
+    close(r_c, O.mdm_forward(sdt, x, t_model, cond), 2e-5, "forward text")
+    close(r_u, O.mdm_forward(sdt, x, t_model, cond, uncond=True), 2e-5, "forward uncond")
+    close(r_cfg, O.cfg_forward(sdt, x, t_model, cond, scale), 5e-5, "cfg forward")
+    out["fwd_text.out"] = r_c.numpy()
+    out["fwd_cfg.out"] = r_cfg.numpy()
+
+    # ---------------- loops ----------------
+    def run_ref(model, diffusion, kwargs, sampler, steps, tape_, **kw):
+        """first `steps` iterations of the reference's progressive loop"""
+        outs = []
+        fn = diffusion.p_sample_loop_progressive if sampler == "ddpm" else diffusion.ddim_sample_loop_progressive
+        with RH.noise_tape(tape_):
+            for k, o_ in enumerate(fn(model, (B, D, 1, L), model_kwargs=kwargs, device="cpu", clip_denoised=False, **kw)):
+                outs.append(o_)
+                if k + 1 == steps:
+                    break
+        return outs
+
+    print("p_sample_loop, unconditional, 3 steps (T=1000)")
+    diff = RH.build_reference_diffusion("")
+    tab = O.make_tables("")
+    r = run_ref(m, diff, {"y": {}}, "ddpm", 3, tape)
+    o = O.sample_loop(sd, tab, (B, D, 1, L), O.Conditioning(), tape, "ddpm", max_steps=3, return_all=True)
+    close(r[-1]["sample"], o[-1]["sample"], 5e-5, "ddpm uncond sample")
+    close(r[-1]["pred_xstart"], o[-1]["pred_xstart"], 5e-5, "ddpm uncond pred_xstart")
+    out["ddpm_uncond.sample"] = r[-1]["sample"].numpy()
+    out["ddpm_uncond.pred_xstart"] = r[-1]["pred_xstart"].numpy()
+
+    print("ddim_sample_loop ddim50, all 50 steps incl. t=0, tape cycled")
+    diff50 = RH.build_reference_diffusion("ddim50")
+    tab50 = O.make_tables("ddim50")
+    tape50 = tape[torch.arange(51) % 8]
+    with RH.noise_tape(tape50):
+        r = diff50.ddim_sample_loop(m, (B, D, 1, L), model_kwargs={"y": {}}, device="cpu", clip_denoised=False)
+    o = O.sample_loop(sd, tab50, (B, D, 1, L), O.Conditioning(), tape50, "ddim")
+    close(r, o, 2e-4, "ddim50 final sample")
+    out["ddim50.sample"] = r.numpy()
+
+    print("p_sample_loop, CFG + imputation (conditional), last 4 steps via skip_timesteps")
+    ykw = {"text": ["a", "b"], "text_scale": scale, "mask": y_mask, "lengths": lengths, "imputate": 1,
+           "stop_imputation_at": 1, "replacement_distribution": "conditional", "inpainted_motion": x_obs,
+           "inpainting_mask": kf_mask}
+    r = run_ref(cfgm, diff, {"y": ykw}, "ddpm", 4, tape, skip_timesteps=996, init_image=x_obs)
+    c = O.Conditioning(cond_emb=cond, cfg=True, text_scale=scale, y_mask=y_mask, imputate=True, stop_imputation_at=1,
+                       inpainted_motion=x_obs, inpainting_mask=kf_mask)
+    o = O.sample_loop(sdt, tab, (B, D, 1, L), c, tape, "ddpm", skip_timesteps=996, init_image=x_obs, return_all=True)
+    assert len(o) == 4
+    for k in range(4):
+        close(r[k]["sample"], o[k]["sample"], 1e-4, f"cfg+impute step {k} sample")
+    # at t >= stop_imputation_at the observed entries of pred_xstart are exactly x_obs
+    M = (kf_mask * y_mask.float()).bool()
+    assert torch.equal(r[2]["pred_xstart"][M], x_obs[M])
+    out["cfg_impute.sample"] = r[-1]["sample"].numpy()
+    out["cfg_impute.pred_xstart_t1"] = r[2]["pred_xstart"].numpy()
+    out["kf_mask.bits"] = np.packbits(kf_mask.numpy().reshape(-1))
+
+    print("p_sample_loop, imputation + reconstruction guidance (w=20), 2 steps from t=999")
+    ykw2 = dict(ykw)
+    ykw2.update(reconstruction_guidance=True, reconstruction_weight=20.0, gradient_schedule=None, diffusion_steps=1000,
+                stop_recguidance_at=0)
+    r = run_ref(cfgm, diff, {"y": ykw2}, "ddpm", 2, tape)
+    c2 = O.Conditioning(cond_emb=cond, cfg=True, text_scale=scale, y_mask=y_mask, imputate=True, stop_imputation_at=1,
+                        inpainted_motion=x_obs, inpainting_mask=kf_mask, reconstruction_guidance=True,
+                        reconstruction_weight=20.0)
+    o = O.sample_loop(sdt, tab, (B, D, 1, L), c2, tape, "ddpm", max_steps=2, return_all=True)
+    close(r[-1]["sample"], o[-1]["sample"], 2e-4, "recon-guidance sample")
+    out["recon.sample"] = r[-1]["sample"].numpy()
+    out["recon.pred_xstart"] = r[-1]["pred_xstart"].numpy()
+
+    np.savez_compressed(os.path.join(GOLDEN, "sampler.npz"), **out)
+
+
+def main():
+    if not RH.available():
+        raise SystemExit("the reference tree is required to (re)generate golden vectors")
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    golden_schedules()
+    golden_masks()
+    golden_model_and_sampler()
+    for f in sorted(os.listdir(GOLDEN)):
+        print(f, os.path.getsize(os.path.join(GOLDEN, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
