@@ -246,6 +246,11 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
 
 }  // namespace
 
+cudaError_t configure_attention_kernel() {
+  return cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)(1024 + kSmemTiles + sizeof(AttnBarriers)));
+}
+
 cudaError_t launch_attention(const CUtensorMap& q_hi, const CUtensorMap& q_lo, const CUtensorMap& kv_hi,
                              const CUtensorMap& kv_lo, const AttnParams& p, cudaStream_t stream) {
   if (p.seq_len > kKeyPad || p.seq_len < 1 || (p.nsplit != 1 && p.nsplit != 3)) {
@@ -253,12 +258,6 @@ cudaError_t launch_attention(const CUtensorMap& q_hi, const CUtensorMap& q_lo, c
     return cudaErrorInvalidValue;
   }
   const size_t smem = 1024 + kSmemTiles + sizeof(AttnBarriers);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   dim3 grid((p.seq_len + kQTile - 1) / kQTile, p.num_heads, p.num_seqs);
   attention_kernel<<<grid, kThreads, smem, stream>>>(q_hi, q_lo, kv_hi, kv_lo, p);
   return cudaGetLastError();

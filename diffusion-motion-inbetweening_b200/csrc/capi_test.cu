@@ -63,6 +63,7 @@ extern "C" int cmdi_test_linear(const float* A, const float* W, const float* bia
   if (make_tmap_bf16_2d(&ma_lo, a_lo.p, Mp, Kp, Kp, 64, 128)) return 1;
   if (make_tmap_bf16_2d(&mw_hi, w_hi.p, Np, Kp, Kp, 64, block_n)) return 1;
   if (make_tmap_bf16_2d(&mw_lo, w_lo.p, Np, Kp, Kp, 64, block_n)) return 1;
+  CK(configure_linear_kernels());
   LinearParams p{};
   p.M = M; p.N = N; p.K = K; p.nsplit = precision;
   p.bias = bias; p.residual = residual; p.ld_res = N;
@@ -101,6 +102,7 @@ extern "C" int cmdi_test_attention(const float* qkv, float* O, int num_seqs, int
   if (make_tmap_bf16_2d(&mq_lo, q_lo.p, rows_p, ld, ld, 64, 128)) return 1;
   if (make_tmap_bf16_2d(&mkv_hi, q_hi.p, rows_p, ld, ld, 64, kAttnKeyPad)) return 1;
   if (make_tmap_bf16_2d(&mkv_lo, q_lo.p, rows_p, ld, ld, 64, kAttnKeyPad)) return 1;
+  CK(configure_attention_kernel());
   AttnParams p{};
   p.num_seqs = num_seqs; p.seq_len = S; p.num_heads = H; p.nsplit = precision; p.nsplit_out = 3;
   p.out_hi = o_hi.as<__nv_bfloat16>(); p.out_lo = o_lo.as<__nv_bfloat16>(); p.ld_out = ldo;
@@ -121,5 +123,12 @@ extern "C" int cmdi_test_attention(const float* qkv, float* O, int num_seqs, int
     }
     CK(cudaMemcpy(O, ho.data(), ho.size() * 4, cudaMemcpyHostToDevice));
   }
+  return 0;
+}
+
+extern "C" int cmdi_test_normal(float* out, int B, long long per_sample, unsigned long long seed, unsigned long long stream_id,
+                                unsigned long long sample_offset, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CK(launch_fill_normal_ref(out, B, (size_t)per_sample, seed, stream_id, sample_offset, stream));
   return 0;
 }

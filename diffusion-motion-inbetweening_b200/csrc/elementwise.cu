@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) token_rows_kernel(const TokenParams p) {
   const int seq = blockIdx.x;
-  const int t = *p.step_ptr;
+  int t = *p.step_ptr;
+  if (p.timestep_map) t = p.timestep_map[t];
   const int col = threadIdx.x * 4;
   float4 e = *reinterpret_cast<const float4*>(p.temb_table + (size_t)t * 512 + col);
   if (p.cond_proj) {
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(256) diffusion_step_kernel(const StepParams p)
   const int t = *p.step_ptr;
 
   // ---- noise tile (reference layout [b][c][l], l contiguous) ----
-  const bool want_noise = true;  // the reference draws noise at every step, including t == 0
+  const bool want_noise = p.sampler != 2;  // the reference draws noise at every step, including t == 0
   if (want_noise) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(256) diffusion_step_kernel(const StepParams p)
       float nz = 0.f;
       if (c < p.D && l < p.L) {
         const size_t e = (size_t)c * p.L + l;
-        nz = p.noise_ref ? p.noise_ref[(size_t)b * p.D * p.L + e]
+        nz = p.noise_ref ? p.noise_ref[((size_t)(p.tape_t0 - t) * p.B + b) * p.D * p.L + e]
                          : philox_normal(p.seed, (unsigned long long)(t + 1), p.sample_offset + b, e);
       }
       s_noise[ty + i * 8][tx] = nz;
@@ -188,8 +189,9 @@ __global__ void __launch_bounds__(256) diffusion_step_kernel(const StepParams p)
   __syncthreads();
 
   // ---- per-step scalars (fp32, gathered exactly like _extract_into_tensor(...).float()) ----
-  const float coef1 = p.tab.post_coef1[t], coef2 = p.tab.post_coef2[t];
-  const float logvar = p.tab.post_logvar[t];
+  // (sampler 2 = plain denoiser evaluation: no schedule is needed, and none may be set)
+  const float coef1 = p.sampler == 0 ? p.tab.post_coef1[t] : 0.f, coef2 = p.sampler == 0 ? p.tab.post_coef2[t] : 0.f;
+  const float logvar = p.sampler == 0 ? p.tab.post_logvar[t] : 0.f;
   const float nonzero = (t != 0) ? 1.0f : 0.0f;
   const float text_scale = p.cfg ? p.text_scale[b] : 0.f;
   const bool do_impute = p.impute && (t >= p.stop_imputation_at);
@@ -215,7 +217,9 @@ __global__ void __launch_bounds__(256) diffusion_step_kernel(const StepParams p)
       x0 = out;  // START_X, no clipping (:513-515)
       const float xt = p.x_t[idx];
       const float noise = s_noise[tx][ty + i * 8];
-      if (p.sampler == 0) {
+      if (p.sampler == 2) {
+        xn = 0.f;
+      } else if (p.sampler == 0) {
         // mean = coef1*x0 + coef2*x_t (:338-342); sample = mean + nonzero*exp(0.5*logvar)*noise (:710-711)
         const float mean = __fadd_rn(__fmul_rn(coef1, x0), __fmul_rn(coef2, xt));
         const float sd = expf(__fmul_rn(0.5f, logvar));
@@ -232,11 +236,13 @@ __global__ void __launch_bounds__(256) diffusion_step_kernel(const StepParams p)
         xn = __fadd_rn(mean_pred, __fmul_rn(__fmul_rn(nonzero, sigma), noise));
       }
     }
-    p.x_next[idx] = xn;
-    __nv_bfloat16 h, lo;
-    split_bf16(xn, h, lo);
-    p.x_next_hi[idx] = h;
-    if (p.x_next_lo) p.x_next_lo[idx] = lo;
+    if (p.x_next) {
+      p.x_next[idx] = xn;
+      __nv_bfloat16 h, lo;
+      split_bf16(xn, h, lo);
+      p.x_next_hi[idx] = h;
+      if (p.x_next_lo) p.x_next_lo[idx] = lo;
+    }
     if (p.pred_xstart) p.pred_xstart[idx] = x0;
   }
 

@@ -1,0 +1,822 @@
+// The sampling engine behind the C ABI of include/condmdi_b200.h.
+//
+// One engine per device.  It owns (a) the MDM weights as bf16 hi/lo planes + their TMA descriptors,
+// (b) the diffusion tables as fp32 device arrays, (c) every activation buffer of one denoiser pass, sized
+// once for 2*max_batch sequences (the CFG cond+uncond pass is one batch-doubled pass), and (d) one captured
+// CUDA graph per loop configuration.  A sampling step is 60 kernel launches of this library and nothing else:
+//
+//   token_rows -> frame-embed GEMM -> 8 x [QKV GEMM, attention, out-proj GEMM(+residual), LayerNorm,
+//                 FFN1 GEMM(+GELU), FFN2 GEMM(+residual), LayerNorm] -> output-head GEMM -> diffusion_step
+//
+// The step index lives on the device (decremented by diffusion_step), so the same graph is replayed for
+// every step of a loop with no host work in between (reference: one Python iteration + ~150 PyTorch ops
+// + several H2D table copies per step, gaussian_diffusion.py:1270-1297, :2225, respace.py:129).
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/condmdi_b200.h"
+#include "kernels.h"
+
+using namespace cmdi;
+
+namespace {
+
+#define CK(expr)                                                                                    \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);   \
+      return 1;                                                                                     \
+    }                                                                                               \
+  } while (0)
+#define CKI(expr)          \
+  do {                     \
+    if ((expr) != 0) return 1; \
+  } while (0)
+
+constexpr int kDModel = 512;
+constexpr int kBnWide = 256;    // QKV, FFN1
+constexpr int kBnNarrow = 128;  // N = 512 / 264 outputs: more tiles per wave
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct Planes {  // a bf16 hi/lo operand: [rows, ld] row-major, with TMA maps for a given box height
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+  int rows = 0, cols = 0, ld = 0;
+  CUtensorMap map_hi{}, map_lo{};
+};
+
+struct LayerW {
+  Planes wqkv, wo, w1, w2;
+  float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
+  float *g1 = nullptr, *be1 = nullptr, *g2 = nullptr, *be2 = nullptr;
+};
+
+struct GraphKey {
+  int B, cfg, sampler, impute, stop_at, tape_mode, has_cond;
+  float eta;
+  const void* tape;
+  unsigned long long seed, sample_offset;
+  int t0, uncond;
+  bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
+};
+
+}  // namespace
+
+struct cmdi_engine {
+  cmdi_model_cfg cfg{};
+  int device = 0, num_sms = 148;
+  int nsplit = 3;
+  int D = 263, D_pad = 264, L = 196, S = 197, ff = 1024, H = 4, layers = 8, maxB = 0;
+  int max_seqs = 0, seq_rows = 0, seq_rows_pad = 0, frame_rows = 0, frame_rows_pad = 0;
+  std::vector<void*> allocs;
+  // weights
+  Planes w_in, w_out;
+  float *b_in = nullptr, *b_out = nullptr;
+  std::vector<LayerW> lw;
+  float *pe = nullptr;  // [5000, 512]
+  float *te_w0 = nullptr, *te_b0 = nullptr, *te_w2 = nullptr, *te_b2 = nullptr;
+  float *et_w = nullptr, *et_b = nullptr;
+  bool weights_loaded = false, temb_valid = false;
+  float* temb_table = nullptr;  // [5000, 512] time_embed(pe[t]) for every ORIGINAL timestep t
+  float* temb_hidden = nullptr;
+  // schedule
+  int T = 0;
+  std::vector<double> h_sqrt_acp, h_sqrt_1m_acp;
+  std::vector<int> h_tmap;
+  float* tables = nullptr;  // 7 x [T]
+  int* d_tmap = nullptr;
+  StepTables tab{};
+  // activations
+  float* x_state = nullptr;
+  Planes x_state_p;
+  float *xseq = nullptr, *x1 = nullptr, *vsum = nullptr, *model_out = nullptr, *pred_x0 = nullptr, *x_obs = nullptr;
+  Planes xseq_p, x1_p, qkv_p, attn_p, ffh_p;
+  CUtensorMap q_map_hi{}, q_map_lo{}, kv_map_hi{}, kv_map_lo{};
+  uint8_t* obs_mask = nullptr;
+  float *cond_emb = nullptr, *cond_proj = nullptr, *text_scale = nullptr;
+  int* step_ctr = nullptr;  // [2]: step index, block-arrival counter
+  float *ref_a = nullptr, *ref_b = nullptr;  // reference-layout staging [maxB, D, L]
+  uint8_t *ref_mask = nullptr, *ymask = nullptr;
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  int64_t launches = 0;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(cmdi_engine* e, T** out, size_t count) {
+  void* p = nullptr;
+  const size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
+  CK(cudaMalloc(&p, bytes));
+  CK(cudaMemset(p, 0, bytes));
+  e->allocs.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return 0;
+}
+
+int alloc_planes(cmdi_engine* e, Planes* pl, int rows, int cols, int ld, int box_rows) {
+  pl->rows = rows; pl->cols = cols; pl->ld = ld;
+  CKI(dev_alloc(e, &pl->hi, (size_t)rows * ld));
+  CKI(dev_alloc(e, &pl->lo, (size_t)rows * ld));
+  CKI(make_tmap_bf16_2d(&pl->map_hi, pl->hi, rows, cols, ld, 64, box_rows));
+  CKI(make_tmap_bf16_2d(&pl->map_lo, pl->lo, rows, cols, ld, 64, box_rows));
+  return 0;
+}
+
+// fp32 source (host or device) -> device fp32 copy of `count` floats
+int upload_f32(cmdi_engine* e, float* dst, const cmdi_tensor_desc& t, size_t count, cudaStream_t s) {
+  if ((size_t)t.numel != count) {
+    set_last_error("tensor %s: expected %zu elements, got %lld", t.name, count, (long long)t.numel);
+    return 1;
+  }
+  CK(cudaMemcpyAsync(dst, t.data, count * 4, t.on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+// fp32 [rows, cols] source -> bf16 planes (zero padded to pl.ld / pl.rows)
+int upload_planes(cmdi_engine* e, Planes& pl, const cmdi_tensor_desc& t, int rows, int cols, float* scratch, cudaStream_t s) {
+  if ((size_t)t.numel != (size_t)rows * cols) {
+    set_last_error("tensor %s: expected %d x %d elements, got %lld", t.name, rows, cols, (long long)t.numel);
+    return 1;
+  }
+  const float* src = t.data;
+  if (t.on_host) {
+    CK(cudaMemcpyAsync(scratch, t.data, (size_t)rows * cols * 4, cudaMemcpyHostToDevice, s));
+    src = scratch;
+  }
+  CK(launch_split_planes(src, rows, cols, cols, pl.hi, pl.lo, pl.ld, s));
+  return 0;
+}
+
+int ensure_temb(cmdi_engine* e, cudaStream_t s) {
+  if (e->temb_valid) return 0;
+  // TimestepEmbedder (mdm.py:345-353) for every original timestep: time_embed(pe[t]); fp32 CUDA cores, once.
+  const int n = 5000;
+  CK(launch_small_linear(e->pe, e->te_w0, e->te_b0, e->temb_hidden, n, kDModel, kDModel, /*SiLU*/ 2, s));
+  CK(launch_small_linear(e->temb_hidden, e->te_w2, e->te_b2, e->temb_table, n, kDModel, kDModel, 0, s));
+  e->launches += 2;
+  e->temb_valid = true;
+  return 0;
+}
+
+// One denoiser pass over `nseq` sequences whose frame features are in x_state planes (first B sequences;
+// with dup the frame embedding is written for sequences [0,B) and [B,2B)).
+int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond, const int* tmap_dev, cudaStream_t s,
+                 std::vector<cudaEvent_t>* evs = nullptr) {
+  auto mark = [&]() -> int {
+    if (!evs) return 0;
+    cudaEvent_t ev;
+    CK(cudaEventCreate(&ev));
+    CK(cudaEventRecord(ev, s));
+    evs->push_back(ev);
+    return 0;
+  };
+  CKI(mark());
+  const int nseq = dup ? 2 * B : B;
+  const int M = nseq * e->S;
+  TokenParams tk{};
+  tk.temb_table = e->temb_table; tk.step_ptr = e->step_ctr; tk.timestep_map = tmap_dev;
+  tk.cond_proj = has_cond ? e->cond_proj : nullptr; tk.uncond_proj = has_cond ? e->et_b : nullptr;
+  tk.pe0 = e->pe; tk.num_seqs = nseq; tk.n_cond_seqs = n_cond_seqs; tk.seq_len = e->S;
+  tk.x_f32 = e->xseq; tk.x_hi = e->xseq_p.hi; tk.x_lo = e->xseq_p.lo;
+  CK(launch_token_rows(tk, s));
+  CKI(mark());
+
+  LinearParams p{};
+  // frame embedding + positional encoding (mdm.py:271, :279-280)
+  p.M = B * e->L; p.N = kDModel; p.K = e->D; p.nsplit = e->nsplit; p.bias = e->b_in; p.pos_enc = e->pe;
+  p.rowmap = ROWMAP_FRAMES_TO_SEQ; p.frames = e->L; p.dup_row_offset = dup ? B * e->S : 0;
+  p.out_f32 = e->xseq; p.ld_f32 = kDModel; p.out_hi = e->xseq_p.hi; p.out_lo = e->xseq_p.lo; p.ld_bf = kDModel;
+  p.nsplit_out = e->nsplit;
+  CK(launch_linear(e->x_state_p.map_hi, e->x_state_p.map_lo, e->w_in.map_hi, e->w_in.map_lo, p, kBnNarrow, e->num_sms, s));
+  CKI(mark());
+
+  for (int l = 0; l < e->layers; ++l) {
+    const LayerW& w = e->lw[l];
+    // QKV projection
+    LinearParams q{};
+    q.M = M; q.N = 3 * kDModel; q.K = kDModel; q.nsplit = e->nsplit; q.bias = w.bqkv;
+    q.out_hi = e->qkv_p.hi; q.out_lo = e->qkv_p.lo; q.ld_bf = 3 * kDModel; q.nsplit_out = e->nsplit;
+    CK(launch_linear(e->xseq_p.map_hi, e->xseq_p.map_lo, w.wqkv.map_hi, w.wqkv.map_lo, q, kBnWide, e->num_sms, s));
+    CKI(mark());
+    // attention core
+    AttnParams a{};
+    a.num_seqs = nseq; a.seq_len = e->S; a.num_heads = e->H; a.nsplit = e->nsplit; a.nsplit_out = e->nsplit;
+    a.out_hi = e->attn_p.hi; a.out_lo = e->attn_p.lo; a.ld_out = kDModel;
+    CK(launch_attention(e->q_map_hi, e->q_map_lo, e->kv_map_hi, e->kv_map_lo, a, s));
+    CKI(mark());
+    // out-proj + residual, then LayerNorm1
+    LinearParams o{};
+    o.M = M; o.N = kDModel; o.K = kDModel; o.nsplit = e->nsplit; o.bias = w.bo; o.residual = e->xseq; o.ld_res = kDModel;
+    o.out_f32 = e->vsum; o.ld_f32 = kDModel; o.nsplit_out = e->nsplit;
+    CK(launch_linear(e->attn_p.map_hi, e->attn_p.map_lo, w.wo.map_hi, w.wo.map_lo, o, kBnNarrow, e->num_sms, s));
+    CKI(mark());
+    CK(launch_layernorm512(e->vsum, w.g1, w.be1, 1e-5f, M, e->x1, e->x1_p.hi, e->nsplit == 3 ? e->x1_p.lo : nullptr, s));
+    CKI(mark());
+    // FFN
+    LinearParams f1{};
+    f1.M = M; f1.N = e->ff; f1.K = kDModel; f1.nsplit = e->nsplit; f1.bias = w.b1; f1.act = 1;
+    f1.out_hi = e->ffh_p.hi; f1.out_lo = e->ffh_p.lo; f1.ld_bf = e->ff; f1.nsplit_out = e->nsplit;
+    CK(launch_linear(e->x1_p.map_hi, e->x1_p.map_lo, w.w1.map_hi, w.w1.map_lo, f1, kBnWide, e->num_sms, s));
+    CKI(mark());
+    LinearParams f2{};
+    f2.M = M; f2.N = kDModel; f2.K = e->ff; f2.nsplit = e->nsplit; f2.bias = w.b2; f2.residual = e->x1; f2.ld_res = kDModel;
+    f2.out_f32 = e->vsum; f2.ld_f32 = kDModel; f2.nsplit_out = e->nsplit;
+    CK(launch_linear(e->ffh_p.map_hi, e->ffh_p.map_lo, w.w2.map_hi, w.w2.map_lo, f2, kBnNarrow, e->num_sms, s));
+    CKI(mark());
+    CK(launch_layernorm512(e->vsum, w.g2, w.be2, 1e-5f, M, e->xseq, e->xseq_p.hi, e->nsplit == 3 ? e->xseq_p.lo : nullptr, s));
+    CKI(mark());
+  }
+  // output head on tokens 1.. (mdm.py:284 "[1:]", :304-305)
+  LinearParams h{};
+  h.M = M; h.N = e->D_pad; h.K = kDModel; h.nsplit = e->nsplit; h.bias = e->b_out;
+  h.rowmap = ROWMAP_SEQ_TO_FRAMES; h.frames = e->L; h.out_f32 = e->model_out; h.ld_f32 = e->D_pad; h.nsplit_out = e->nsplit;
+  CK(launch_linear(e->xseq_p.map_hi, e->xseq_p.map_lo, e->w_out.map_hi, e->w_out.map_lo, h, kBnNarrow, e->num_sms, s));
+  CKI(mark());
+  return 0;
+}
+int launches_per_pass(const cmdi_engine* e) { return 1 + 1 + e->layers * 7 + 1; }
+
+int check_ready(cmdi_engine* e, int B, bool need_schedule) {
+  if (!e->weights_loaded) {
+    set_last_error("weights not loaded (cmdi_load_weights)");
+    return 1;
+  }
+  if (need_schedule && e->T == 0) {
+    set_last_error("schedule not set (cmdi_set_schedule)");
+    return 1;
+  }
+  if (B < 1 || B > e->maxB) {
+    set_last_error("batch %d outside [1, max_batch=%d]", B, e->maxB);
+    return 1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ==================================================================================================
+// C ABI
+// ==================================================================================================
+extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_engine** out) {
+  if (!cfg || !out) {
+    set_last_error("null argument");
+    return 1;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_last_error("no CUDA device: condmdi_b200 has no CPU fallback");
+    return 1;
+  }
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop{};
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_last_error("device %d is sm_%d%d; this library contains sm_100a code only (B200)", device, prop.major, prop.minor);
+    return 1;
+  }
+  if (cfg->latent_dim != kDModel || cfg->num_heads * 128 != cfg->latent_dim || cfg->ff_size % 256 != 0 ||
+      cfg->nframes + 1 > kAttnKeyPad || cfg->njoints < 8 || cfg->max_batch < 1 ||
+      (cfg->precision != CMDI_PRECISION_BF16X3 && cfg->precision != CMDI_PRECISION_BF16)) {
+    set_last_error("unsupported model configuration (need latent_dim=512, 4 heads of 128, ff %% 256 == 0, nframes <= 207)");
+    return 1;
+  }
+  CK(configure_linear_kernels());
+  CK(configure_attention_kernel());
+  cmdi_engine* e = new cmdi_engine();
+  e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount; e->nsplit = cfg->precision;
+  e->D = cfg->njoints; e->D_pad = round_up(cfg->njoints, 8); e->L = cfg->nframes; e->S = cfg->nframes + 1;
+  e->ff = cfg->ff_size; e->H = cfg->num_heads; e->layers = cfg->num_layers; e->maxB = cfg->max_batch;
+  e->max_seqs = 2 * e->maxB;
+  e->seq_rows = e->max_seqs * e->S;
+  e->seq_rows_pad = round_up(e->seq_rows, 128) + 256;  // attention K/V boxes of the last sequence read 208 rows
+  e->frame_rows = e->maxB * e->L;
+  e->frame_rows_pad = round_up(e->frame_rows, 128);
+  int rc = 0;
+#define A(expr) rc = rc || (expr)
+  // weights
+  A(alloc_planes(e, &e->w_in, kDModel, e->D_pad, e->D_pad, kBnNarrow));
+  A(alloc_planes(e, &e->w_out, round_up(e->D_pad, kBnNarrow), kDModel, kDModel, kBnNarrow));
+  A(dev_alloc(e, &e->b_in, kDModel));
+  A(dev_alloc(e, &e->b_out, round_up(e->D_pad, kBnNarrow)));
+  e->lw.resize(e->layers);
+  for (auto& w : e->lw) {
+    A(alloc_planes(e, &w.wqkv, 3 * kDModel, kDModel, kDModel, kBnWide));
+    A(alloc_planes(e, &w.wo, kDModel, kDModel, kDModel, kBnNarrow));
+    A(alloc_planes(e, &w.w1, e->ff, kDModel, kDModel, kBnWide));
+    A(alloc_planes(e, &w.w2, kDModel, e->ff, e->ff, kBnNarrow));
+    A(dev_alloc(e, &w.bqkv, 3 * kDModel)); A(dev_alloc(e, &w.bo, kDModel));
+    A(dev_alloc(e, &w.b1, e->ff)); A(dev_alloc(e, &w.b2, kDModel));
+    A(dev_alloc(e, &w.g1, kDModel)); A(dev_alloc(e, &w.be1, kDModel));
+    A(dev_alloc(e, &w.g2, kDModel)); A(dev_alloc(e, &w.be2, kDModel));
+  }
+  A(dev_alloc(e, &e->pe, (size_t)5000 * kDModel));
+  A(dev_alloc(e, &e->te_w0, (size_t)kDModel * kDModel)); A(dev_alloc(e, &e->te_b0, kDModel));
+  A(dev_alloc(e, &e->te_w2, (size_t)kDModel * kDModel)); A(dev_alloc(e, &e->te_b2, kDModel));
+  A(dev_alloc(e, &e->et_w, (size_t)kDModel * 512)); A(dev_alloc(e, &e->et_b, kDModel));
+  A(dev_alloc(e, &e->temb_table, (size_t)5000 * kDModel));
+  A(dev_alloc(e, &e->temb_hidden, (size_t)5000 * kDModel));
+  // activations
+  A(dev_alloc(e, &e->x_state, (size_t)e->frame_rows_pad * e->D_pad));
+  A(alloc_planes(e, &e->x_state_p, e->frame_rows_pad, e->D_pad, e->D_pad, 128));
+  A(dev_alloc(e, &e->xseq, (size_t)e->seq_rows_pad * kDModel));
+  A(dev_alloc(e, &e->x1, (size_t)e->seq_rows_pad * kDModel));
+  A(dev_alloc(e, &e->vsum, (size_t)e->seq_rows_pad * kDModel));
+  A(alloc_planes(e, &e->xseq_p, e->seq_rows_pad, kDModel, kDModel, 128));
+  A(alloc_planes(e, &e->x1_p, e->seq_rows_pad, kDModel, kDModel, 128));
+  A(alloc_planes(e, &e->qkv_p, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 128));
+  A(alloc_planes(e, &e->attn_p, e->seq_rows_pad, kDModel, kDModel, 128));
+  A(alloc_planes(e, &e->ffh_p, e->seq_rows_pad, e->ff, e->ff, 128));
+  A(make_tmap_bf16_2d(&e->q_map_hi, e->qkv_p.hi, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, 128));
+  A(make_tmap_bf16_2d(&e->q_map_lo, e->qkv_p.lo, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, 128));
+  A(make_tmap_bf16_2d(&e->kv_map_hi, e->qkv_p.hi, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, kAttnKeyPad));
+  A(make_tmap_bf16_2d(&e->kv_map_lo, e->qkv_p.lo, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, kAttnKeyPad));
+  A(dev_alloc(e, &e->model_out, (size_t)2 * e->frame_rows_pad * e->D_pad));
+  A(dev_alloc(e, &e->pred_x0, (size_t)e->frame_rows_pad * e->D_pad));
+  A(dev_alloc(e, &e->x_obs, (size_t)e->frame_rows_pad * e->D_pad));
+  A(dev_alloc(e, &e->obs_mask, (size_t)e->frame_rows_pad * e->D_pad));
+  A(dev_alloc(e, &e->cond_emb, (size_t)e->maxB * 512));
+  A(dev_alloc(e, &e->cond_proj, (size_t)e->maxB * kDModel));
+  A(dev_alloc(e, &e->text_scale, e->maxB));
+  A(dev_alloc(e, &e->step_ctr, 2));
+  A(dev_alloc(e, &e->ref_a, (size_t)e->maxB * e->D * e->L));
+  A(dev_alloc(e, &e->ref_b, (size_t)e->maxB * e->D * e->L));
+  A(dev_alloc(e, &e->ref_mask, (size_t)e->maxB * e->D * e->L));
+  A(dev_alloc(e, &e->ymask, (size_t)e->maxB * e->L));
+#undef A
+  if (rc) {
+    cmdi_engine_destroy(e);
+    return 1;
+  }
+  // default positional-encoding buffer (mdm.py:322-330); overwritten if the state dict carries 'sequence_pos_encoder.pe'
+  {
+    std::vector<float> pe((size_t)5000 * kDModel);
+    for (int pos = 0; pos < 5000; ++pos)
+      for (int i = 0; i < kDModel; i += 2) {
+        const float div = expf((float)i * (float)(-std::log(10000.0) / kDModel));
+        pe[(size_t)pos * kDModel + i] = sinf((float)pos * div);
+        pe[(size_t)pos * kDModel + i + 1] = cosf((float)pos * div);
+      }
+    CK(cudaMemcpy(e->pe, pe.data(), pe.size() * 4, cudaMemcpyHostToDevice));
+  }
+  *out = e;
+  return 0;
+}
+
+extern "C" int cmdi_engine_destroy(cmdi_engine* e) {
+  if (!e) return 0;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->tables) cudaFree(e->tables);
+  if (e->d_tmap) cudaFree(e->d_tmap);
+  delete e;
+  return 0;
+}
+
+extern "C" int64_t cmdi_launch_count(const cmdi_engine* e) { return e ? e->launches : 0; }
+
+extern "C" int cmdi_load_weights(cmdi_engine* e, const cmdi_tensor_desc* tensors, int n) {
+  if (!e || !tensors) {
+    set_last_error("null argument");
+    return 1;
+  }
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = 0;
+  float* scratch = nullptr;
+  CK(cudaMalloc(&scratch, (size_t)3 * kDModel * 1024 * 4));
+  std::map<std::string, const cmdi_tensor_desc*> by_name;
+  for (int i = 0; i < n; ++i) by_name[tensors[i].name] = &tensors[i];
+  std::string missing;
+  auto get = [&](const std::string& k) -> const cmdi_tensor_desc* {
+    auto it = by_name.find(k);
+    if (it == by_name.end()) {
+      missing += k + " ";
+      return nullptr;
+    }
+    return it->second;
+  };
+  int rc = 0;
+#define LOAD_F32(dst, key, count)                         \
+  do {                                                    \
+    const cmdi_tensor_desc* t_ = get(key);                \
+    if (t_) rc = rc || upload_f32(e, dst, *t_, count, s); \
+  } while (0)
+#define LOAD_PL(pl, key, rows, cols)                                        \
+  do {                                                                      \
+    const cmdi_tensor_desc* t_ = get(key);                                  \
+    if (t_) rc = rc || upload_planes(e, pl, *t_, rows, cols, scratch, s);   \
+  } while (0)
+  LOAD_PL(e->w_in, "input_process.poseEmbedding.weight", kDModel, e->D);
+  LOAD_F32(e->b_in, "input_process.poseEmbedding.bias", kDModel);
+  LOAD_PL(e->w_out, "output_process.poseFinal.weight", e->D, kDModel);
+  LOAD_F32(e->b_out, "output_process.poseFinal.bias", (size_t)e->D);
+  LOAD_F32(e->te_w0, "embed_timestep.time_embed.0.weight", (size_t)kDModel * kDModel);
+  LOAD_F32(e->te_b0, "embed_timestep.time_embed.0.bias", kDModel);
+  LOAD_F32(e->te_w2, "embed_timestep.time_embed.2.weight", (size_t)kDModel * kDModel);
+  LOAD_F32(e->te_b2, "embed_timestep.time_embed.2.bias", kDModel);
+  if (e->cfg.has_text) {
+    LOAD_F32(e->et_w, "embed_text.weight", (size_t)kDModel * 512);
+    LOAD_F32(e->et_b, "embed_text.bias", kDModel);
+  }
+  if (by_name.count("sequence_pos_encoder.pe")) LOAD_F32(e->pe, "sequence_pos_encoder.pe", (size_t)5000 * kDModel);
+  for (int l = 0; l < e->layers; ++l) {
+    LayerW& w = e->lw[l];
+    const std::string p = "seqTransEncoder.layers." + std::to_string(l) + ".";
+    LOAD_PL(w.wqkv, p + "self_attn.in_proj_weight", 3 * kDModel, kDModel);
+    LOAD_F32(w.bqkv, p + "self_attn.in_proj_bias", (size_t)3 * kDModel);
+    LOAD_PL(w.wo, p + "self_attn.out_proj.weight", kDModel, kDModel);
+    LOAD_F32(w.bo, p + "self_attn.out_proj.bias", kDModel);
+    LOAD_PL(w.w1, p + "linear1.weight", e->ff, kDModel);
+    LOAD_F32(w.b1, p + "linear1.bias", (size_t)e->ff);
+    LOAD_PL(w.w2, p + "linear2.weight", kDModel, e->ff);
+    LOAD_F32(w.b2, p + "linear2.bias", kDModel);
+    LOAD_F32(w.g1, p + "norm1.weight", kDModel);
+    LOAD_F32(w.be1, p + "norm1.bias", kDModel);
+    LOAD_F32(w.g2, p + "norm2.weight", kDModel);
+    LOAD_F32(w.be2, p + "norm2.bias", kDModel);
+  }
+#undef LOAD_F32
+#undef LOAD_PL
+  cudaError_t se = cudaStreamSynchronize(s);
+  cudaFree(scratch);
+  if (!missing.empty()) {
+    set_last_error("state dict is missing: %s", missing.c_str());
+    return 1;
+  }
+  if (rc) return 1;
+  CK(se);
+  e->weights_loaded = true;
+  e->temb_valid = false;
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  e->graphs.clear();
+  return 0;
+}
+
+extern "C" int cmdi_set_schedule(cmdi_engine* e, const double* betas_in, int T, const int64_t* timestep_map) {
+  if (!e || !betas_in || T < 2 || !timestep_map) {
+    set_last_error("cmdi_set_schedule: bad arguments");
+    return 1;
+  }
+  CK(cudaSetDevice(e->device));
+  // float64 tables exactly as GaussianDiffusion.__init__ builds them (gaussian_diffusion.py:183-217),
+  // cast to fp32 at the point _extract_into_tensor does (.float() after the gather, :2225).
+  std::vector<double> betas(betas_in, betas_in + T), acp(T), acp_prev(T), post_var(T);
+  double run = 1.0;
+  for (int i = 0; i < T; ++i) {
+    if (!(betas[i] > 0 && betas[i] <= 1)) {
+      set_last_error("betas must lie in (0, 1]");
+      return 1;
+    }
+    run *= (1.0 - betas[i]);
+    acp[i] = run;
+  }
+  // np.cumprod is a sequential product in float64: identical rounding to the loop above
+  for (int i = 0; i < T; ++i) acp_prev[i] = i == 0 ? 1.0 : acp[i - 1];
+  std::vector<float> host((size_t)7 * T);
+  e->h_sqrt_acp.assign(T, 0.0);
+  e->h_sqrt_1m_acp.assign(T, 0.0);
+  for (int i = 0; i < T; ++i) post_var[i] = betas[i] * (1.0 - acp_prev[i]) / (1.0 - acp[i]);
+  for (int i = 0; i < T; ++i) {
+    const double alpha = 1.0 - betas[i];
+    host[0 * T + i] = (float)(betas[i] * std::sqrt(acp_prev[i]) / (1.0 - acp[i]));          // posterior_mean_coef1
+    host[1 * T + i] = (float)((1.0 - acp_prev[i]) * std::sqrt(alpha) / (1.0 - acp[i]));     // posterior_mean_coef2
+    host[2 * T + i] = (float)std::log(post_var[i == 0 ? 1 : i]);                            // posterior_log_variance_clipped
+    host[3 * T + i] = (float)std::sqrt(1.0 / acp[i]);                                       // sqrt_recip_alphas_cumprod
+    host[4 * T + i] = (float)std::sqrt(1.0 / acp[i] - 1);                                   // sqrt_recipm1_alphas_cumprod
+    host[5 * T + i] = (float)acp[i];
+    host[6 * T + i] = (float)acp_prev[i];
+    e->h_sqrt_acp[i] = std::sqrt(acp[i]);
+    e->h_sqrt_1m_acp[i] = std::sqrt(1.0 - acp[i]);
+  }
+  if (e->tables) cudaFree(e->tables);
+  if (e->d_tmap) cudaFree(e->d_tmap);
+  e->tables = nullptr; e->d_tmap = nullptr;
+  CK(cudaMalloc(&e->tables, host.size() * 4));
+  CK(cudaMemcpy(e->tables, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+  e->h_tmap.resize(T);
+  for (int i = 0; i < T; ++i) {
+    if (timestep_map[i] < 0 || timestep_map[i] >= 5000) {
+      set_last_error("timestep_map[%d]=%lld outside the positional table", i, (long long)timestep_map[i]);
+      return 1;
+    }
+    e->h_tmap[i] = (int)timestep_map[i];
+  }
+  CK(cudaMalloc(&e->d_tmap, (size_t)T * 4));
+  CK(cudaMemcpy(e->d_tmap, e->h_tmap.data(), (size_t)T * 4, cudaMemcpyHostToDevice));
+  e->T = T;
+  e->tab.post_coef1 = e->tables + 0 * T; e->tab.post_coef2 = e->tables + 1 * T; e->tab.post_logvar = e->tables + 2 * T;
+  e->tab.sqrt_recip_acp = e->tables + 3 * T; e->tab.sqrt_recipm1_acp = e->tables + 4 * T;
+  e->tab.acp = e->tables + 5 * T; e->tab.acp_prev = e->tables + 6 * T;
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  e->graphs.clear();
+  return 0;
+}
+
+namespace {
+
+// staging helper: returns a device pointer holding `bytes` of user data (copying when the user pointer is host memory)
+const void* stage_in(const void* user, void* dev_scratch, size_t bytes, bool host, cudaStream_t s, int* rc) {
+  if (!user) return nullptr;
+  if (!host) return user;
+  cudaError_t e = cudaMemcpyAsync(dev_scratch, user, bytes, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) {
+    set_last_error("H2D copy failed: %s", cudaGetErrorString(e));
+    *rc = 1;
+  }
+  return dev_scratch;
+}
+
+int prepare_cond(cmdi_engine* e, int B, const float* cond_emb_user, bool host, cudaStream_t s) {
+  if (!cond_emb_user) return 0;
+  if (!e->cfg.has_text) {
+    set_last_error("cond_emb given but the engine was created with has_text = 0");
+    return 1;
+  }
+  CK(cudaMemcpyAsync(e->cond_emb, cond_emb_user, (size_t)B * 512 * 4, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+  // embed_text(enc_text): once per call instead of once per step and pass (mdm.py:249-250 re-runs it every step)
+  CK(launch_small_linear(e->cond_emb, e->et_w, e->et_b, e->cond_proj, B, kDModel, 512, 0, s));
+  e->launches += 1;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int cmdi_model_forward(cmdi_engine* e, const cmdi_forward_args* a, float* out, void* stream_) {
+  if (!e || !a || !out || !a->x) {
+    set_last_error("null argument");
+    return 1;
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  CK(cudaSetDevice(e->device));
+  const int B = a->batch;
+  CKI(check_ready(e, B, false));
+  if (a->cfg && (!a->cond_emb || !a->text_scale)) {
+    set_last_error("cfg forward needs cond_emb and text_scale (cfg_sampler.py:26, :35)");
+    return 1;
+  }
+  if (a->timestep < 0 || a->timestep >= 5000) {
+    set_last_error("timestep %d outside the positional table", a->timestep);
+    return 1;
+  }
+  const bool host = a->host_buffers != 0;
+  const size_t n = (size_t)B * e->D * e->L;
+  CKI(ensure_temb(e, s));
+  int rc = 0;
+  const float* x = (const float*)stage_in(a->x, e->ref_a, n * 4, host, s, &rc);
+  if (rc) return 1;
+  CK(launch_ref_to_frames(x, B, e->D, e->L, e->D_pad, nullptr, e->x_state_p.hi, e->x_state_p.lo, s));
+  CKI(prepare_cond(e, B, a->cond_emb, host, s));
+  if (a->cfg) CK(cudaMemcpyAsync(e->text_scale, a->text_scale, (size_t)B * 4, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+  CK(launch_set_int(e->step_ctr, a->timestep, s));
+  const bool has_cond = a->cond_emb != nullptr;
+  const int n_cond = a->cfg ? B : (a->uncond ? 0 : B);
+  CKI(run_denoiser(e, B, a->cfg != 0, n_cond, has_cond, /*tmap*/ nullptr, s));
+  // combine (cfg) into pred_x0 via the step kernel's pass-through mode, then back to the reference layout
+  StepParams sp{};
+  sp.tab = e->tab; sp.step_ptr = e->step_ctr; sp.advance = 0; sp.B = B; sp.L = e->L; sp.D = e->D; sp.D_pad = e->D_pad;
+  sp.sampler = 2; sp.model_out = e->model_out; sp.cfg = a->cfg != 0; sp.text_scale = e->text_scale; sp.x_t = e->x_state;
+  sp.x_next = nullptr; sp.pred_xstart = e->pred_x0;
+  CK(launch_diffusion_step(sp, s));
+  float* dst = host ? e->ref_b : out;
+  CK(launch_frames_to_ref(e->pred_x0, B, e->D, e->L, e->D_pad, dst, s));
+  e->launches += launches_per_pass(e) + 4;
+  if (host) {
+    CK(cudaMemcpyAsync(out, e->ref_b, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  return 0;
+}
+
+extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out, void* stream_) {
+  if (!e || !a || !out) {
+    set_last_error("null argument");
+    return 1;
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  CK(cudaSetDevice(e->device));
+  const int B = a->batch;
+  CKI(check_ready(e, B, true));
+  if (a->sampler != CMDI_SAMPLER_DDPM && a->sampler != CMDI_SAMPLER_DDIM) {
+    set_last_error("unknown sampler %d", a->sampler);
+    return 1;
+  }
+  if (a->cfg && (!a->cond_emb || !a->text_scale)) {
+    set_last_error("cfg sampling needs cond_emb and text_scale (cfg_sampler.py:26, :35)");
+    return 1;
+  }
+  if (a->imputate && (!a->inpainted_motion || !a->inpainting_mask)) {
+    set_last_error("imputate needs inpainted_motion and inpainting_mask (editing_util.py:343)");
+    return 1;
+  }
+  if (a->skip_timesteps < 0 || a->skip_timesteps >= e->T) {
+    set_last_error("skip_timesteps %d outside [0, %d)", a->skip_timesteps, e->T);
+    return 1;
+  }
+  const bool host = a->host_buffers != 0;
+  const size_t n = (size_t)B * e->D * e->L;
+  const int t0 = e->T - 1 - a->skip_timesteps;
+  const int nsteps = (a->num_steps > 0 && a->num_steps < t0 + 1) ? a->num_steps : t0 + 1;
+  CKI(ensure_temb(e, s));
+  int rc = 0;
+
+  // ---- x_T (gaussian_diffusion.py:1245-1248) ----
+  const float* xT = (const float*)stage_in(a->x_T, e->ref_a, n * 4, host, s, &rc);
+  if (rc) return 1;
+  if (!xT) {
+    CK(launch_fill_normal_ref(e->ref_a, B, (size_t)e->D * e->L, a->seed, 0ull, a->sample_offset, s));
+    xT = e->ref_a;
+    e->launches += 1;
+  }
+  // ---- init_image / skip_timesteps: img = q_sample(init_image, t0, img) (:1252-1260) ----
+  if (!a->resume && (a->init_image || a->skip_timesteps)) {
+    const float* init = (const float*)stage_in(a->init_image, e->ref_b, n * 4, host, s, &rc);
+    if (rc) return 1;
+    if (!init) {
+      CK(cudaMemsetAsync(e->ref_b, 0, n * 4, s));
+      init = e->ref_b;
+    }
+    CK(launch_axpby(init, xT, (float)e->h_sqrt_acp[t0], (float)e->h_sqrt_1m_acp[t0], e->ref_a, n, s));
+    xT = e->ref_a;
+    e->launches += 1;
+  }
+  CK(launch_ref_to_frames(xT, B, e->D, e->L, e->D_pad, e->x_state, e->x_state_p.hi, e->x_state_p.lo, s));
+  e->launches += 1;
+  // ---- keyframes ----
+  if (a->imputate) {
+    const float* obs = (const float*)stage_in(a->inpainted_motion, e->ref_b, n * 4, host, s, &rc);
+    const uint8_t* msk = (const uint8_t*)stage_in(a->inpainting_mask, e->ref_mask, n, host, s, &rc);
+    const uint8_t* ym = (const uint8_t*)stage_in(a->y_mask, e->ymask, (size_t)B * e->L, host, s, &rc);
+    if (rc) return 1;
+    CK(launch_ref_to_frames(obs, B, e->D, e->L, e->D_pad, e->x_obs, nullptr, nullptr, s));
+    CK(launch_mask_to_frames(msk, ym, B, e->D, e->L, e->D_pad, e->obs_mask, s));
+    e->launches += 2;
+  }
+  // ---- conditioning ----
+  CKI(prepare_cond(e, B, a->cond_emb, host, s));
+  if (a->cfg) CK(cudaMemcpyAsync(e->text_scale, a->text_scale, (size_t)B * 4, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+  CK(launch_set_int(e->step_ctr, t0, s));
+  e->launches += 1;
+
+  const float* tape = a->noise_tape;
+  if (tape && host) {
+    set_last_error("noise_tape must be a device pointer (it is a test aid; stage it once outside the call)");
+    return 1;
+  }
+  const bool has_cond = a->cond_emb != nullptr;
+  auto enqueue_step = [&](cudaStream_t st) -> int {
+    CKI(run_denoiser(e, B, a->cfg != 0, (a->uncond && !a->cfg) ? 0 : B, has_cond, e->d_tmap, st));
+    StepParams sp{};
+    sp.tab = e->tab; sp.step_ptr = e->step_ctr; sp.advance = 1; sp.B = B; sp.L = e->L; sp.D = e->D; sp.D_pad = e->D_pad;
+    sp.sampler = a->sampler; sp.eta = a->eta; sp.model_out = e->model_out; sp.cfg = a->cfg != 0; sp.text_scale = e->text_scale;
+    sp.x_t = e->x_state; sp.impute = a->imputate != 0; sp.stop_imputation_at = a->stop_imputation_at;
+    sp.x_obs = e->x_obs; sp.obs_mask = e->obs_mask;
+    sp.noise_ref = tape; sp.tape_t0 = t0; sp.seed = a->seed; sp.sample_offset = a->sample_offset;
+    sp.x_next = e->x_state; sp.x_next_hi = e->x_state_p.hi; sp.x_next_lo = e->nsplit == 3 ? e->x_state_p.lo : nullptr;
+    sp.pred_xstart = e->pred_x0;
+    CK(launch_diffusion_step(sp, st));
+    return 0;
+  };
+
+  cudaGraphExec_t exec = nullptr;
+  if (a->use_graph) {
+    GraphKey key{};
+    memset(&key, 0, sizeof(key));
+    key.B = B; key.cfg = a->cfg != 0; key.sampler = a->sampler; key.impute = a->imputate != 0;
+    key.stop_at = a->stop_imputation_at; key.tape_mode = tape != nullptr; key.has_cond = has_cond; key.eta = a->eta;
+    key.tape = tape; key.seed = a->seed; key.sample_offset = a->sample_offset; key.t0 = t0; key.uncond = a->uncond != 0;
+    auto it = e->graphs.find(key);
+    if (it == e->graphs.end()) {
+      // capture on a private stream so a caller's legacy/default stream is never put into capture mode
+      cudaStream_t cs = nullptr;
+      CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      const int erc = enqueue_step(cs);
+      cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+      cudaStreamDestroy(cs);
+      if (erc) return 1;
+      CK(ce);
+      CK(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      if (e->graphs.size() > 16) {  // bounded cache
+        for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+        e->graphs.clear();
+      }
+      e->graphs[key] = exec;
+    } else {
+      exec = it->second;
+    }
+  }
+
+  int dump_i = 0;
+  for (int k = 0; k < nsteps; ++k) {
+    if (exec) {
+      CK(cudaGraphLaunch(exec, s));
+    } else {
+      CKI(enqueue_step(s));
+    }
+    e->launches += launches_per_pass(e) + 1;
+    if (a->dump_xstart && dump_i < a->n_dump && a->dump_steps[dump_i] == k) {
+      if (host) {
+        CK(launch_frames_to_ref(e->pred_x0, B, e->D, e->L, e->D_pad, e->ref_b, s));
+        CK(cudaMemcpyAsync(a->dump_xstart + (size_t)dump_i * n, e->ref_b, n * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+      } else {
+        CK(launch_frames_to_ref(e->pred_x0, B, e->D, e->L, e->D_pad, a->dump_xstart + (size_t)dump_i * n, s));
+      }
+      e->launches += 1;
+      ++dump_i;
+    }
+  }
+  // ---- results back in the reference layout ----
+  if (host) {
+    CK(launch_frames_to_ref(e->x_state, B, e->D, e->L, e->D_pad, e->ref_a, s));
+    CK(cudaMemcpyAsync(out, e->ref_a, n * 4, cudaMemcpyDeviceToHost, s));
+    if (a->pred_xstart_out) {
+      CK(launch_frames_to_ref(e->pred_x0, B, e->D, e->L, e->D_pad, e->ref_b, s));
+      CK(cudaMemcpyAsync(a->pred_xstart_out, e->ref_b, n * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+  } else {
+    CK(launch_frames_to_ref(e->x_state, B, e->D, e->L, e->D_pad, out, s));
+    if (a->pred_xstart_out) CK(launch_frames_to_ref(e->pred_x0, B, e->D, e->L, e->D_pad, a->pred_xstart_out, s));
+  }
+  e->launches += a->pred_xstart_out ? 2 : 1;
+  return 0;
+}
+
+extern "C" int cmdi_test_step(cmdi_engine* e, int sampler, float eta, int t, int B, const float* model_out_c,
+                              const float* model_out_u, const float* text_scale, const float* x_t, const float* noise,
+                              int impute, int stop_imputation_at, const float* x_obs, const uint8_t* mask, float* x_next,
+                              float* pred_xstart, void* stream_) {
+  if (!e) {
+    set_last_error("null engine");
+    return 1;
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  CK(cudaSetDevice(e->device));
+  if (e->T == 0 || B < 1 || B > e->maxB || t < 0 || t >= e->T) {
+    set_last_error("cmdi_test_step: bad state/arguments");
+    return 1;
+  }
+  const size_t fr = (size_t)B * e->L * e->D_pad;
+  CK(launch_ref_to_frames(model_out_c, B, e->D, e->L, e->D_pad, e->model_out, nullptr, nullptr, s));
+  if (model_out_u) CK(launch_ref_to_frames(model_out_u, B, e->D, e->L, e->D_pad, e->model_out + fr, nullptr, nullptr, s));
+  CK(launch_ref_to_frames(x_t, B, e->D, e->L, e->D_pad, e->x_state, nullptr, nullptr, s));
+  if (impute) {
+    CK(launch_ref_to_frames(x_obs, B, e->D, e->L, e->D_pad, e->x_obs, nullptr, nullptr, s));
+    CK(launch_mask_to_frames(mask, nullptr, B, e->D, e->L, e->D_pad, e->obs_mask, s));
+  }
+  if (model_out_u) CK(cudaMemcpyAsync(e->text_scale, text_scale, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
+  CK(launch_set_int(e->step_ctr, t, s));
+  StepParams sp{};
+  sp.tab = e->tab; sp.step_ptr = e->step_ctr; sp.advance = 0; sp.B = B; sp.L = e->L; sp.D = e->D; sp.D_pad = e->D_pad;
+  sp.sampler = sampler; sp.eta = eta; sp.model_out = e->model_out; sp.cfg = model_out_u != nullptr; sp.text_scale = e->text_scale;
+  sp.x_t = e->x_state; sp.impute = impute; sp.stop_imputation_at = stop_imputation_at; sp.x_obs = e->x_obs; sp.obs_mask = e->obs_mask;
+  sp.noise_ref = noise; sp.tape_t0 = t; sp.x_next = e->x_state; sp.x_next_hi = e->x_state_p.hi; sp.x_next_lo = e->x_state_p.lo;
+  sp.pred_xstart = e->pred_x0;
+  CK(launch_diffusion_step(sp, s));
+  CK(launch_frames_to_ref(e->x_state, B, e->D, e->L, e->D_pad, x_next, s));
+  if (pred_xstart) CK(launch_frames_to_ref(e->pred_x0, B, e->D, e->L, e->D_pad, pred_xstart, s));
+  return 0;
+}
+
+// Per-kernel device times of one denoiser pass (plain launches with CUDA events between them, on the caller's
+// stream): ms[i] is the i-th launch of the pass in order
+//   token_rows, frame_embed, {qkv, attention, out_proj, ln1, ffn1, ffn2, ln2} x layers, out_head.
+extern "C" int cmdi_profile_pass(cmdi_engine* e, int batch, int cfg, float* ms, int capacity, int* count, void* stream_) {
+  if (!e || !ms || !count) {
+    set_last_error("null argument");
+    return 1;
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  CK(cudaSetDevice(e->device));
+  CKI(check_ready(e, batch, false));
+  CKI(ensure_temb(e, s));
+  CK(launch_set_int(e->step_ctr, 500, s));
+  std::vector<cudaEvent_t> evs;
+  const bool has_cond = cfg != 0 && e->cfg.has_text;
+  if (cfg && !has_cond) {
+    set_last_error("cfg profiling needs a text model");
+    return 1;
+  }
+  const int rc = run_denoiser(e, batch, cfg != 0, batch, has_cond, nullptr, s, &evs);
+  cudaError_t se = cudaStreamSynchronize(s);
+  int n = (int)evs.size() - 1;
+  if (rc == 0 && se == cudaSuccess) {
+    *count = n;
+    for (int i = 0; i < n && i < capacity; ++i) cudaEventElapsedTime(&ms[i], evs[i], evs[i + 1]);
+  }
+  for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
+  if (rc) return 1;
+  CK(se);
+  e->launches += launches_per_pass(e);
+  return 0;
+}

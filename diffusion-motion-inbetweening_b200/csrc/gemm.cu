@@ -295,12 +295,6 @@ cudaError_t launch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const 
   int num_stages = (kSmemLimit - 1024 - (int)sizeof(PipeBarriers)) / stage_bytes;
   if (num_stages > kMaxStages) num_stages = kMaxStages;
   const size_t smem = 1024 + (size_t)num_stages * stage_bytes + sizeof(PipeBarriers);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(linear_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   const int num_m_blocks = (p.M + kBlockM - 1) / kBlockM;
   const int num_n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m_blocks * num_n_blocks;
@@ -311,6 +305,12 @@ cudaError_t launch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const 
 }
 
 }  // namespace
+
+cudaError_t configure_linear_kernels() {
+  cudaError_t e = cudaFuncSetAttribute(linear_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(linear_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+}
 
 cudaError_t launch_linear(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                           const CUtensorMap& w_lo, const LinearParams& p, int block_n, int num_sms,

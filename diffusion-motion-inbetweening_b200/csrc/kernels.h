@@ -40,6 +40,7 @@ struct LinearParams {
 };
 
 // block_n: 128 or 256. Tensor maps: bf16 row-major, box {64, 128} for A and {64, block_n} for W, 128B swizzle.
+cudaError_t configure_linear_kernels();
 cudaError_t launch_linear(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                           const CUtensorMap& w_lo, const LinearParams& p, int block_n, int num_sms,
                           cudaStream_t stream);
@@ -58,6 +59,7 @@ struct AttnParams {
   int ld_out;
 };
 // qkv maps: bf16 [rows, 3*H*128] row-major planes (hi, lo); box {64, 128} for Q, {64, 208} for K and V.
+cudaError_t configure_attention_kernel();
 cudaError_t launch_attention(const CUtensorMap& q_hi, const CUtensorMap& q_lo, const CUtensorMap& kv_hi,
                              const CUtensorMap& kv_lo, const AttnParams& p, cudaStream_t stream);
 constexpr int kAttnKeyPad = 208;
@@ -77,8 +79,9 @@ cudaError_t launch_small_linear(const float* in, const float* W, const float* bi
 // Conditioning token rows of the sequence buffer (mdm.py:245-251, :279-280):
 //   x[seq*S + 0, :] = temb[step_t, :] + (cond_proj[seq % B] if seq < n_cond_seqs else uncond_bias) + pe[0, :]
 struct TokenParams {
-  const float* temb_table;  // [T, 512] time_embed(pe[timestep_map[t]]) for every sampler step t
+  const float* temb_table;  // [5000, 512] time_embed(pe[t]) for every ORIGINAL timestep t
   const int* step_ptr;      // device: current sampler step index t
+  const int* timestep_map;  // device [T]: sampler step -> original timestep (respace.py:128-133); null = identity
   const float* cond_proj;   // [B, 512] embed_text(cond) (bias included) or null (no_cond)
   const float* uncond_proj; // [512] embed_text(0) = bias, or null
   const float* pe0;         // [512]
@@ -106,7 +109,8 @@ struct StepParams {
   int* step_ptr;            // device: current step t; decremented by the kernel's last block when advance != 0
   int advance;
   int B, L, D, D_pad;
-  int sampler;              // 0 = ancestral DDPM (p_sample), 1 = DDIM (ddim_sample_with_grad, cond_fn=None)
+  int sampler;              // 0 = ancestral DDPM (p_sample), 1 = DDIM (ddim_sample_with_grad, cond_fn=None),
+                            // 2 = no update: only pred_xstart (= guided/imputed model output) is written
   float eta;                // DDIM
   const float* model_out;   // [B*L (x2 when cfg), D_pad] raw denoiser output(s); uncond half at +B*L rows
   int cfg;                  // 1: out = u + s[b]*(c - u)
@@ -118,7 +122,9 @@ struct StepParams {
   const float* x_obs;          // [B*L, D_pad] frame-major
   const uint8_t* obs_mask;     // [B*L, D_pad] frame-major, already AND-ed with y.mask
   // noise
-  const float* noise_ref;      // reference layout [B, D, 1, L] for this step, or null -> in-kernel Philox
+  const float* noise_ref;      // tape base, reference layout [steps][B, D, 1, L]; slice (tape_t0 - t) is this step's
+                               // randn_like draw; null -> in-kernel Philox
+  int tape_t0;
   unsigned long long seed;     // Philox key
   unsigned long long sample_offset;  // global index of local sample 0 (multi-GPU: results independent of sharding)
   // outputs

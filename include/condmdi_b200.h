@@ -86,7 +86,10 @@ typedef struct {
   int32_t batch;
   int32_t sampler;              /* CMDI_SAMPLER_* */
   float eta;                    /* DDIM eta (0 in the reference's callers) */
-  int32_t skip_timesteps;       /* gaussian_diffusion.py:1252-1260 */
+  int32_t skip_timesteps;       /* gaussian_diffusion.py:1252-1260: the loop starts at t0 = T - 1 - skip_timesteps */
+  int32_t num_steps;            /* loop iterations to run; 0 = all the way down to t = 0 */
+  int32_t resume;               /* 1: x_T already IS the state x_t0 (no q_sample of init_image); used to continue a
+                                   loop chunk by chunk, e.g. for the *_progressive generators (:1217, :1514) */
   const float* init_image;      /* ref layout or NULL (zeros when skip_timesteps > 0, :1252-1253) */
   /* noise: either a tape or the engine's counter-based generator */
   const float* x_T;             /* ref layout initial noise (p_sample_loop's `noise=` / randn(*shape), :1245-1248) or NULL */
@@ -96,6 +99,7 @@ typedef struct {
   uint64_t sample_offset;       /* global index of local sample 0: results are independent of how a batch is sharded */
   /* conditioning */
   const float* cond_emb;        /* (B, 512) or NULL */
+  int32_t uncond;               /* y['uncond'] on a plain (non-CFG) model: zero the text embedding (mdm.py:188-191) */
   int32_t cfg;                  /* model is wrapped in ClassifierFreeSampleModel */
   const float* text_scale;      /* (B,) y['text_scale'] */
   const uint8_t* y_mask;        /* (B, 196) y['mask'] as bytes, or NULL (= all true) */
@@ -136,6 +140,13 @@ CMDI_API int cmdi_test_layernorm(const float* v, const float* gamma, const float
 CMDI_API int cmdi_test_step(cmdi_engine* e, int sampler, float eta, int t, int B, const float* model_out_c, const float* model_out_u,
                    const float* text_scale, const float* x_t, const float* noise, int impute, int stop_imputation_at,
                    const float* x_obs, const uint8_t* mask, float* x_next, float* pred_xstart, void* stream);
+
+/* per-launch device times (ms) of one denoiser pass at `batch` (x2 sequences when cfg), in launch order:
+ * token_rows, frame_embed, {qkv, attention, out_proj, ln1, ffn1, ffn2, ln2} x num_layers, out_head */
+CMDI_API int cmdi_profile_pass(cmdi_engine* e, int batch, int cfg, float* ms, int capacity, int* count, void* stream);
+/* the engine's counter-based N(0,1) generator: out[b, i] depends only on (seed, stream_id, sample_offset + b, i) */
+CMDI_API int cmdi_test_normal(float* out, int B, long long per_sample, unsigned long long seed, unsigned long long stream_id,
+                     unsigned long long sample_offset, void* stream);
 
 #ifdef __cplusplus
 }

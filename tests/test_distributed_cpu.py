@@ -1,0 +1,87 @@
+"""CPU, world_size 2 over gloo: the batch-sharding + all-gather logic of condmdi_b200.distributed
+(the N>1 path of bench.py) with a stand-in sampler, so no GPU is needed."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from condmdi_b200.distributed import shard_model_kwargs, sharded_sample
+
+
+class StandInDiffusion:
+    """Returns a value per sample that encodes everything sharding must get right."""
+    sample_offset = 0
+    noise_tape = None
+
+    def p_sample_loop(self, model, shape, noise=None, model_kwargs=None, **kw):
+        B = shape[0]
+        y = model_kwargs["y"]
+        assert len(y["text"]) == B and y["text_scale"].shape[0] == B and y["mask"].shape[0] == B
+        assert y["imputate"] == 1  # non-batched entries pass through
+        out = torch.zeros(shape)
+        for b in range(B):
+            out[b] = (self.sample_offset + b) + 1000.0 * y["text_scale"][b] + float(len(y["text"][b])) * 1e-3 \
+                + (noise[b].sum() if noise is not None else 0.0) + (self.noise_tape[:, b].sum() if self.noise_tape is not None else 0.0)
+        return out
+
+
+def _expected(B, shape, text, scale, noise, tape):
+    out = torch.zeros((B,) + shape)
+    for b in range(B):
+        out[b] = b + 1000.0 * scale[b] + len(text[b]) * 1e-3 + noise[b].sum() + tape[:, b].sum()
+    return out
+
+
+def _worker(rank, world, port, B):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        shape = (3, 1, 5)
+        text = ["x" * (i + 1) for i in range(B)]
+        scale = torch.arange(B, dtype=torch.float32) * 0.5
+        noise = torch.randn((B,) + shape, generator=g)
+        tape = torch.randn((4, B) + shape, generator=g)
+        d = StandInDiffusion()
+        d.noise_tape = tape
+        kw = {"y": {"text": text, "text_scale": scale, "mask": torch.ones(B, 1, 1, 5, dtype=torch.bool), "imputate": 1}}
+        out = sharded_sample(d, None, (B,) + shape, model_kwargs=kw, noise=noise)
+        assert out.shape == (B,) + shape
+        assert torch.allclose(out, _expected(B, shape, text, scale, noise, tape), atol=1e-5)
+        assert d.sample_offset == 0 and d.noise_tape is tape  # restored
+        with pytest.raises(ValueError):
+            sharded_sample(d, None, (B + 1,) + shape, model_kwargs=kw)
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.timeout(180)
+def test_sharded_sample_world2_gloo():
+    mp.spawn(_worker, args=(2, _free_port(), 6), nprocs=2, join=True)
+
+
+def test_shard_model_kwargs_slices_only_batched_entries():
+    B = 4
+    kw = {"y": {"text": list("abcd"), "lengths": torch.arange(B), "scalar": 3, "vec5": torch.zeros(5)}, "obs_x0": torch.zeros(B, 2)}
+    s = shard_model_kwargs(kw, 2, 4, B)
+    assert s["y"]["text"] == ["c", "d"] and s["y"]["lengths"].tolist() == [2, 3] and s["y"]["scalar"] == 3
+    assert s["y"]["vec5"].shape == (5,) and s["obs_x0"].shape == (2, 2)
+
+
+def test_single_process_is_identity():
+    d = StandInDiffusion()
+    kw = {"y": {"text": ["a", "bb"], "text_scale": torch.tensor([1.0, 2.0]), "mask": torch.ones(2, 1, 1, 5), "imputate": 1}}
+    out = sharded_sample(d, None, (2, 3, 1, 5), model_kwargs=kw)
+    assert out.shape == (2, 3, 1, 5) and float(out[1, 0, 0, 0]) == pytest.approx(1 + 2000 + 2e-3)

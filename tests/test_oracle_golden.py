@@ -1,0 +1,114 @@
+"""CPU: the oracle restatement against the fixtures generated from the UNMODIFIED reference
+(oracle/make_golden.py).  This is what pins the oracle where /root/reference does not exist."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import condmdi_oracle as O
+
+B, D, L = 2, 263, 196
+
+
+@pytest.fixture(scope="module")
+def sched(golden_dir):
+    return np.load(os.path.join(golden_dir, "schedules.npz"))
+
+
+@pytest.fixture(scope="module")
+def samp(golden_dir):
+    return np.load(os.path.join(golden_dir, "sampler.npz"))
+
+
+@pytest.mark.parametrize("name,resp", [("full", ""), ("ddim50", "ddim50"), ("ddim100", "ddim100"), ("sect", "10,15,20")])
+def test_schedule_tables_bit_exact(sched, name, resp):
+    t = O.make_tables(resp)
+    assert np.array_equal(sched[f"{name}.timestep_map"], np.array(t.timestep_map))
+    for f in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+              "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_variance",
+              "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2"):
+        assert np.array_equal(sched[f"{name}.{f}"], getattr(t, f)), f
+
+
+@pytest.mark.parametrize("name", [None, "first-half", "last-half", "exponential", "sigmoid", "half-sigmoid"])
+def test_gradient_schedule(sched, name):
+    assert np.array_equal(sched[f"grad.{name}"], O.get_gradient_schedule(name, 1000))
+
+
+def test_keyframe_masks_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "masks.npz"))
+    keys = sorted(k[:-5] for k in g.files if k.endswith(".bits"))
+    assert len(keys) == 27
+    for key in keys:
+        mode, T, fm = key.split(".")
+        lengths = torch.tensor(g[key + ".lengths"])
+        m = O.get_keyframes_mask(torch.zeros(len(lengths), D, 1, L), lengths, edit_mode=mode, trans_length=int(T), feature_mode=fm)
+        assert np.array_equal(np.packbits(m.numpy().reshape(-1)), g[key + ".bits"]), key
+        assert np.array_equal(m.sum(dim=(1, 2, 3)).numpy(), g[key + ".sums"])
+    # the known-answer row of SURVEY.md 8(c)
+    assert g["benchmark_sparse.5.pos_rot_vel.sums"].tolist() == [10520, 6312, 3156, 263]
+
+
+def _inputs(samp):
+    gi = O.golden_inputs()
+    chk = np.array([float(gi["x"].double().sum()), float(gi["tape"].double().sum()), float(gi["cond"].double().sum())])
+    assert np.allclose(chk, samp["inputs.checksum"], rtol=0, atol=1e-9), "seeded inputs differ from the ones the fixtures were made with"
+    return gi
+
+
+def test_forward_matches_reference(samp):
+    gi = _inputs(samp)
+    sd = O.random_state_dict(seed=7)
+    out = O.mdm_forward(sd, gi["x"], torch.tensor(samp["fwd_nocond.t"]))
+    assert torch.allclose(out, torch.tensor(samp["fwd_nocond.out"]), rtol=1e-4, atol=2e-5)
+
+
+def test_text_and_cfg_forward_match_reference(samp):
+    gi = _inputs(samp)
+    sdt = O.random_state_dict(seed=7, text=True)
+    t = torch.tensor([500, 500])
+    assert torch.allclose(O.mdm_forward(sdt, gi["x"], t, gi["cond"]), torch.tensor(samp["fwd_text.out"]), rtol=1e-4, atol=2e-5)
+    assert torch.allclose(O.cfg_forward(sdt, gi["x"], t, gi["cond"], gi["text_scale"]), torch.tensor(samp["fwd_cfg.out"]),
+                          rtol=1e-4, atol=5e-5)
+
+
+def test_ddpm_loop_matches_reference(samp):
+    gi = _inputs(samp)
+    sd = O.random_state_dict(seed=7)
+    outs = O.sample_loop(sd, O.make_tables(""), (B, D, 1, L), O.Conditioning(), gi["tape"], "ddpm", max_steps=3, return_all=True)
+    assert torch.allclose(outs[-1]["sample"], torch.tensor(samp["ddpm_uncond.sample"]), rtol=1e-4, atol=5e-5)
+    assert torch.allclose(outs[-1]["pred_xstart"], torch.tensor(samp["ddpm_uncond.pred_xstart"]), rtol=1e-4, atol=5e-5)
+
+
+def test_cfg_imputation_loop_matches_reference(samp):
+    gi = _inputs(samp)
+    sdt = O.random_state_dict(seed=7, text=True)
+    c = O.Conditioning(cond_emb=gi["cond"], cfg=True, text_scale=gi["text_scale"], y_mask=gi["y_mask"], imputate=True,
+                       stop_imputation_at=1, inpainted_motion=gi["x_obs"], inpainting_mask=gi["kf_mask"])
+    assert np.array_equal(np.packbits(gi["kf_mask"].numpy().reshape(-1)), samp["kf_mask.bits"])
+    outs = O.sample_loop(sdt, O.make_tables(""), (B, D, 1, L), c, gi["tape"], "ddpm", skip_timesteps=996,
+                         init_image=gi["x_obs"], return_all=True)
+    assert torch.allclose(outs[-1]["sample"], torch.tensor(samp["cfg_impute.sample"]), rtol=1e-4, atol=1e-4)
+    assert torch.allclose(outs[2]["pred_xstart"], torch.tensor(samp["cfg_impute.pred_xstart_t1"]), rtol=1e-4, atol=1e-4)
+    M = (gi["kf_mask"] * gi["y_mask"].float()).bool()
+    assert torch.equal(outs[2]["pred_xstart"][M], gi["x_obs"][M])  # imputed entries are exactly the observations
+
+
+def test_reconstruction_guidance_matches_reference(samp):
+    gi = _inputs(samp)
+    sdt = O.random_state_dict(seed=7, text=True)
+    c = O.Conditioning(cond_emb=gi["cond"], cfg=True, text_scale=gi["text_scale"], y_mask=gi["y_mask"], imputate=True,
+                       stop_imputation_at=1, inpainted_motion=gi["x_obs"], inpainting_mask=gi["kf_mask"],
+                       reconstruction_guidance=True, reconstruction_weight=20.0)
+    outs = O.sample_loop(sdt, O.make_tables(""), (B, D, 1, L), c, gi["tape"], "ddpm", max_steps=2, return_all=True)
+    assert torch.allclose(outs[-1]["sample"], torch.tensor(samp["recon.sample"]), rtol=1e-4, atol=2e-4)
+    assert torch.allclose(outs[-1]["pred_xstart"], torch.tensor(samp["recon.pred_xstart"]), rtol=1e-4, atol=2e-4)
+
+
+def test_ddim50_full_loop_matches_reference(samp):
+    gi = _inputs(samp)
+    sd = O.random_state_dict(seed=7)
+    tape50 = gi["tape"][torch.arange(51) % 8]
+    out = O.sample_loop(sd, O.make_tables("ddim50"), (B, D, 1, L), O.Conditioning(), tape50, "ddim")
+    assert torch.allclose(out, torch.tensor(samp["ddim50.sample"]), rtol=1e-3, atol=2e-4)
