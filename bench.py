@@ -114,10 +114,34 @@ def dist_env():
     return rank, world, local
 
 
+def usable_cpus() -> int:
+    """Host threads this process may actually use: affinity mask and cgroup CPU quota, not just os.cpu_count()."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as f:
+                parts = f.read().split()
+            if path.endswith("cpu.max"):
+                if parts[0] != "max":
+                    n = min(n, max(1, int(float(parts[0]) / float(parts[1]) + 0.5)))
+            else:
+                quota = int(parts[0])
+                if quota > 0:
+                    with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                        n = min(n, max(1, int(quota / int(f.read()) + 0.5)))
+        except (OSError, ValueError, IndexError):
+            continue
+    return n
+
+
 def cpu_reference_steps(max_steps: int, budget_s: float, warmup: int = 1):
-    """The reference's CPU implementation of one loop iteration at B=64 (pinned restatement, all host threads)."""
+    """The reference's CPU implementation of one loop iteration at B=64 (pinned restatement, all usable host threads)."""
     from oracle import condmdi_oracle as O
-    threads = os.cpu_count() or 1
+    threads = usable_cpus()
     torch.set_num_threads(threads)
     sd = O.random_state_dict(seed=0)
     tab = O.make_tables("")

@@ -86,7 +86,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.cmdi_test_step.argtypes = [c_void_p, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.cmdi_test_normal.argtypes = [c_void_p, c_int, ctypes.c_longlong, c_uint64, c_uint64, c_uint64, c_void_p]
-    lib.cmdi_profile_pass.argtypes = [c_void_p, c_int, c_int, POINTER(c_float), c_int, POINTER(c_int), c_void_p]
+    lib.cmdi_profile_pass.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_float), c_int, POINTER(c_int), c_void_p]
     _lib = lib
     return lib
 

@@ -11,8 +11,13 @@
 // (no head-split or transpose kernels).  With nsplit = 3 every product uses the hi/lo bf16 split
 // (X_lo*Y_hi + X_hi*Y_lo + X_hi*Y_hi), P included, so the result is fp32-accurate.
 //
-// warp 0: TMA producer   warp 1: MMA issuer (+TMEM alloc)   warps 2..5: softmax + output (thread = query row)
+// warp 0: TMA producer   warp 1: MMA issuer (+TMEM alloc)
+// warps 2..9: softmax + output.  Two threads per query row (TMEM lane group = warp % 4, key half = (warp-2)/4):
+//   each keeps its ~104 logits in registers (one TMEM read), the halves exchange row max / row sum through
+//   shared memory, P is written back to TMEM, and O leaves through coalesced 16-byte stores staged in the
+//   (by then free) Q tile region.
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 #include "kernels.h"
 
 namespace cmdi {
@@ -31,15 +36,66 @@ constexpr int kOffKHi = 2 * kQPlane, kOffKLo = kOffKHi + kKVPlane;
 constexpr int kOffVHi = kOffKLo + kKVPlane;
 constexpr int kOffVLo = kOffKHi;                // V_lo reuses the K region once S is complete
 constexpr int kSmemTiles = kOffVHi + kKVPlane;  // 225280
-constexpr int kThreads = 192;
+constexpr int kNumSoftmaxWarps = 8;
+constexpr int kThreads = 64 + kNumSoftmaxWarps * 32;
 // TMEM columns
 constexpr uint32_t kColS = 0, kColPHi = 0, kColPLo = 208, kColO = 320, kTmemCols = 512;
+// key chunks (16 keys each) per half: half 0 -> chunks [0,7), half 1 -> chunks [7,13)
+constexpr int kChunks0 = 7, kChunks1 = 6;
 
 struct __align__(8) AttnBarriers {
-  uint64_t qk_full, vhi_full, vlo_full, s_full, p_full, o_full;
+  uint64_t qk_full[2], vhi_full, vlo_full, s_full, p_full, o_full;
   uint32_t tmem_base;
   uint32_t pad;
+  float red_max[2][128];
+  float red_sum[2][128];
 };
+
+__device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// logits of this thread's key range -> registers, row max, exchange, probabilities -> TMEM, row sum
+template <int CHUNK0, int NCHUNKS>
+__device__ __forceinline__ float softmax_half(uint32_t trow, int S, bool split, float c_scale, AttnBarriers* bars, int half,
+                                              int row) {
+  float s[NCHUNKS * 16];
+#pragma unroll
+  for (int c = 0; c < NCHUNKS; ++c) {
+    uint32_t v[16];
+    tmem_ld16(trow + kColS + (CHUNK0 + c) * 16, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s[c * 16 + j] = __uint_as_float(v[j]);
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NCHUNKS * 16; ++i)
+    if ((CHUNK0 * 16 + i) < S) mx = fmaxf(mx, s[i]);
+  bars->red_max[half][row] = mx;
+  // every S value is in registers now: after this barrier P may overwrite the S columns
+  tc_fence_before();
+  named_barrier_sync(1, kNumSoftmaxWarps * 32);
+  tc_fence_after();
+  mx = fmaxf(bars->red_max[0][row], bars->red_max[1][row]);
+  const float mc = mx * c_scale;
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCHUNKS; ++c) {
+    uint32_t ph[8], pl[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = (CHUNK0 + c) * 16 + j * 2;
+      const float p0 = (col < S) ? exp2f(fmaf(s[c * 16 + j * 2], c_scale, -mc)) : 0.f;
+      const float p1 = (col + 1 < S) ? exp2f(fmaf(s[c * 16 + j * 2 + 1], c_scale, -mc)) : 0.f;
+      sum += p0 + p1;
+      split_bf16x2(p0, p1, ph[j], pl[j]);
+    }
+    tmem_st8(trow + kColPHi + (CHUNK0 + c) * 8, ph);
+    if (split) tmem_st8(trow + kColPLo + (CHUNK0 + c) * 8, pl);
+  }
+  return sum;
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
@@ -62,11 +118,12 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&map_q_hi);
     tma_prefetch_desc(&map_kv_hi);
-    mbar_init(&bars->qk_full, 1);
+    mbar_init(&bars->qk_full[0], 1);
+    mbar_init(&bars->qk_full[1], 1);
     mbar_init(&bars->vhi_full, 1);
     mbar_init(&bars->vlo_full, 1);
     mbar_init(&bars->s_full, 1);
-    mbar_init(&bars->p_full, 128);
+    mbar_init(&bars->p_full, kNumSoftmaxWarps * 32);
     mbar_init(&bars->o_full, 1);
     fence_barrier_init();
   }
@@ -81,14 +138,14 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
 
   if (warp_idx == 0) {
     if (lane == 0) {
-      // Q + K
-      mbar_arrive_expect_tx(&bars->qk_full, (split ? 2 : 1) * (kQPlane + kKVPlane));
+      // Q + K, one barrier per 64-wide head-dim block so the first MMAs start after half the bytes
       for (int j = 0; j < 2; ++j) {
-        tma_load_2d(smem + kOffQHi + j * kQBlockBytes, &map_q_hi, &bars->qk_full, q_col + j * 64, row0 + qtile * kQTile);
-        tma_load_2d(smem + kOffKHi + j * kKVBlockBytes, &map_kv_hi, &bars->qk_full, k_col + j * 64, row0);
+        mbar_arrive_expect_tx(&bars->qk_full[j], (split ? 2 : 1) * (kQBlockBytes + kKVBlockBytes));
+        tma_load_2d(smem + kOffQHi + j * kQBlockBytes, &map_q_hi, &bars->qk_full[j], q_col + j * 64, row0 + qtile * kQTile);
+        tma_load_2d(smem + kOffKHi + j * kKVBlockBytes, &map_kv_hi, &bars->qk_full[j], k_col + j * 64, row0);
         if (split) {
-          tma_load_2d(smem + kOffQLo + j * kQBlockBytes, &map_q_lo, &bars->qk_full, q_col + j * 64, row0 + qtile * kQTile);
-          tma_load_2d(smem + kOffKLo + j * kKVBlockBytes, &map_kv_lo, &bars->qk_full, k_col + j * 64, row0);
+          tma_load_2d(smem + kOffQLo + j * kQBlockBytes, &map_q_lo, &bars->qk_full[j], q_col + j * 64, row0 + qtile * kQTile);
+          tma_load_2d(smem + kOffKLo + j * kKVBlockBytes, &map_kv_lo, &bars->qk_full[j], k_col + j * 64, row0);
         }
       }
       // V_hi (own buffer, lands while S is being computed)
@@ -109,15 +166,15 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
       const uint32_t sbase = smem_u32(smem);
       // ---------------- S = Q K^T ----------------
       constexpr uint32_t idesc_s = make_idesc_bf16(kQTile, kKeyPad, 0);
-      mbar_wait(&bars->qk_full, 0);
-      tc_fence_after();
       uint32_t accum = 0;
       const int nterms = split ? 3 : 1;
-      for (int term = 0; term < nterms; ++term) {
-        // split order: Q_lo*K_hi, Q_hi*K_lo, Q_hi*K_hi ; fast mode: Q_hi*K_hi
-        const uint32_t qo = (split && term == 0) ? kOffQLo : kOffQHi;
-        const uint32_t ko = (split && term == 1) ? kOffKLo : kOffKHi;
-        for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < 2; ++j) {
+        mbar_wait(&bars->qk_full[j], 0);
+        tc_fence_after();
+        for (int term = 0; term < nterms; ++term) {
+          // split order: Q_lo*K_hi, Q_hi*K_lo, Q_hi*K_hi ; fast mode: Q_hi*K_hi
+          const uint32_t qo = (split && term == 0) ? kOffQLo : kOffQHi;
+          const uint32_t ko = (split && term == 1) ? kOffKLo : kOffKHi;
           const uint64_t da = make_desc_kmajor_sw128(sbase + qo + j * kQBlockBytes);
           const uint64_t db = make_desc_kmajor_sw128(sbase + ko + j * kKVBlockBytes);
 #pragma unroll
@@ -159,8 +216,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
     }
     __syncwarp();
   } else {
-    // ---------------- softmax (thread = query row) ----------------
+    // ---------------- softmax: two threads per query row ----------------
+    const int sw = warp_idx - 2;
     const int lane_group = warp_idx & 3;
+    const int half = sw >> 2;
     const int row = lane_group * 32 + lane;
     const int qpos = qtile * kQTile + row;
     const uint32_t trow = tmem_base + ((uint32_t)(lane_group * 32) << 16);
@@ -168,71 +227,41 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
 
     mbar_wait(&bars->s_full, 0);
     tc_fence_after();
-    float mx = -INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < kKeyPad / 16; ++c) {
-      uint32_t v[16];
-      tmem_ld16(trow + kColS + c * 16, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (c * 16 + j < S) mx = fmaxf(mx, __uint_as_float(v[j]));
+    float sum;
+    if (half == 0) {
+      sum = softmax_half<0, kChunks0>(trow, S, split, c_scale, bars, 0, row);
+    } else {
+      sum = softmax_half<kChunks0, kChunks1>(trow, S, split, c_scale, bars, 1, row);
     }
-    const float mc = mx * c_scale;
-    float sum = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < kKeyPad / 16; ++c) {
-      uint32_t v[16];
-      tmem_ld16(trow + kColS + c * 16, v);
-      tmem_ld_wait();
-      uint32_t ph[8], pl[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int col = c * 16 + j * 2;
-        const float p0 = (col < S) ? exp2f(fmaf(__uint_as_float(v[j * 2]), c_scale, -mc)) : 0.f;
-        const float p1 = (col + 1 < S) ? exp2f(fmaf(__uint_as_float(v[j * 2 + 1]), c_scale, -mc)) : 0.f;
-        sum += p0 + p1;
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(p0, h0, l0);
-        split_bf16(p1, h1, l1);
-        ph[j] = pack_bf16x2(h0, h1);
-        pl[j] = pack_bf16x2(l0, l1);
-      }
-      // P_hi aliases S: columns [8c, 8c+8) were consumed in iterations <= c
-      tmem_st8(trow + kColPHi + c * 8, ph);
-      if (split) tmem_st8(trow + kColPLo + c * 8, pl);
-    }
+    bars->red_sum[half][row] = sum;
     tmem_st_wait();
     tc_fence_before();
     mbar_arrive(&bars->p_full);
+    named_barrier_sync(1, kNumSoftmaxWarps * 32);  // red_sum of both halves visible
+    const float inv = 1.0f / (bars->red_sum[0][row] + bars->red_sum[1][row]);
 
-    // ---------------- output ----------------
+    // ---------------- output: this thread's row, 64 of the 128 head-dim columns ----------------
     mbar_wait(&bars->o_full, 0);
     tc_fence_after();
-    const float inv = 1.0f / sum;
+    // all MMAs are complete: the Q tile region is free and becomes the store-staging area (8 x 4 KB)
+    const uint32_t stage = smem_u32(smem + kOffQHi + sw * kEpiStageBytes);
     const bool valid = qpos < S;
-    const size_t orow = (size_t)(row0 + qpos) * p.ld_out + head * kHeadDim;
-#pragma unroll 1
-    for (int c = 0; c < kHeadDim / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(trow + kColO + c * 32, v);
-      tmem_ld_wait();
-      if (valid) {
+    const long long roff = valid ? (long long)(row0 + qpos) * p.ld_out * 2 : 0;
+    uint32_t v0[32], v1[32];
+    tmem_ld32(trow + kColO + half * 64, v0);
+    tmem_ld32(trow + kColO + half * 64 + 32, v1);
+    tmem_ld_wait();
+    uint32_t hw[32], lw[32];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t hw[4], lw[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(__uint_as_float(v[g * 8 + q * 2]) * inv, h0, l0);
-            split_bf16(__uint_as_float(v[g * 8 + q * 2 + 1]) * inv, h1, l1);
-            hw[q] = pack_bf16x2(h0, h1);
-            lw[q] = pack_bf16x2(l0, l1);
-          }
-          st_global_v4(p.out_hi + orow + c * 32 + g * 8, hw[0], hw[1], hw[2], hw[3]);
-          if (p.nsplit_out == 3) st_global_v4(p.out_lo + orow + c * 32 + g * 8, lw[0], lw[1], lw[2], lw[3]);
-        }
-      }
+    for (int j = 0; j < 16; ++j) {
+      split_bf16x2(__uint_as_float(v0[2 * j]) * inv, __uint_as_float(v0[2 * j + 1]) * inv, hw[j], lw[j]);
+      split_bf16x2(__uint_as_float(v1[2 * j]) * inv, __uint_as_float(v1[2 * j + 1]) * inv, hw[16 + j], lw[16 + j]);
+    }
+    char* dst_hi = reinterpret_cast<char*>(p.out_hi + head * kHeadDim + half * 64);
+    store_block_coalesced(stage, lane, hw, dst_hi, roff, valid, 8, 1, 0);
+    if (p.nsplit_out == 3) {
+      char* dst_lo = reinterpret_cast<char*>(p.out_lo + head * kHeadDim + half * 64);
+      store_block_coalesced(stage, lane, lw, dst_lo, roff, valid, 8, 1, 0);
     }
   }
 

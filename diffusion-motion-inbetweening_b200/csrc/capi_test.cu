@@ -50,7 +50,8 @@ int num_sms_of_current_device() {
 extern "C" int cmdi_test_linear(const float* A, const float* W, const float* bias, const float* residual, float* C, int M,
                                 int N, int K, int act, int precision, int block_n, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const int Kp = round_up(K, 8), Mp = round_up(M, 128), Np = round_up(N, block_n);
+  const int bn_abs = block_n < 0 ? -block_n : block_n;
+  const int Kp = round_up(K, 8), Mp = round_up(M, 256), Np = round_up(N, bn_abs);
   DevBuf a_hi, a_lo, w_hi, w_lo;
   CK(a_hi.alloc((size_t)Mp * Kp * 2));
   CK(a_lo.alloc((size_t)Mp * Kp * 2));
@@ -58,11 +59,13 @@ extern "C" int cmdi_test_linear(const float* A, const float* W, const float* bia
   CK(w_lo.alloc((size_t)Np * Kp * 2));
   CK(launch_split_planes(A, M, K, K, a_hi.as<__nv_bfloat16>(), a_lo.as<__nv_bfloat16>(), Kp, stream));
   CK(launch_split_planes(W, N, K, K, w_hi.as<__nv_bfloat16>(), w_lo.as<__nv_bfloat16>(), Kp, stream));
+  const bool pair = block_n < 0;  // negative block_n selects the CTA-pair kernel
+  if (pair) block_n = -block_n;
   CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
   if (make_tmap_bf16_2d(&ma_hi, a_hi.p, Mp, Kp, Kp, 64, 128)) return 1;
   if (make_tmap_bf16_2d(&ma_lo, a_lo.p, Mp, Kp, Kp, 64, 128)) return 1;
-  if (make_tmap_bf16_2d(&mw_hi, w_hi.p, Np, Kp, Kp, 64, block_n)) return 1;
-  if (make_tmap_bf16_2d(&mw_lo, w_lo.p, Np, Kp, Kp, 64, block_n)) return 1;
+  if (make_tmap_bf16_2d(&mw_hi, w_hi.p, Np, Kp, Kp, 64, pair ? block_n / 2 : block_n)) return 1;
+  if (make_tmap_bf16_2d(&mw_lo, w_lo.p, Np, Kp, Kp, 64, pair ? block_n / 2 : block_n)) return 1;
   CK(configure_linear_kernels());
   LinearParams p{};
   p.M = M; p.N = N; p.K = K; p.nsplit = precision;
@@ -70,7 +73,12 @@ extern "C" int cmdi_test_linear(const float* A, const float* W, const float* bia
   p.act = act; p.rowmap = ROWMAP_IDENTITY;
   p.out_f32 = C; p.ld_f32 = N;
   p.nsplit_out = precision;
-  CK(launch_linear(ma_hi, ma_lo, mw_hi, mw_lo, p, block_n, num_sms_of_current_device(), stream));
+  if (pair) {
+    CK(configure_linear2_kernels());
+    CK(launch_linear_pair(ma_hi, ma_lo, mw_hi, mw_lo, p, block_n, num_sms_of_current_device(), stream));
+  } else {
+    CK(launch_linear(ma_hi, ma_lo, mw_hi, mw_lo, p, block_n, num_sms_of_current_device(), stream));
+  }
   CK(cudaStreamSynchronize(stream));  // staging buffers are freed on return
   return 0;
 }

@@ -135,27 +135,37 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
-// standard normal for flat element index `idx` of sample `sample` on stream `stream_id`
+// four standard normals for the flat element indices 4*q .. 4*q+3 of sample `sample` on stream `stream_id`
+__device__ __forceinline__ void philox_normal4(unsigned long long seed, unsigned long long stream_id, unsigned long long sample,
+                                               unsigned long long q, float (&out)[4]) {
+  const uint4 ctr = make_uint4((uint32_t)q, (uint32_t)sample, (uint32_t)stream_id,
+                               (uint32_t)((q >> 32) | ((sample >> 32) << 8) | ((stream_id >> 32) << 20)));
+  const uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float rad0 = sqrtf(-2.0f * logf(u01(r.x))), rad1 = sqrtf(-2.0f * logf(u01(r.z)));
+  float s0, c0, s1, c1;
+  sincospif(2.0f * u01(r.y), &s0, &c0);
+  sincospif(2.0f * u01(r.w), &s1, &c1);
+  out[0] = rad0 * c0; out[1] = rad0 * s0; out[2] = rad1 * c1; out[3] = rad1 * s1;
+}
+// standard normal for flat element index `idx` (element idx & 3 of its quad)
 __device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned long long stream_id,
                                                unsigned long long sample, unsigned long long idx) {
-  const uint4 ctr = make_uint4((uint32_t)(idx >> 2), (uint32_t)sample, (uint32_t)stream_id,
-                               (uint32_t)((idx >> 34) | ((sample >> 32) << 8) | ((stream_id >> 32) << 20)));
-  const uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const int lane = (int)(idx & 3);
-  const uint32_t a = (lane & 2) ? r.z : r.x;
-  const uint32_t b = (lane & 2) ? r.w : r.y;
-  const float rad = sqrtf(-2.0f * logf(u01(a)));
-  float sn, cs;
-  sincospif(2.0f * u01(b), &sn, &cs);
-  return rad * ((lane & 1) ? sn : cs);
+  float v[4];
+  philox_normal4(seed, stream_id, sample, idx >> 2, v);
+  return v[idx & 3];
 }
 
 __global__ void fill_normal_ref_kernel(float* out, int B, size_t per_sample, unsigned long long seed,
                                        unsigned long long stream_id, unsigned long long sample_offset) {
-  const size_t total = (size_t)B * per_sample;
+  const size_t quads = (per_sample + 3) / 4;
+  const size_t total = (size_t)B * quads;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t b = i / per_sample, e = i - b * per_sample;
-    out[i] = philox_normal(seed, stream_id, sample_offset + b, e);
+    const size_t b = i / quads, q = i - b * quads;
+    float v[4];
+    philox_normal4(seed, stream_id, sample_offset + b, q, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (q * 4 + j < per_sample) out[b * per_sample + q * 4 + j] = v[j];
   }
 }
 
@@ -174,16 +184,27 @@ __global__ void __launch_bounds__(256) diffusion_step_kernel(const StepParams p)
   // ---- noise tile (reference layout [b][c][l], l contiguous) ----
   const bool want_noise = p.sampler != 2;  // the reference draws noise at every step, including t == 0
   if (want_noise) {
+    if (!p.noise_ref && (p.L & 3) == 0) {
+      // engine generator: one Philox call yields the 4 consecutive frames of a quad (l0 and L are multiples of 4)
+      const int q = ty * 32 + tx;          // 256 quads = 32 features x 8 frame-quads
+      const int cl = q >> 3, lq = (q & 7) * 4;
+      const int c = c0 + cl, l = l0 + lq;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (c < p.D && l < p.L) philox_normal4(p.seed, (unsigned long long)(t + 1), p.sample_offset + b, ((size_t)c * p.L + l) >> 2, v);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = c0 + ty + i * 8, l = l0 + tx;
-      float nz = 0.f;
-      if (c < p.D && l < p.L) {
-        const size_t e = (size_t)c * p.L + l;
-        nz = p.noise_ref ? p.noise_ref[((size_t)(p.tape_t0 - t) * p.B + b) * p.D * p.L + e]
-                         : philox_normal(p.seed, (unsigned long long)(t + 1), p.sample_offset + b, e);
+      for (int j = 0; j < 4; ++j) s_noise[cl][lq + j] = v[j];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + i * 8, l = l0 + tx;
+        float nz = 0.f;
+        if (c < p.D && l < p.L) {
+          const size_t e = (size_t)c * p.L + l;
+          nz = p.noise_ref ? p.noise_ref[((size_t)(p.tape_t0 - t) * p.B + b) * p.D * p.L + e]
+                           : philox_normal(p.seed, (unsigned long long)(t + 1), p.sample_offset + b, e);
+        }
+        s_noise[ty + i * 8][tx] = nz;
       }
-      s_noise[ty + i * 8][tx] = nz;
     }
   }
   __syncthreads();

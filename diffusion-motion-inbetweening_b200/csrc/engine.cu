@@ -12,6 +12,7 @@
 // every step of a loop with no host work in between (reference: one Python iteration + ~150 PyTorch ops
 // + several H2D table copies per step, gaussian_diffusion.py:1270-1297, :2225, respace.py:129).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -48,6 +49,7 @@ struct Planes {  // a bf16 hi/lo operand: [rows, ld] row-major, with TMA maps fo
   __nv_bfloat16* lo = nullptr;
   int rows = 0, cols = 0, ld = 0;
   CUtensorMap map_hi{}, map_lo{};
+  CUtensorMap pair_hi{}, pair_lo{};  // same planes, box height halved: W operand of the CTA-pair kernel
 };
 
 struct LayerW {
@@ -71,6 +73,8 @@ struct cmdi_engine {
   cmdi_model_cfg cfg{};
   int device = 0, num_sms = 148;
   int nsplit = 3;
+  int debug = 0, bn_wide = kBnWide, bn_narrow = kBnNarrow;  // CMDI_DEBUG / CMDI_BN_WIDE / CMDI_BN_NARROW (bring-up knobs)
+  bool use_pair = true;  // CTA-pair (cta_group::2) linear kernels; CMDI_GEMM=single selects the 1-CTA kernels
   int D = 263, D_pad = 264, L = 196, S = 197, ff = 1024, H = 4, layers = 8, maxB = 0;
   int max_seqs = 0, seq_rows = 0, seq_rows_pad = 0, frame_rows = 0, frame_rows_pad = 0;
   std::vector<void*> allocs;
@@ -125,6 +129,8 @@ int alloc_planes(cmdi_engine* e, Planes* pl, int rows, int cols, int ld, int box
   CKI(dev_alloc(e, &pl->lo, (size_t)rows * ld));
   CKI(make_tmap_bf16_2d(&pl->map_hi, pl->hi, rows, cols, ld, 64, box_rows));
   CKI(make_tmap_bf16_2d(&pl->map_lo, pl->lo, rows, cols, ld, 64, box_rows));
+  CKI(make_tmap_bf16_2d(&pl->pair_hi, pl->hi, rows, cols, ld, 64, box_rows / 2));
+  CKI(make_tmap_bf16_2d(&pl->pair_lo, pl->lo, rows, cols, ld, 64, box_rows / 2));
   return 0;
 }
 
@@ -164,10 +170,21 @@ int ensure_temb(cmdi_engine* e, cudaStream_t s) {
   return 0;
 }
 
+int run_linear(cmdi_engine* e, const Planes& a, const Planes& w, const LinearParams& p_in, int block_n, cudaStream_t s) {
+  LinearParams p = p_in;
+  p.debug = e->debug;
+  if (e->use_pair) {
+    CK(launch_linear_pair(a.map_hi, a.map_lo, w.pair_hi, w.pair_lo, p, block_n, e->num_sms, s));
+  } else {
+    CK(launch_linear(a.map_hi, a.map_lo, w.map_hi, w.map_lo, p, block_n, e->num_sms, s));
+  }
+  return 0;
+}
+
 // One denoiser pass over `nseq` sequences whose frame features are in x_state planes (first B sequences;
 // with dup the frame embedding is written for sequences [0,B) and [B,2B)).
 int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond, const int* tmap_dev, cudaStream_t s,
-                 std::vector<cudaEvent_t>* evs = nullptr) {
+                 std::vector<cudaEvent_t>* evs = nullptr, int reps = 1) {
   auto mark = [&]() -> int {
     if (!evs) return 0;
     cudaEvent_t ev;
@@ -184,7 +201,7 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
   tk.cond_proj = has_cond ? e->cond_proj : nullptr; tk.uncond_proj = has_cond ? e->et_b : nullptr;
   tk.pe0 = e->pe; tk.num_seqs = nseq; tk.n_cond_seqs = n_cond_seqs; tk.seq_len = e->S;
   tk.x_f32 = e->xseq; tk.x_hi = e->xseq_p.hi; tk.x_lo = e->xseq_p.lo;
-  CK(launch_token_rows(tk, s));
+  for (int r_ = 0; r_ < reps; ++r_) CK(launch_token_rows(tk, s));
   CKI(mark());
 
   LinearParams p{};
@@ -193,7 +210,7 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
   p.rowmap = ROWMAP_FRAMES_TO_SEQ; p.frames = e->L; p.dup_row_offset = dup ? B * e->S : 0;
   p.out_f32 = e->xseq; p.ld_f32 = kDModel; p.out_hi = e->xseq_p.hi; p.out_lo = e->xseq_p.lo; p.ld_bf = kDModel;
   p.nsplit_out = e->nsplit;
-  CK(launch_linear(e->x_state_p.map_hi, e->x_state_p.map_lo, e->w_in.map_hi, e->w_in.map_lo, p, kBnNarrow, e->num_sms, s));
+  for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->x_state_p, e->w_in, p, kBnNarrow, s));
   CKI(mark());
 
   for (int l = 0; l < e->layers; ++l) {
@@ -202,41 +219,41 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
     LinearParams q{};
     q.M = M; q.N = 3 * kDModel; q.K = kDModel; q.nsplit = e->nsplit; q.bias = w.bqkv;
     q.out_hi = e->qkv_p.hi; q.out_lo = e->qkv_p.lo; q.ld_bf = 3 * kDModel; q.nsplit_out = e->nsplit;
-    CK(launch_linear(e->xseq_p.map_hi, e->xseq_p.map_lo, w.wqkv.map_hi, w.wqkv.map_lo, q, kBnWide, e->num_sms, s));
+    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->xseq_p, w.wqkv, q, kBnWide, s));
     CKI(mark());
     // attention core
     AttnParams a{};
     a.num_seqs = nseq; a.seq_len = e->S; a.num_heads = e->H; a.nsplit = e->nsplit; a.nsplit_out = e->nsplit;
     a.out_hi = e->attn_p.hi; a.out_lo = e->attn_p.lo; a.ld_out = kDModel;
-    CK(launch_attention(e->q_map_hi, e->q_map_lo, e->kv_map_hi, e->kv_map_lo, a, s));
+    for (int r_ = 0; r_ < reps; ++r_) CK(launch_attention(e->q_map_hi, e->q_map_lo, e->kv_map_hi, e->kv_map_lo, a, s));
     CKI(mark());
     // out-proj + residual, then LayerNorm1
     LinearParams o{};
     o.M = M; o.N = kDModel; o.K = kDModel; o.nsplit = e->nsplit; o.bias = w.bo; o.residual = e->xseq; o.ld_res = kDModel;
     o.out_f32 = e->vsum; o.ld_f32 = kDModel; o.nsplit_out = e->nsplit;
-    CK(launch_linear(e->attn_p.map_hi, e->attn_p.map_lo, w.wo.map_hi, w.wo.map_lo, o, kBnNarrow, e->num_sms, s));
+    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->attn_p, w.wo, o, kBnNarrow, s));
     CKI(mark());
-    CK(launch_layernorm512(e->vsum, w.g1, w.be1, 1e-5f, M, e->x1, e->x1_p.hi, e->nsplit == 3 ? e->x1_p.lo : nullptr, s));
+    for (int r_ = 0; r_ < reps; ++r_) CK(launch_layernorm512(e->vsum, w.g1, w.be1, 1e-5f, M, e->x1, e->x1_p.hi, e->nsplit == 3 ? e->x1_p.lo : nullptr, s));
     CKI(mark());
     // FFN
     LinearParams f1{};
     f1.M = M; f1.N = e->ff; f1.K = kDModel; f1.nsplit = e->nsplit; f1.bias = w.b1; f1.act = 1;
     f1.out_hi = e->ffh_p.hi; f1.out_lo = e->ffh_p.lo; f1.ld_bf = e->ff; f1.nsplit_out = e->nsplit;
-    CK(launch_linear(e->x1_p.map_hi, e->x1_p.map_lo, w.w1.map_hi, w.w1.map_lo, f1, kBnWide, e->num_sms, s));
+    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->x1_p, w.w1, f1, kBnWide, s));
     CKI(mark());
     LinearParams f2{};
     f2.M = M; f2.N = kDModel; f2.K = e->ff; f2.nsplit = e->nsplit; f2.bias = w.b2; f2.residual = e->x1; f2.ld_res = kDModel;
     f2.out_f32 = e->vsum; f2.ld_f32 = kDModel; f2.nsplit_out = e->nsplit;
-    CK(launch_linear(e->ffh_p.map_hi, e->ffh_p.map_lo, w.w2.map_hi, w.w2.map_lo, f2, kBnNarrow, e->num_sms, s));
+    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->ffh_p, w.w2, f2, kBnNarrow, s));
     CKI(mark());
-    CK(launch_layernorm512(e->vsum, w.g2, w.be2, 1e-5f, M, e->xseq, e->xseq_p.hi, e->nsplit == 3 ? e->xseq_p.lo : nullptr, s));
+    for (int r_ = 0; r_ < reps; ++r_) CK(launch_layernorm512(e->vsum, w.g2, w.be2, 1e-5f, M, e->xseq, e->xseq_p.hi, e->nsplit == 3 ? e->xseq_p.lo : nullptr, s));
     CKI(mark());
   }
   // output head on tokens 1.. (mdm.py:284 "[1:]", :304-305)
   LinearParams h{};
   h.M = M; h.N = e->D_pad; h.K = kDModel; h.nsplit = e->nsplit; h.bias = e->b_out;
   h.rowmap = ROWMAP_SEQ_TO_FRAMES; h.frames = e->L; h.out_f32 = e->model_out; h.ld_f32 = e->D_pad; h.nsplit_out = e->nsplit;
-  CK(launch_linear(e->xseq_p.map_hi, e->xseq_p.map_lo, e->w_out.map_hi, e->w_out.map_lo, h, kBnNarrow, e->num_sms, s));
+  for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->xseq_p, e->w_out, h, kBnNarrow, s));
   CKI(mark());
   return 0;
 }
@@ -287,8 +304,11 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
     return 1;
   }
   CK(configure_linear_kernels());
+  CK(configure_linear2_kernels());
   CK(configure_attention_kernel());
   cmdi_engine* e = new cmdi_engine();
+  if (const char* g = getenv("CMDI_GEMM")) e->use_pair = strcmp(g, "single") != 0;
+  if (const char* g = getenv("CMDI_DEBUG")) e->debug = atoi(g);
   e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount; e->nsplit = cfg->precision;
   e->D = cfg->njoints; e->D_pad = round_up(cfg->njoints, 8); e->L = cfg->nframes; e->S = cfg->nframes + 1;
   e->ff = cfg->ff_size; e->H = cfg->num_heads; e->layers = cfg->num_layers; e->maxB = cfg->max_batch;
@@ -789,9 +809,10 @@ extern "C" int cmdi_test_step(cmdi_engine* e, int sampler, float eta, int t, int
 }
 
 // Per-kernel device times of one denoiser pass (plain launches with CUDA events between them, on the caller's
-// stream): ms[i] is the i-th launch of the pass in order
+// stream; each launch is issued `repeats` times back to back and the mean is reported, which hides the host's
+// launch latency behind queued work): ms[i] is the i-th launch of the pass in order
 //   token_rows, frame_embed, {qkv, attention, out_proj, ln1, ffn1, ffn2, ln2} x layers, out_head.
-extern "C" int cmdi_profile_pass(cmdi_engine* e, int batch, int cfg, float* ms, int capacity, int* count, void* stream_) {
+extern "C" int cmdi_profile_pass(cmdi_engine* e, int batch, int cfg, int repeats, float* ms, int capacity, int* count, void* stream_) {
   if (!e || !ms || !count) {
     set_last_error("null argument");
     return 1;
@@ -807,16 +828,20 @@ extern "C" int cmdi_profile_pass(cmdi_engine* e, int batch, int cfg, float* ms, 
     set_last_error("cfg profiling needs a text model");
     return 1;
   }
-  const int rc = run_denoiser(e, batch, cfg != 0, batch, has_cond, nullptr, s, &evs);
+  if (repeats < 1) repeats = 1;
+  const int rc = run_denoiser(e, batch, cfg != 0, batch, has_cond, nullptr, s, &evs, repeats);
   cudaError_t se = cudaStreamSynchronize(s);
   int n = (int)evs.size() - 1;
   if (rc == 0 && se == cudaSuccess) {
     *count = n;
-    for (int i = 0; i < n && i < capacity; ++i) cudaEventElapsedTime(&ms[i], evs[i], evs[i + 1]);
+    for (int i = 0; i < n && i < capacity; ++i) {
+      cudaEventElapsedTime(&ms[i], evs[i], evs[i + 1]);
+      ms[i] /= (float)repeats;
+    }
   }
   for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
   if (rc) return 1;
   CK(se);
-  e->launches += launches_per_pass(e);
+  e->launches += (int64_t)launches_per_pass(e) * repeats;
   return 0;
 }

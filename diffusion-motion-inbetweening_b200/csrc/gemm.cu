@@ -22,6 +22,7 @@
 // The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps
 // the MMAs of tile i+1.
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 #include "kernels.h"
 
 namespace cmdi {
@@ -46,8 +47,6 @@ struct __align__(8) PipeBarriers {
   uint32_t pad;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kNumThreads, 1)
 linear_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -62,7 +61,8 @@ linear_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 
   const int nplanes = (p.nsplit == 3) ? 2 : 1;
   const uint32_t stage_bytes = nplanes * (kABytes + kBBytes);
-  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + (size_t)num_stages * stage_bytes);
+  uint8_t* epi_stage = smem + (size_t)num_stages * stage_bytes;  // kNumEpiWarps x 4 KB store-staging tiles
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(epi_stage + kNumEpiWarps * kEpiStageBytes);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -107,6 +107,11 @@ linear_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
           mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           uint8_t* sb = sa + nplanes * kABytes;
+          if (p.debug & 4) {
+            mbar_arrive(&bars->full[stage]);
+            if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&bars->full[stage], stage_bytes);
           tma_load_2d(sa, &map_a_hi, &bars->full[stage], kb * kBlockK, m_blk * kBlockM);
           tma_load_2d(sb, &map_w_hi, &bars->full[stage], kb * kBlockK, n_blk * BLOCK_N);
@@ -141,7 +146,9 @@ linear_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
           const uint32_t sb = sa + nplanes * kABytes;
           const uint64_t da_hi = make_desc_kmajor_sw128(sa);
           const uint64_t db_hi = make_desc_kmajor_sw128(sb);
-          if (nplanes == 2) {
+          if (p.debug & 2) {
+            // no MMAs: only the pipeline bookkeeping
+          } else if (nplanes == 2) {
             const uint64_t da_lo = make_desc_kmajor_sw128(sa + kABytes);
             const uint64_t db_lo = make_desc_kmajor_sw128(sb + kBBytes);
             // small cross terms first, the dominant hi*hi term last
@@ -177,8 +184,8 @@ linear_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     // ======================================= epilogue =======================================
     const int epi = warp_idx - 2;
     const int lane_group = warp_idx & 3;  // TMEM lanes this warp may touch: 32*lane_group ..
-    const int col_part = epi >> 2;        // which half of the tile's columns
-    constexpr int kColsPerPart = BLOCK_N / 2;
+    const int col_part = epi >> 2;
+    const uint32_t epi_stage_addr = smem_u32(epi_stage + epi * kEpiStageBytes);        // which half of the tile's columns
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -187,88 +194,7 @@ linear_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
 
-      const int a_row = m_blk * kBlockM + lane_group * 32 + lane;
-      bool valid = a_row < p.M;
-      long long out_row = a_row;
-      int pos = 0;  // sequence position for the positional-encoding add
-      if (p.rowmap == ROWMAP_FRAMES_TO_SEQ) {
-        const int b = a_row / p.frames;
-        const int l = a_row - b * p.frames;
-        out_row = (long long)b * (p.frames + 1) + l + 1;
-        pos = l + 1;
-      } else if (p.rowmap == ROWMAP_SEQ_TO_FRAMES) {
-        const int S = p.frames + 1;
-        const int b = a_row / S;
-        const int s = a_row - b * S;
-        valid = valid && (s > 0);
-        out_row = (long long)b * p.frames + (s - 1);
-      }
-
-#pragma unroll 1
-      for (int c = 0; c < kColsPerPart / 32; ++c) {
-        const int col_in_tile = col_part * kColsPerPart + c * 32;
-        uint32_t v[32];
-        tmem_ld32(tmem_addr(tmem_base, lane_group * 32, acc * BLOCK_N + col_in_tile), v);
-        tmem_ld_wait();
-        const int n0 = n_blk * BLOCK_N + col_in_tile;
-        if (valid && n0 < p.N) {
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const int n = n0 + g * 4;
-            if (n < p.N) {
-              if (p.bias) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                f[g * 4 + 0] += bv.x; f[g * 4 + 1] += bv.y; f[g * 4 + 2] += bv.z; f[g * 4 + 3] += bv.w;
-              }
-              if (p.pos_enc) {
-                const float4 pv = __ldg(reinterpret_cast<const float4*>(p.pos_enc + (size_t)pos * p.N + n));
-                f[g * 4 + 0] += pv.x; f[g * 4 + 1] += pv.y; f[g * 4 + 2] += pv.z; f[g * 4 + 3] += pv.w;
-              }
-              if (p.residual) {
-                const float4 rv = *reinterpret_cast<const float4*>(p.residual + (size_t)out_row * p.ld_res + n);
-                f[g * 4 + 0] += rv.x; f[g * 4 + 1] += rv.y; f[g * 4 + 2] += rv.z; f[g * 4 + 3] += rv.w;
-              }
-              if (p.act == 1) {
-                f[g * 4 + 0] = gelu_erf(f[g * 4 + 0]); f[g * 4 + 1] = gelu_erf(f[g * 4 + 1]);
-                f[g * 4 + 2] = gelu_erf(f[g * 4 + 2]); f[g * 4 + 3] = gelu_erf(f[g * 4 + 3]);
-              }
-            }
-          }
-          const int ncopies = (p.dup_row_offset > 0) ? 2 : 1;
-          for (int cp = 0; cp < ncopies; ++cp) {
-            const long long orow = out_row + (long long)cp * p.dup_row_offset;
-            if (p.out_f32) {
-              float* dst = p.out_f32 + (size_t)orow * p.ld_f32 + n0;
-#pragma unroll
-              for (int g = 0; g < 8; ++g)
-                if (n0 + g * 4 < p.N) st_global_v4f(dst + g * 4, f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-            }
-            if (p.out_hi) {
-              __nv_bfloat16* dh = p.out_hi + (size_t)orow * p.ld_bf + n0;
-              __nv_bfloat16* dl = (p.nsplit_out == 3) ? p.out_lo + (size_t)orow * p.ld_bf + n0 : nullptr;
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if (n0 + g * 8 < p.N) {
-                  uint32_t hw[4], lw[4];
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    __nv_bfloat16 h0, l0, h1, l1;
-                    split_bf16(f[g * 8 + q * 2], h0, l0);
-                    split_bf16(f[g * 8 + q * 2 + 1], h1, l1);
-                    hw[q] = pack_bf16x2(h0, h1);
-                    lw[q] = pack_bf16x2(l0, l1);
-                  }
-                  st_global_v4(dh + g * 8, hw[0], hw[1], hw[2], hw[3]);
-                  if (dl) st_global_v4(dl + g * 8, lw[0], lw[1], lw[2], lw[3]);
-                }
-              }
-            }
-          }
-        }
-      }
+      epilogue_tile<BLOCK_N>(p, tmem_base, acc, m_blk, n_blk, lane_group, col_part, lane, epi_stage_addr);
       // accumulator buffer drained -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -292,9 +218,9 @@ cudaError_t launch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const 
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   const int nplanes = (p.nsplit == 3) ? 2 : 1;
   const int stage_bytes = nplanes * (kABytes + kBBytes);
-  int num_stages = (kSmemLimit - 1024 - (int)sizeof(PipeBarriers)) / stage_bytes;
+  int num_stages = (kSmemLimit - 1024 - kNumEpiWarps * kEpiStageBytes - (int)sizeof(PipeBarriers)) / stage_bytes;
   if (num_stages > kMaxStages) num_stages = kMaxStages;
-  const size_t smem = 1024 + (size_t)num_stages * stage_bytes + sizeof(PipeBarriers);
+  const size_t smem = 1024 + (size_t)num_stages * stage_bytes + kNumEpiWarps * kEpiStageBytes + sizeof(PipeBarriers);
   const int num_m_blocks = (p.M + kBlockM - 1) / kBlockM;
   const int num_n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m_blocks * num_n_blocks;

@@ -1,0 +1,245 @@
+// CTA-pair version of the linear layers: two SMs of a cluster share one 256 x BLOCK_N output tile
+// (tcgen05.mma.cta_group::2, M = 256).
+//
+// Why: with one CTA per tile the operand traffic is 128*64 (A) + BLOCK_N*64 (W) elements per k-block for
+// 128 x BLOCK_N x 64 MACs; at B=64 the QKV GEMM then pulls ~460 MB through L2->SM per launch and is bound by
+// that (profiles/r01: 15% of tensor peak).  In pair mode each CTA loads its own 128 A rows but only HALF of the
+// W tile (the MMA reads the other half from the peer's shared memory), so the same MACs need 1.5x fewer bytes
+// from L2, the smem ring is 64 KB/stage (3 stages instead of 2) and W is read from smem once per pair.
+//
+// Protocol (both CTAs run the same code; rank 0 is the leader):
+//   full[s]       lives on the leader: 1 arrival (leader's arrive.expect_tx for BOTH CTAs' bytes) + complete_tx from
+//                 the TMA loads of both CTAs (cp.async.bulk.tensor ... cta_group::2 targets the leader's barrier)
+//   empty[s]      per CTA, signalled by the leader's tcgen05.commit multicast to both CTAs
+//   tmem_full[a]  per CTA, same multicast commit
+//   tmem_empty[a] on the leader: epilogue warps of BOTH CTAs arrive on it (remote arrive from the peer)
+#include "common.cuh"
+#include "gemm_epilogue.cuh"
+#include "kernels.h"
+
+namespace cmdi {
+
+namespace {
+
+constexpr int kBlockM = 128;  // per CTA; 256 per pair
+constexpr int kBlockK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kNumEpiWarps = 8;
+constexpr int kNumThreads = 64 + kNumEpiWarps * 32;
+constexpr int kMaxStages = 8;
+constexpr int kSmemLimit = 232448;
+constexpr int kABytes = kBlockM * kBlockK * 2;
+
+struct __align__(8) PairBarriers {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+               const LinearParams p, const int num_stages, const int num_m_pairs, const int num_n_blocks) {
+  constexpr int kHalfN = BLOCK_N / 2;               // W rows this CTA loads
+  constexpr int kBBytes = kHalfN * kBlockK * 2;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N;       // double-buffered accumulator: 128 lanes x BLOCK_N fp32 each
+  static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int nplanes = (p.nsplit == 3) ? 2 : 1;
+  const uint32_t stage_bytes = nplanes * (kABytes + kBBytes);
+  uint8_t* epi_stage = smem + (size_t)num_stages * stage_bytes;  // kNumEpiWarps x 4 KB store-staging tiles
+  PairBarriers* bars = reinterpret_cast<PairBarriers*>(epi_stage + kNumEpiWarps * kEpiStageBytes);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_tiles = num_m_pairs * num_n_blocks;
+  const int num_k_blocks = (p.K + kBlockK - 1) / kBlockK;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_w_hi);
+    for (int s = 0; s < num_stages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->tmem_full[s], 1);
+      mbar_init(&bars->tmem_empty[s], 2 * kNumEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    tmem_alloc_2sm(&bars->tmem_base, kTmemCols);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits + TMEM allocation visible to both CTAs
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp_idx == 0) {
+    // ===================================== TMA producer (both CTAs) =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = 2 * (tile / num_n_blocks) + (int)cta_rank;
+        const int n_blk = tile % num_n_blocks;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          uint8_t* sb = sa + nplanes * kABytes;
+          if (p.debug & 4) {
+            if (leader) mbar_arrive(&bars->full[stage]);
+            if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          if (leader) mbar_arrive_expect_tx(&bars->full[stage], 2 * stage_bytes);
+          tma_load_2d_2sm(sa, &map_a_hi, &bars->full[stage], kb * kBlockK, m_blk * kBlockM);
+          tma_load_2d_2sm(sb, &map_w_hi, &bars->full[stage], kb * kBlockK, n_blk * BLOCK_N + (int)cta_rank * kHalfN);
+          if (nplanes == 2) {
+            tma_load_2d_2sm(sa + kABytes, &map_a_lo, &bars->full[stage], kb * kBlockK, m_blk * kBlockM);
+            tma_load_2d_2sm(sb + kBBytes, &map_w_lo, &bars->full[stage], kb * kBlockK, n_blk * BLOCK_N + (int)cta_rank * kHalfN);
+          }
+          if (++stage == num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx == 1) {
+    // ====================================== MMA issuer (leader CTA only) ======================================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * kBlockM, BLOCK_N, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + nplanes * kABytes;
+          const uint64_t da_hi = make_desc_kmajor_sw128(sa);
+          const uint64_t db_hi = make_desc_kmajor_sw128(sb);
+          if (p.debug & 2) {
+            // no MMAs: only the pipeline bookkeeping
+          } else if (nplanes == 2) {
+            const uint64_t da_lo = make_desc_kmajor_sw128(sa + kABytes);
+            const uint64_t db_lo = make_desc_kmajor_sw128(sb + kBBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_ss_2sm(d_tmem, desc_advance(da_lo, k * kUmmaK * 2), desc_advance(db_hi, k * kUmmaK * 2), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_ss_2sm(d_tmem, desc_advance(da_hi, k * kUmmaK * 2), desc_advance(db_lo, k * kUmmaK * 2), idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_ss_2sm(d_tmem, desc_advance(da_hi, k * kUmmaK * 2), desc_advance(db_hi, k * kUmmaK * 2), idesc, 1u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_ss_2sm(d_tmem, desc_advance(da_hi, k * kUmmaK * 2), desc_advance(db_hi, k * kUmmaK * 2), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&bars->empty[stage], 0x3);  // frees the slot in BOTH CTAs
+          if (++stage == num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&bars->tmem_full[acc], 0x3);  // both CTAs' epilogues may read their half of the tile
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================================= epilogue (both CTAs, own 128 rows) =======================================
+    const int epi = warp_idx - 2;
+    const int lane_group = warp_idx & 3;
+    const int col_part = epi >> 2;
+    const uint32_t epi_stage_addr = smem_u32(epi_stage + epi * kEpiStageBytes);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = 2 * (tile / num_n_blocks) + (int)cta_rank;
+      const int n_blk = tile % num_n_blocks;
+      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      epilogue_tile<BLOCK_N>(p, tmem_base, acc, m_blk, n_blk, lane_group, col_part, lane, epi_stage_addr);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_on_leader(&bars->tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody touches the pair's TMEM / barriers after this point
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, kTmemCols);
+  }
+}
+
+template <int BLOCK_N>
+cudaError_t launch_impl2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+                         const LinearParams& p, int num_sms, cudaStream_t stream) {
+  constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;
+  const int nplanes = (p.nsplit == 3) ? 2 : 1;
+  const int stage_bytes = nplanes * (kABytes + kBBytes);
+  int num_stages = (kSmemLimit - 1024 - kNumEpiWarps * kEpiStageBytes - (int)sizeof(PairBarriers)) / stage_bytes;
+  if (num_stages > kMaxStages) num_stages = kMaxStages;
+  const size_t smem = 1024 + (size_t)num_stages * stage_bytes + kNumEpiWarps * kEpiStageBytes + sizeof(PairBarriers);
+  const int num_m_pairs = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);
+  const int num_n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m_pairs * num_n_blocks;
+  int clusters = num_sms / 2;
+  if (clusters > num_tiles) clusters = num_tiles;
+  linear2_kernel<BLOCK_N><<<2 * clusters, kNumThreads, smem, stream>>>(a_hi, a_lo, w_hi, w_lo, p, num_stages, num_m_pairs,
+                                                                      num_n_blocks);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t configure_linear2_kernels() {
+  cudaError_t e = cudaFuncSetAttribute(linear2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(linear2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+}
+
+// Tensor maps: A box {64, 128}; W box {64, block_n / 2}.
+cudaError_t launch_linear_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+                               const LinearParams& p, int block_n, int num_sms, cudaStream_t stream) {
+  if (p.N % 8 != 0 || (p.nsplit != 1 && p.nsplit != 3)) {
+    set_last_error("launch_linear_pair: N must be a multiple of 8 and nsplit 1 or 3 (N=%d nsplit=%d)", p.N, p.nsplit);
+    return cudaErrorInvalidValue;
+  }
+  if (block_n == 256) return launch_impl2<256>(a_hi, a_lo, w_hi, w_lo, p, num_sms, stream);
+  if (block_n == 128) return launch_impl2<128>(a_hi, a_lo, w_hi, w_lo, p, num_sms, stream);
+  set_last_error("launch_linear_pair: unsupported block_n %d", block_n);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace cmdi

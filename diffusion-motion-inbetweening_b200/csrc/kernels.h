@@ -37,6 +37,7 @@ struct LinearParams {
   __nv_bfloat16* out_lo;  // written only when nsplit_out == 3
   int ld_bf;
   int nsplit_out;  // 1 or 3: whether the consumer of out_hi/out_lo wants the lo plane
+  int debug;       // bring-up only (CMDI_DEBUG): 1 = skip global stores, 2 = skip MMA issue, 4 = skip TMA loads
 };
 
 // block_n: 128 or 256. Tensor maps: bf16 row-major, box {64, 128} for A and {64, block_n} for W, 128B swizzle.
@@ -44,6 +45,12 @@ cudaError_t configure_linear_kernels();
 cudaError_t launch_linear(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                           const CUtensorMap& w_lo, const LinearParams& p, int block_n, int num_sms,
                           cudaStream_t stream);
+
+// CTA-pair (cta_group::2) version: 256-row tiles shared by two SMs of a cluster. W box is {64, block_n / 2}.   (gemm2.cu)
+cudaError_t configure_linear2_kernels();
+cudaError_t launch_linear_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                               const CUtensorMap& w_lo, const LinearParams& p, int block_n, int num_sms,
+                               cudaStream_t stream);
 
 // ----------------------------------------------------------------------------------------------
 // self-attention core: O = softmax(Q K^T / sqrt(dh)) V per (sequence, head)      (attention.cu)

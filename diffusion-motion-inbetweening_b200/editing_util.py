@@ -38,9 +38,10 @@ def joint_to_full_mask(joint_mask: torch.Tensor, mode: str = "pos_rot_vel") -> t
         m = m | inc["rot"]
     if mode == "pos_rot_vel":
         m = m | inc["vel"]
-    # out[b, f, 0, l] = any_j joint_mask[b, j, 0, l] & m[j, f]   (integer matmul: exact)
-    jm = joint_mask[:, :, 0, :].to(torch.int32)                   # (B, 22, L)
-    out = torch.einsum("bjl,jf->bfl", jm, m.to(torch.int32)) > 0  # (B, 263, L)
+    # out[b, f, 0, l] = any_j joint_mask[b, j, 0, l] & m[j, f]: counts <= 22, exact in fp32 (the reference's
+    # bool_matmul does the same float matmul and asserts exactness, editing_util.py:8-11)
+    jm = joint_mask[:, :, 0, :].to(torch.float32)                     # (B, 22, L)
+    out = torch.einsum("bjl,jf->bfl", jm, m.to(torch.float32)) > 0.5  # (B, 263, L)
     return out.unsqueeze(2)
 
 

@@ -165,13 +165,13 @@ class Engine:
             result["dump"] = [dump[i] for i in range(n_dump)]
         return result
 
-    def profile_pass(self, batch: int, cfg: bool = False):
+    def profile_pass(self, batch: int, cfg: bool = False, repeats: int = 10):
         """[(kernel name, device ms)] for every launch of one denoiser pass (CUDA events between plain launches)."""
         cap = 2 + 7 * self.cfg.num_layers + 1
         ms = (ctypes.c_float * cap)()
         count = ctypes.c_int(0)
         with torch.cuda.device(self.device):
-            capi.check(self.lib.cmdi_profile_pass(self._h, batch, int(cfg), ms, cap, ctypes.byref(count), _stream_ptr(self.device)),
+            capi.check(self.lib.cmdi_profile_pass(self._h, batch, int(cfg), int(repeats), ms, cap, ctypes.byref(count), _stream_ptr(self.device)),
                        "cmdi_profile_pass")
         names = ["token_rows", "frame_embed"]
         for _ in range(self.cfg.num_layers):

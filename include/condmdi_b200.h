@@ -130,7 +130,7 @@ CMDI_API const char* cmdi_last_error(void);
 CMDI_API const char* cmdi_version(void);
 
 /* ---- kernel-level entry points (used by the parity tests; device pointers, fp32 row-major) ---- */
-/* C[M,N] = act(A[M,K] W[N,K]^T + bias) (+ residual); outputs fp32 C and the bf16 hi/lo planes it would hand on */
+/* C[M,N] = act(A[M,K] W[N,K]^T + bias) (+ residual); block_n in {128, 256}: one CTA per tile; {-128, -256}: CTA-pair kernel */
 CMDI_API int cmdi_test_linear(const float* A, const float* W, const float* bias, const float* residual, float* C, int M, int N,
                      int K, int act, int precision, int block_n, void* stream);
 /* O = softmax(Q K^T / sqrt(128)) V for `num_seqs` sequences of length S and H heads; qkv: [num_seqs*S, 3*H*128] */
@@ -141,9 +141,10 @@ CMDI_API int cmdi_test_step(cmdi_engine* e, int sampler, float eta, int t, int B
                    const float* text_scale, const float* x_t, const float* noise, int impute, int stop_imputation_at,
                    const float* x_obs, const uint8_t* mask, float* x_next, float* pred_xstart, void* stream);
 
-/* per-launch device times (ms) of one denoiser pass at `batch` (x2 sequences when cfg), in launch order:
+/* per-launch device times (ms, mean over `repeats` back-to-back launches of each kernel) of one denoiser pass at
+ * `batch` (x2 sequences when cfg), in launch order:
  * token_rows, frame_embed, {qkv, attention, out_proj, ln1, ffn1, ffn2, ln2} x num_layers, out_head */
-CMDI_API int cmdi_profile_pass(cmdi_engine* e, int batch, int cfg, float* ms, int capacity, int* count, void* stream);
+CMDI_API int cmdi_profile_pass(cmdi_engine* e, int batch, int cfg, int repeats, float* ms, int capacity, int* count, void* stream);
 /* the engine's counter-based N(0,1) generator: out[b, i] depends only on (seed, stream_id, sample_offset + b, i) */
 CMDI_API int cmdi_test_normal(float* out, int B, long long per_sample, unsigned long long seed, unsigned long long stream_id,
                      unsigned long long sample_offset, void* stream);
