@@ -221,7 +221,6 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
     const int lane_group = warp_idx & 3;
     const int half = sw >> 2;
     const int row = lane_group * 32 + lane;
-    const int qpos = qtile * kQTile + row;
     const uint32_t trow = tmem_base + ((uint32_t)(lane_group * 32) << 16);
     const float c_scale = 0.08838834764831845f * 1.4426950408889634f;  // 1/sqrt(128) * log2(e)
 
@@ -245,8 +244,15 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
     tc_fence_after();
     // all MMAs are complete: the Q tile region is free and becomes the store-staging area (8 x 4 KB)
     const uint32_t stage = smem_u32(smem + kOffQHi + sw * kEpiStageBytes);
-    const bool valid = qpos < S;
-    const long long roff = valid ? (long long)(row0 + qpos) * p.ld_out * 2 : 0;
+    RowSlots rows;
+    rows.ok = 0;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int qp = qtile * kQTile + lane_group * 32 + it * 4 + (lane >> 3);
+      rows.row[it] = (qp < S) ? (row0 + qp) : 0;
+      if (qp < S) rows.ok |= 1u << it;
+    }
+    const long long pitch = (long long)p.ld_out * 2;
     uint32_t v0[32], v1[32];
     tmem_ld32(trow + kColO + half * 64, v0);
     tmem_ld32(trow + kColO + half * 64 + 32, v1);
@@ -258,10 +264,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
       split_bf16x2(__uint_as_float(v1[2 * j]) * inv, __uint_as_float(v1[2 * j + 1]) * inv, hw[16 + j], lw[16 + j]);
     }
     char* dst_hi = reinterpret_cast<char*>(p.out_hi + head * kHeadDim + half * 64);
-    store_block_coalesced(stage, lane, hw, dst_hi, roff, valid, 8, 1, 0);
+    store_block_coalesced(stage, lane, hw, dst_hi, rows, pitch, 8, 1, 0);
     if (p.nsplit_out == 3) {
       char* dst_lo = reinterpret_cast<char*>(p.out_lo + head * kHeadDim + half * 64);
-      store_block_coalesced(stage, lane, lw, dst_lo, roff, valid, 8, 1, 0);
+      store_block_coalesced(stage, lane, lw, dst_lo, rows, pitch, 8, 1, 0);
     }
   }
 

@@ -1,6 +1,8 @@
 // Kernel-level C-ABI entry points used by the parity tests (declared in include/condmdi_b200.h).
 // They stage fp32 inputs into the bf16 hi/lo planes the kernels consume, build the TMA descriptors,
 // launch the production kernel and hand back fp32 results.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -67,6 +69,11 @@ extern "C" int cmdi_test_linear(const float* A, const float* W, const float* bia
   if (make_tmap_bf16_2d(&mw_hi, w_hi.p, Np, Kp, Kp, 64, pair ? block_n / 2 : block_n)) return 1;
   if (make_tmap_bf16_2d(&mw_lo, w_lo.p, Np, Kp, Kp, 64, pair ? block_n / 2 : block_n)) return 1;
   CK(configure_linear_kernels());
+  CUtensorMap mc_f32;
+  if (make_tmap_2d(&mc_f32, C, 4, M, N, N, 32, 32)) return 1;
+  LinearStoreMaps stm;
+  stm.f32 = &mc_f32;
+  const LinearStoreMaps* stp = getenv("CMDI_EPI") && !strcmp(getenv("CMDI_EPI"), "stg") ? nullptr : &stm;
   LinearParams p{};
   p.M = M; p.N = N; p.K = K; p.nsplit = precision;
   p.bias = bias; p.residual = residual; p.ld_res = N;
@@ -75,9 +82,44 @@ extern "C" int cmdi_test_linear(const float* A, const float* W, const float* bia
   p.nsplit_out = precision;
   if (pair) {
     CK(configure_linear2_kernels());
-    CK(launch_linear_pair(ma_hi, ma_lo, mw_hi, mw_lo, p, block_n, num_sms_of_current_device(), stream));
+    DevBuf dbg, o_hi, o_lo;
+    CUtensorMap mo_hi, mo_lo;
+    const bool want_dbg = getenv("CMDI_TEST_DBG") != nullptr;
+    if (const char* d = getenv("CMDI_DEBUG")) p.debug = atoi(d);
+    if (want_dbg) {
+      CK(dbg.alloc(148 * 16 * 8));
+      p.dbg_cycles = dbg.as<long long>();
+      CK(o_hi.alloc((size_t)Mp * Np * 2));
+      CK(o_lo.alloc((size_t)Mp * Np * 2));
+      if (make_tmap_bf16_2d(&mo_hi, o_hi.p, Mp, Np, Np, 64, 32)) return 1;
+      if (make_tmap_bf16_2d(&mo_lo, o_lo.p, Mp, Np, Np, 64, 32)) return 1;
+      stm.hi = &mo_hi;
+      stm.lo = &mo_lo;
+      p.out_hi = o_hi.as<__nv_bfloat16>();  // realistic stores: bf16 planes like the engine's QKV / FFN1
+      p.out_lo = o_lo.as<__nv_bfloat16>();
+      p.ld_bf = Np;
+      if (getenv("CMDI_TEST_NOF32")) p.out_f32 = nullptr;
+      CK(launch_linear_pair(ma_hi, ma_lo, mw_hi, mw_lo, p, block_n, num_sms_of_current_device(), stream, stp));
+    }
+    CK(launch_linear_pair(ma_hi, ma_lo, mw_hi, mw_lo, p, block_n, num_sms_of_current_device(), stream, stp));
+    if (want_dbg) {
+      std::vector<long long> h(148 * 16);
+      CK(cudaStreamSynchronize(stream));
+      CK(cudaMemcpy(h.data(), dbg.p, h.size() * 8, cudaMemcpyDeviceToHost));
+      double acc[16] = {0};
+      int n_lead = 0, n_all = 0;
+      for (int b = 0; b < 148; ++b) {
+        if (h[b * 16 + 4] == 0) continue;
+        ++n_all;
+        for (int k = 4; k < 8; ++k) acc[k] += (double)h[b * 16 + k];
+        if (h[b * 16 + 0]) { ++n_lead; for (int k = 0; k < 3; ++k) acc[k] += (double)h[b * 16 + k]; }
+      }
+      printf("dbg cycles (mean per CTA): mma total=%.0f wait_tmem_empty=%.0f wait_full=%.0f | epi total=%.0f wait_tmem_full=%.0f work=%.0f arrive=%.0f (leaders %d, ctas %d)\n",
+             acc[0] / n_lead, acc[1] / n_lead, acc[2] / n_lead, acc[4] / n_all, acc[5] / n_all, acc[6] / n_all, acc[7] / n_all, n_lead, n_all);
+      fflush(stdout);
+    }
   } else {
-    CK(launch_linear(ma_hi, ma_lo, mw_hi, mw_lo, p, block_n, num_sms_of_current_device(), stream));
+    CK(launch_linear(ma_hi, ma_lo, mw_hi, mw_lo, p, block_n, num_sms_of_current_device(), stream, stp));
   }
   CK(cudaStreamSynchronize(stream));  // staging buffers are freed on return
   return 0;

@@ -50,6 +50,7 @@ struct Planes {  // a bf16 hi/lo operand: [rows, ld] row-major, with TMA maps fo
   int rows = 0, cols = 0, ld = 0;
   CUtensorMap map_hi{}, map_lo{};
   CUtensorMap pair_hi{}, pair_lo{};  // same planes, box height halved: W operand of the CTA-pair kernel
+  CUtensorMap st_hi{}, st_lo{};      // same planes as a TMA-store target: box {64, 32}
 };
 
 struct LayerW {
@@ -74,6 +75,7 @@ struct cmdi_engine {
   int device = 0, num_sms = 148;
   int nsplit = 3;
   int debug = 0, bn_wide = kBnWide, bn_narrow = kBnNarrow;  // CMDI_DEBUG / CMDI_BN_WIDE / CMDI_BN_NARROW (bring-up knobs)
+  bool tma_store = true;  // CMDI_EPI=stg selects the coalesced-STG epilogue everywhere
   bool use_pair = true;  // CTA-pair (cta_group::2) linear kernels; CMDI_GEMM=single selects the 1-CTA kernels
   int D = 263, D_pad = 264, L = 196, S = 197, ff = 1024, H = 4, layers = 8, maxB = 0;
   int max_seqs = 0, seq_rows = 0, seq_rows_pad = 0, frame_rows = 0, frame_rows_pad = 0;
@@ -101,6 +103,7 @@ struct cmdi_engine {
   float *xseq = nullptr, *x1 = nullptr, *vsum = nullptr, *model_out = nullptr, *pred_x0 = nullptr, *x_obs = nullptr;
   Planes xseq_p, x1_p, qkv_p, attn_p, ffh_p;
   CUtensorMap q_map_hi{}, q_map_lo{}, kv_map_hi{}, kv_map_lo{};
+  CUtensorMap vsum_st{};  // fp32 TMA-store target for the pre-LayerNorm sums
   uint8_t* obs_mask = nullptr;
   float *cond_emb = nullptr, *cond_proj = nullptr, *text_scale = nullptr;
   int* step_ctr = nullptr;  // [2]: step index, block-arrival counter
@@ -131,6 +134,8 @@ int alloc_planes(cmdi_engine* e, Planes* pl, int rows, int cols, int ld, int box
   CKI(make_tmap_bf16_2d(&pl->map_lo, pl->lo, rows, cols, ld, 64, box_rows));
   CKI(make_tmap_bf16_2d(&pl->pair_hi, pl->hi, rows, cols, ld, 64, box_rows / 2));
   CKI(make_tmap_bf16_2d(&pl->pair_lo, pl->lo, rows, cols, ld, 64, box_rows / 2));
+  CKI(make_tmap_bf16_2d(&pl->st_hi, pl->hi, rows, cols, ld, 64, 32));
+  CKI(make_tmap_bf16_2d(&pl->st_lo, pl->lo, rows, cols, ld, 64, 32));
   return 0;
 }
 
@@ -170,13 +175,18 @@ int ensure_temb(cmdi_engine* e, cudaStream_t s) {
   return 0;
 }
 
-int run_linear(cmdi_engine* e, const Planes& a, const Planes& w, const LinearParams& p_in, int block_n, cudaStream_t s) {
+int run_linear(cmdi_engine* e, const Planes& a, const Planes& w, const LinearParams& p_in, int block_n, cudaStream_t s,
+               const Planes* out_planes = nullptr, const CUtensorMap* out_f32 = nullptr) {
   LinearParams p = p_in;
   p.debug = e->debug;
+  LinearStoreMaps st;
+  if (out_planes) { st.hi = &out_planes->st_hi; st.lo = &out_planes->st_lo; }
+  st.f32 = out_f32;
+  const LinearStoreMaps* stp = (e->tma_store && (out_planes || out_f32)) ? &st : nullptr;
   if (e->use_pair) {
-    CK(launch_linear_pair(a.map_hi, a.map_lo, w.pair_hi, w.pair_lo, p, block_n, e->num_sms, s));
+    CK(launch_linear_pair(a.map_hi, a.map_lo, w.pair_hi, w.pair_lo, p, block_n, e->num_sms, s, stp));
   } else {
-    CK(launch_linear(a.map_hi, a.map_lo, w.map_hi, w.map_lo, p, block_n, e->num_sms, s));
+    CK(launch_linear(a.map_hi, a.map_lo, w.map_hi, w.map_lo, p, block_n, e->num_sms, s, stp));
   }
   return 0;
 }
@@ -219,7 +229,7 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
     LinearParams q{};
     q.M = M; q.N = 3 * kDModel; q.K = kDModel; q.nsplit = e->nsplit; q.bias = w.bqkv;
     q.out_hi = e->qkv_p.hi; q.out_lo = e->qkv_p.lo; q.ld_bf = 3 * kDModel; q.nsplit_out = e->nsplit;
-    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->xseq_p, w.wqkv, q, kBnWide, s));
+    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->xseq_p, w.wqkv, q, kBnWide, s, &e->qkv_p));
     CKI(mark());
     // attention core
     AttnParams a{};
@@ -231,7 +241,7 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
     LinearParams o{};
     o.M = M; o.N = kDModel; o.K = kDModel; o.nsplit = e->nsplit; o.bias = w.bo; o.residual = e->xseq; o.ld_res = kDModel;
     o.out_f32 = e->vsum; o.ld_f32 = kDModel; o.nsplit_out = e->nsplit;
-    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->attn_p, w.wo, o, kBnNarrow, s));
+    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->attn_p, w.wo, o, kBnNarrow, s, nullptr, &e->vsum_st));
     CKI(mark());
     for (int r_ = 0; r_ < reps; ++r_) CK(launch_layernorm512(e->vsum, w.g1, w.be1, 1e-5f, M, e->x1, e->x1_p.hi, e->nsplit == 3 ? e->x1_p.lo : nullptr, s));
     CKI(mark());
@@ -239,12 +249,12 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
     LinearParams f1{};
     f1.M = M; f1.N = e->ff; f1.K = kDModel; f1.nsplit = e->nsplit; f1.bias = w.b1; f1.act = 1;
     f1.out_hi = e->ffh_p.hi; f1.out_lo = e->ffh_p.lo; f1.ld_bf = e->ff; f1.nsplit_out = e->nsplit;
-    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->x1_p, w.w1, f1, kBnWide, s));
+    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->x1_p, w.w1, f1, kBnWide, s, &e->ffh_p));
     CKI(mark());
     LinearParams f2{};
     f2.M = M; f2.N = kDModel; f2.K = e->ff; f2.nsplit = e->nsplit; f2.bias = w.b2; f2.residual = e->x1; f2.ld_res = kDModel;
     f2.out_f32 = e->vsum; f2.ld_f32 = kDModel; f2.nsplit_out = e->nsplit;
-    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->ffh_p, w.w2, f2, kBnNarrow, s));
+    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->ffh_p, w.w2, f2, kBnNarrow, s, nullptr, &e->vsum_st));
     CKI(mark());
     for (int r_ = 0; r_ < reps; ++r_) CK(launch_layernorm512(e->vsum, w.g2, w.be2, 1e-5f, M, e->xseq, e->xseq_p.hi, e->nsplit == 3 ? e->xseq_p.lo : nullptr, s));
     CKI(mark());
@@ -309,6 +319,7 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   cmdi_engine* e = new cmdi_engine();
   if (const char* g = getenv("CMDI_GEMM")) e->use_pair = strcmp(g, "single") != 0;
   if (const char* g = getenv("CMDI_DEBUG")) e->debug = atoi(g);
+  if (const char* g = getenv("CMDI_EPI")) e->tma_store = strcmp(g, "stg") != 0;
   e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount; e->nsplit = cfg->precision;
   e->D = cfg->njoints; e->D_pad = round_up(cfg->njoints, 8); e->L = cfg->nframes; e->S = cfg->nframes + 1;
   e->ff = cfg->ff_size; e->H = cfg->num_heads; e->layers = cfg->num_layers; e->maxB = cfg->max_batch;
@@ -356,6 +367,7 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   A(make_tmap_bf16_2d(&e->q_map_lo, e->qkv_p.lo, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, 128));
   A(make_tmap_bf16_2d(&e->kv_map_hi, e->qkv_p.hi, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, kAttnKeyPad));
   A(make_tmap_bf16_2d(&e->kv_map_lo, e->qkv_p.lo, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, kAttnKeyPad));
+  A(make_tmap_2d(&e->vsum_st, e->vsum, 4, e->seq_rows_pad, kDModel, kDModel, 32, 32));
   A(dev_alloc(e, &e->model_out, (size_t)2 * e->frame_rows_pad * e->D_pad));
   A(dev_alloc(e, &e->pred_x0, (size_t)e->frame_rows_pad * e->D_pad));
   A(dev_alloc(e, &e->x_obs, (size_t)e->frame_rows_pad * e->D_pad));

@@ -51,6 +51,8 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(kNumThreads, 1)
 linear_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+               const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
+               const __grid_constant__ CUtensorMap map_o_f32,
               const LinearParams p, const int num_stages, const int num_m_blocks, const int num_n_blocks) {
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // 256 or 512 (power of two)
@@ -185,7 +187,8 @@ linear_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     const int epi = warp_idx - 2;
     const int lane_group = warp_idx & 3;  // TMEM lanes this warp may touch: 32*lane_group ..
     const int col_part = epi >> 2;
-    const uint32_t epi_stage_addr = smem_u32(epi_stage + epi * kEpiStageBytes);        // which half of the tile's columns
+    const uint32_t epi_stage_addr = smem_u32(epi_stage + epi * kEpiStageBytes);
+    const EpiStoreMaps epi_maps{&map_o_hi, &map_o_lo, &map_o_f32};        // which half of the tile's columns
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -194,7 +197,7 @@ linear_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
 
-      epilogue_tile<BLOCK_N>(p, tmem_base, acc, m_blk, n_blk, lane_group, col_part, lane, epi_stage_addr);
+      epilogue_tile<BLOCK_N>(p, epi_maps, tmem_base, acc, m_blk, n_blk, lane_group, col_part, lane, epi_stage_addr);
       // accumulator buffer drained -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -202,6 +205,7 @@ linear_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (p.tma_store && lane == 0) tma_store_wait_read();
   }
 
   tc_fence_before();
@@ -214,7 +218,17 @@ linear_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 
 template <int BLOCK_N>
 cudaError_t launch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
-                        const CUtensorMap& w_lo, const LinearParams& p, int num_sms, cudaStream_t stream) {
+                        const CUtensorMap& w_lo, const LinearParams& p_in, int num_sms, cudaStream_t stream, const LinearStoreMaps* st) {
+  LinearParams p = p_in;
+  p.tma_store = 0;
+  CUtensorMap o_hi = a_hi, o_lo = a_hi, o_f32 = a_hi;  // placeholders when the STG epilogue is used
+  if (st && p.rowmap == ROWMAP_IDENTITY && p.dup_row_offset == 0 && (!p.out_hi || (st->hi && (p.nsplit_out != 3 || st->lo))) &&
+      (!p.out_f32 || st->f32)) {
+    p.tma_store = 1;
+    if (st->hi) o_hi = *st->hi;
+    if (st->lo) o_lo = *st->lo;
+    if (st->f32) o_f32 = *st->f32;
+  }
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   const int nplanes = (p.nsplit == 3) ? 2 : 1;
   const int stage_bytes = nplanes * (kABytes + kBBytes);
@@ -225,7 +239,7 @@ cudaError_t launch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const 
   const int num_n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m_blocks * num_n_blocks;
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  linear_kernel<BLOCK_N><<<grid, kNumThreads, smem, stream>>>(a_hi, a_lo, w_hi, w_lo, p, num_stages, num_m_blocks,
+  linear_kernel<BLOCK_N><<<grid, kNumThreads, smem, stream>>>(a_hi, a_lo, w_hi, w_lo, o_hi, o_lo, o_f32, p, num_stages, num_m_blocks,
                                                             num_n_blocks);
   return cudaGetLastError();
 }
@@ -240,13 +254,13 @@ cudaError_t configure_linear_kernels() {
 
 cudaError_t launch_linear(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                           const CUtensorMap& w_lo, const LinearParams& p, int block_n, int num_sms,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, const LinearStoreMaps* st) {
   if (p.N % 8 != 0 || (p.nsplit != 1 && p.nsplit != 3)) {
     set_last_error("launch_linear: N must be a multiple of 8 and nsplit 1 or 3 (N=%d nsplit=%d)", p.N, p.nsplit);
     return cudaErrorInvalidValue;
   }
-  if (block_n == 256) return launch_impl<256>(a_hi, a_lo, w_hi, w_lo, p, num_sms, stream);
-  if (block_n == 128) return launch_impl<128>(a_hi, a_lo, w_hi, w_lo, p, num_sms, stream);
+  if (block_n == 256) return launch_impl<256>(a_hi, a_lo, w_hi, w_lo, p, num_sms, stream, st);
+  if (block_n == 128) return launch_impl<128>(a_hi, a_lo, w_hi, w_lo, p, num_sms, stream, st);
   set_last_error("launch_linear: unsupported block_n %d", block_n);
   return cudaErrorInvalidValue;
 }

@@ -43,6 +43,8 @@ template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+               const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
+               const __grid_constant__ CUtensorMap map_o_f32,
                const LinearParams p, const int num_stages, const int num_m_pairs, const int num_n_blocks) {
   constexpr int kHalfN = BLOCK_N / 2;               // W rows this CTA loads
   constexpr int kBBytes = kHalfN * kBlockK * 2;
@@ -128,12 +130,17 @@ linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long t_wait_empty = 0, t_wait_full = 0, t_begin = clock64();
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        long long c0 = clock64();
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+        t_wait_empty += clock64() - c0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
+          c0 = clock64();
           mbar_wait(&bars->full[stage], phase);
+          t_wait_full += clock64() - c0;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t sb = sa + nplanes * kABytes;
@@ -170,6 +177,10 @@ linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+      if (p.dbg_cycles) {
+        long long* d = p.dbg_cycles + (size_t)blockIdx.x * 16;
+        d[0] = clock64() - t_begin; d[1] = t_wait_empty; d[2] = t_wait_full;
+      }
     }
     __syncwarp();
   } else {
@@ -178,20 +189,32 @@ linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int lane_group = warp_idx & 3;
     const int col_part = epi >> 2;
     const uint32_t epi_stage_addr = smem_u32(epi_stage + epi * kEpiStageBytes);
+    const EpiStoreMaps epi_maps{&map_o_hi, &map_o_lo, &map_o_f32};
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long t_wait = 0, t_work = 0, t_arrive = 0, t_begin = clock64();
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = 2 * (tile / num_n_blocks) + (int)cta_rank;
       const int n_blk = tile % num_n_blocks;
+      long long c0 = clock64();
       mbar_wait(&bars->tmem_full[acc], acc_phase);
+      long long c1 = clock64();
       tc_fence_after();
-      epilogue_tile<BLOCK_N>(p, tmem_base, acc, m_blk, n_blk, lane_group, col_part, lane, epi_stage_addr);
+      epilogue_tile<BLOCK_N>(p, epi_maps, tmem_base, acc, m_blk, n_blk, lane_group, col_part, lane, epi_stage_addr);
+      long long c2 = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_on_leader(&bars->tmem_empty[acc]);
+      long long c3 = clock64();
+      t_wait += c1 - c0; t_work += c2 - c1; t_arrive += c3 - c2;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (p.dbg_cycles && epi == 0 && lane == 0) {
+      long long* d = p.dbg_cycles + (size_t)blockIdx.x * 16;
+      d[4] = clock64() - t_begin; d[5] = t_wait; d[6] = t_work; d[7] = t_arrive;
+    }
+    if (p.tma_store && lane == 0) tma_store_wait_read();
   }
 
   tc_fence_before();
@@ -204,7 +227,17 @@ linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
 template <int BLOCK_N>
 cudaError_t launch_impl2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
-                         const LinearParams& p, int num_sms, cudaStream_t stream) {
+                         const LinearParams& p_in, int num_sms, cudaStream_t stream, const LinearStoreMaps* st) {
+  LinearParams p = p_in;
+  p.tma_store = 0;
+  CUtensorMap o_hi = a_hi, o_lo = a_hi, o_f32 = a_hi;  // placeholders when the STG epilogue is used
+  if (st && p.rowmap == ROWMAP_IDENTITY && p.dup_row_offset == 0 && (!p.out_hi || (st->hi && (p.nsplit_out != 3 || st->lo))) &&
+      (!p.out_f32 || st->f32)) {
+    p.tma_store = 1;
+    if (st->hi) o_hi = *st->hi;
+    if (st->lo) o_lo = *st->lo;
+    if (st->f32) o_f32 = *st->f32;
+  }
   constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;
   const int nplanes = (p.nsplit == 3) ? 2 : 1;
   const int stage_bytes = nplanes * (kABytes + kBBytes);
@@ -216,7 +249,7 @@ cudaError_t launch_impl2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const
   const int num_tiles = num_m_pairs * num_n_blocks;
   int clusters = num_sms / 2;
   if (clusters > num_tiles) clusters = num_tiles;
-  linear2_kernel<BLOCK_N><<<2 * clusters, kNumThreads, smem, stream>>>(a_hi, a_lo, w_hi, w_lo, p, num_stages, num_m_pairs,
+  linear2_kernel<BLOCK_N><<<2 * clusters, kNumThreads, smem, stream>>>(a_hi, a_lo, w_hi, w_lo, o_hi, o_lo, o_f32, p, num_stages, num_m_pairs,
                                                                       num_n_blocks);
   return cudaGetLastError();
 }
@@ -231,13 +264,14 @@ cudaError_t configure_linear2_kernels() {
 
 // Tensor maps: A box {64, 128}; W box {64, block_n / 2}.
 cudaError_t launch_linear_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
-                               const LinearParams& p, int block_n, int num_sms, cudaStream_t stream) {
+                               const LinearParams& p, int block_n, int num_sms, cudaStream_t stream,
+                               const LinearStoreMaps* st) {
   if (p.N % 8 != 0 || (p.nsplit != 1 && p.nsplit != 3)) {
     set_last_error("launch_linear_pair: N must be a multiple of 8 and nsplit 1 or 3 (N=%d nsplit=%d)", p.N, p.nsplit);
     return cudaErrorInvalidValue;
   }
-  if (block_n == 256) return launch_impl2<256>(a_hi, a_lo, w_hi, w_lo, p, num_sms, stream);
-  if (block_n == 128) return launch_impl2<128>(a_hi, a_lo, w_hi, w_lo, p, num_sms, stream);
+  if (block_n == 256) return launch_impl2<256>(a_hi, a_lo, w_hi, w_lo, p, num_sms, stream, st);
+  if (block_n == 128) return launch_impl2<128>(a_hi, a_lo, w_hi, w_lo, p, num_sms, stream, st);
   set_last_error("launch_linear_pair: unsupported block_n %d", block_n);
   return cudaErrorInvalidValue;
 }

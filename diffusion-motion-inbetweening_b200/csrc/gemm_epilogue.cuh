@@ -3,10 +3,16 @@
 //
 // Thread mapping: epilogue warp w owns TMEM lanes 32*(w%4).. (thread = output row) and half of the tile's columns,
 // processed 64 columns at a time.  A thread therefore holds a ROW fragment, which is the wrong shape for global
-// stores (32 lanes x 16 B with a multi-KB stride ran at < 1 TB/s; r01 time decomposition: stores were ~50 % of the
-// QKV kernel).  Every 32-row x 128-byte block is therefore transposed through a per-warp 4 KB shared-memory
-// staging tile (16-byte chunks XOR-swizzled by row & 7: conflict-free both ways) and written with fully coalesced
-// 16-byte stores, 4 complete 128-byte row segments per instruction.
+// memory: every 32-row x 128-byte block is transposed through a per-warp 4 KB shared-memory staging tile (16-byte
+// chunks XOR-swizzled by row & 7: conflict-free both ways) and moved with fully coalesced 16-byte accesses, 4
+// complete 128-byte row segments per instruction.
+//
+// Latency notes from the r01 cycle-counter probe (profiles/r01c_*): the first version spent ~18k cycles per tile
+// here (> the 12k-cycle MMA mainloop it should hide under) because (a) the 16 bias loads of a 64-column chunk sat
+// behind per-group bounds branches and were exposed one after the other, and (b) each staged row was load ->
+// shuffle -> store serially.  Now: the bias of a warp's columns is ONE coalesced load per tile (broadcast by shuffle),
+// the row offsets of the 8 rows a lane stores are precomputed per tile, and staging reads are batched ahead of the
+// global stores.
 #pragma once
 
 #include "common.cuh"
@@ -28,64 +34,88 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   return v;
 }
 
-// Store a 32-row x 32-word block (thread `lane` holds row `lane` in w[0..31]) to global memory.
-// Row r goes to dst_base + row_off_bytes(r) if row_ok(r); the 16-byte chunk c of a row is written if c < valid_chunks.
-// `row_off` / `ok` are this thread's own row offset (bytes) and validity; other rows' are fetched by shuffle.
+// The 8 rows (of the warp's 32) that this lane moves in the coalesced phase: row it*4 + lane/8, chunk lane%8.
+struct RowSlots {
+  int row[8];        // output row index of slot `it` (0 when invalid)
+  uint32_t ok;       // bit it: the row is valid
+};
+
+// Store a 32-row x 32-word block (thread `lane` holds row `lane` in w[0..31]).  Slot it's row goes to
+// dst_base + rows.row[it] * pitch_bytes; the 16-byte chunk c of a row is written if c < valid_chunks.
 __device__ __forceinline__ void store_block_coalesced(uint32_t stage, int lane, const uint32_t (&w)[32], char* dst_base,
-                                                      long long row_off, bool ok, int valid_chunks, int ncopies,
-                                                      long long dup_bytes) {
+                                                      const RowSlots& rows, long long pitch_bytes, int valid_chunks,
+                                                      int ncopies, long long dup_bytes) {
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     st_shared_v4(stage + lane * 128 + ((j ^ (lane & 7)) << 4), w[j * 4], w[j * 4 + 1], w[j * 4 + 2], w[j * 4 + 3]);
   __syncwarp();
   const int c = lane & 7;
+  uint4 v[8];
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int rr = it * 4 + (lane >> 3);
-    const uint4 v = ld_shared_v4(stage + rr * 128 + ((c ^ (rr & 7)) << 4));
-    const long long off = __shfl_sync(0xffffffffu, row_off, rr);
-    const int rok = __shfl_sync(0xffffffffu, (int)ok, rr);
-    if (rok && c < valid_chunks) {
-      char* d = dst_base + off + c * 16;
-      st_global_v4(d, v.x, v.y, v.z, v.w);
-      if (ncopies == 2) st_global_v4(d + dup_bytes, v.x, v.y, v.z, v.w);
+    v[it] = ld_shared_v4(stage + rr * 128 + ((c ^ (rr & 7)) << 4));
+  }
+  if (c < valid_chunks) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      if ((rows.ok >> it) & 1u) {
+        char* d = dst_base + (long long)rows.row[it] * pitch_bytes + c * 16;
+        st_global_v4(d, v[it].x, v[it].y, v[it].z, v[it].w);
+        if (ncopies == 2) st_global_v4(d + dup_bytes, v[it].x, v[it].y, v[it].z, v[it].w);
+      }
     }
   }
 }
 
-// Inverse of store_block_coalesced: fetch a 32-row x 128-byte block with coalesced 16-byte loads and hand every
-// thread its own row (w[0..31]).
-__device__ __forceinline__ void load_block_coalesced(uint32_t stage, int lane, uint32_t (&w)[32], const char* src_base,
-                                                     long long row_off, bool ok, int valid_chunks) {
+// Same block, but handed to the TMA: the staging tile already has the 128-byte-swizzle layout a {128 B x 32 rows} box
+// expects, so one elected lane issues a bulk tensor store (rows beyond the map's extent are clipped by the TMA).
+__device__ __forceinline__ void store_block_tma(uint32_t stage, int lane, const uint32_t (&w)[32], const CUtensorMap* map,
+                                                int col, int row) {
+  if (lane == 0) tma_store_wait_read();  // the previous store issued from this staging tile has been read out
   __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    st_shared_v4(stage + lane * 128 + ((j ^ (lane & 7)) << 4), w[j * 4], w[j * 4 + 1], w[j * 4 + 2], w[j * 4 + 3]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(map, stage, col, row);
+    tma_store_commit();
+  }
+}
+
+// Inverse: fetch a 32-row x 128-byte block with coalesced 16-byte loads and hand every thread its own row.
+__device__ __forceinline__ void load_block_coalesced(uint32_t stage, int lane, uint32_t (&w)[32], const char* src_base,
+                                                     const RowSlots& rows, long long pitch_bytes, int valid_chunks) {
   const int c = lane & 7;
+  uint4 v[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    v[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (((rows.ok >> it) & 1u) && c < valid_chunks)
+      v[it] = *reinterpret_cast<const uint4*>(src_base + (long long)rows.row[it] * pitch_bytes + c * 16);
+  }
+  __syncwarp();
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int rr = it * 4 + (lane >> 3);
-    const long long off = __shfl_sync(0xffffffffu, row_off, rr);
-    const int rok = __shfl_sync(0xffffffffu, (int)ok, rr);
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (rok && c < valid_chunks) v = *reinterpret_cast<const uint4*>(src_base + off + c * 16);
-    st_shared_v4(stage + rr * 128 + ((c ^ (rr & 7)) << 4), v.x, v.y, v.z, v.w);
+    st_shared_v4(stage + rr * 128 + ((c ^ (rr & 7)) << 4), v[it].x, v[it].y, v[it].z, v[it].w);
   }
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const uint4 v = ld_shared_v4(stage + lane * 128 + ((j ^ (lane & 7)) << 4));
-    w[j * 4] = v.x; w[j * 4 + 1] = v.y; w[j * 4 + 2] = v.z; w[j * 4 + 3] = v.w;
+    const uint4 u = ld_shared_v4(stage + lane * 128 + ((j ^ (lane & 7)) << 4));
+    w[j * 4] = u.x; w[j * 4 + 1] = u.y; w[j * 4 + 2] = u.z; w[j * 4 + 3] = u.w;
   }
 }
 
-template <int BLOCK_N>
-__device__ __forceinline__ void epilogue_tile(const LinearParams& p, uint32_t tmem_base, int acc, int m_blk, int n_blk,
-                                              int lane_group, int col_part, int lane, uint32_t stage) {
-  constexpr int kBlockM = kEpiBlockM;
-  constexpr int kColsPerPart = BLOCK_N / 2;
-  const int a_row = m_blk * kBlockM + lane_group * 32 + lane;
+// output row / validity of A-row `a_row` under the linear's row map
+__device__ __forceinline__ bool map_row(const LinearParams& p, int a_row, long long& out_row, int& pos) {
   bool valid = a_row < p.M;
-  long long out_row = a_row;
-  int pos = 0;  // sequence position for the positional-encoding add
+  out_row = a_row;
+  pos = 0;
   if (p.rowmap == ROWMAP_FRAMES_TO_SEQ) {
     const int b = a_row / p.frames;
     const int l = a_row - b * p.frames;
@@ -99,60 +129,129 @@ __device__ __forceinline__ void epilogue_tile(const LinearParams& p, uint32_t tm
     out_row = (long long)b * p.frames + (s - 1);
   }
   if (!valid) out_row = 0;
+  return valid;
+}
+
+struct EpiStoreMaps {
+  const CUtensorMap* hi;
+  const CUtensorMap* lo;
+  const CUtensorMap* f32;
+};
+
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_tile(const LinearParams& p, const EpiStoreMaps& maps, uint32_t tmem_base, int acc,
+                                              int m_blk, int n_blk, int lane_group, int col_part, int lane, uint32_t stage) {
+  constexpr int kBlockM = kEpiBlockM;
+  constexpr int kColsPerPart = BLOCK_N / 2;
+  const int warp_row0 = m_blk * kBlockM + lane_group * 32;
+  RowSlots rows;
+  rows.ok = 0;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    int pos_unused;
+    long long r;
+    if (map_row(p, warp_row0 + it * 4 + (lane >> 3), r, pos_unused)) rows.ok |= 1u << it;
+    rows.row[it] = (int)r;
+  }
+  RowSlots pe_rows;  // rows of the positional-encoding table for the same 8 slots (frame embed only)
+  pe_rows.ok = rows.ok;
+  if (p.pos_enc) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) pe_rows.row[it] = (warp_row0 + it * 4 + (lane >> 3)) % p.frames + 1;
+  }
   const int ncopies = (p.debug & 1) ? 0 : ((p.dup_row_offset > 0) ? 2 : 1);
+  // bias of this warp's column range: one coalesced 16-byte load per lane per tile (lane l: 4 columns from 4l),
+  // issued before the accumulator is touched; consumers fetch it by shuffle
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    const int nb = n_blk * BLOCK_N + col_part * kColsPerPart + lane * 4;
+    if (p.bias && lane * 4 < kColsPerPart && nb < p.N) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb));
+  }
 
 #pragma unroll 1
   for (int c64 = 0; c64 < kColsPerPart / 64; ++c64) {
     const int col_in_tile = col_part * kColsPerPart + c64 * 64;
     const int n0 = n_blk * BLOCK_N + col_in_tile;
+    if (p.tma_store) {
+      // the staging tile is about to be rewritten by ordinary shared-memory stores (residual fetch): the bulk store
+      // issued from it earlier must have finished reading it
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+    }
     uint32_t v0[32], v1[32];
     tmem_ld32(tmem_addr(tmem_base, lane_group * 32, acc * BLOCK_N + col_in_tile), v0);
     tmem_ld32(tmem_addr(tmem_base, lane_group * 32, acc * BLOCK_N + col_in_tile + 32), v1);
+    if (n0 >= p.N) {  // warp-uniform: nothing to write for this chunk
+      tmem_ld_wait();
+      continue;
+    }
     tmem_ld_wait();
-    if (n0 >= p.N) continue;  // warp-uniform
     float f[64];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       f[j] = __uint_as_float(v0[j]);
       f[32 + j] = __uint_as_float(v1[j]);
     }
-    if (p.residual) {
-      // x + sublayer(x): the fp32 residual rows are fetched coalesced (two 32-column blocks)
-      const long long roff = out_row * (long long)p.ld_res * 4;
+    if (p.bias) {
+      // lane (c64*16 + g) holds the bias of columns [n0 + 4g, n0 + 4g + 4)
+#pragma unroll
+      for (int g = 0; g < 16; ++g) {
+        const int src = c64 * 16 + g;
+        f[g * 4 + 0] += __shfl_sync(0xffffffffu, bias4.x, src);
+        f[g * 4 + 1] += __shfl_sync(0xffffffffu, bias4.y, src);
+        f[g * 4 + 2] += __shfl_sync(0xffffffffu, bias4.z, src);
+        f[g * 4 + 3] += __shfl_sync(0xffffffffu, bias4.w, src);
+      }
+    }
+    if (p.pos_enc) {
+      // + pe[pos]: rows of the positional table, fetched coalesced like the residual
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int nb = n0 + h * 32;
-        load_block_coalesced(stage, lane, h == 0 ? v0 : v1, reinterpret_cast<const char*>(p.residual + nb), roff, valid,
-                             (p.N - nb) / 4);
+        uint32_t r[32];
+        load_block_coalesced(stage, lane, r, reinterpret_cast<const char*>(p.pos_enc + n0 + h * 32), pe_rows,
+                             (long long)p.N * 4, (p.N - n0 - h * 32) / 4);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[h * 32 + j] += __uint_as_float(r[j]);
       }
     }
+    if (p.residual) {
+      // x + sublayer(x): the fp32 residual rows are fetched coalesced, one 32-column block at a time
 #pragma unroll
-    for (int g = 0; g < 16; ++g) {
-      const int n = n0 + g * 4;
-      if (n < p.N) {
-        if (p.bias) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-          f[g * 4 + 0] += bv.x; f[g * 4 + 1] += bv.y; f[g * 4 + 2] += bv.z; f[g * 4 + 3] += bv.w;
-        }
-        if (p.pos_enc) {
-          const float4 pv = __ldg(reinterpret_cast<const float4*>(p.pos_enc + (size_t)pos * p.N + n));
-          f[g * 4 + 0] += pv.x; f[g * 4 + 1] += pv.y; f[g * 4 + 2] += pv.z; f[g * 4 + 3] += pv.w;
-        }
-        if (p.residual) {
-          const uint32_t* rv = (g < 8) ? &v0[g * 4] : &v1[(g - 8) * 4];
-          f[g * 4 + 0] += __uint_as_float(rv[0]); f[g * 4 + 1] += __uint_as_float(rv[1]);
-          f[g * 4 + 2] += __uint_as_float(rv[2]); f[g * 4 + 3] += __uint_as_float(rv[3]);
-        }
-        if (p.act == 1) {
-          f[g * 4 + 0] = gelu_erf(f[g * 4 + 0]); f[g * 4 + 1] = gelu_erf(f[g * 4 + 1]);
-          f[g * 4 + 2] = gelu_erf(f[g * 4 + 2]); f[g * 4 + 3] = gelu_erf(f[g * 4 + 3]);
-        }
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[32];
+        load_block_coalesced(stage, lane, r, reinterpret_cast<const char*>(p.residual + n0 + h * 32), rows,
+                             (long long)p.ld_res * 4, (p.N - n0 - h * 32) / 4);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[h * 32 + j] += __uint_as_float(r[j]);
       }
+    }
+    if (p.act == 1) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) f[j] = gelu_erf(f[j]);
     }
     if (ncopies == 0) continue;
+    if (p.tma_store) {
+      // identity row map: the staging tile goes out as one bulk tensor store per 32 x 128 B block
+      if (p.out_f32) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t w[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(f[h * 32 + j]);
+          if (n0 + h * 32 < p.N) store_block_tma(stage, lane, w, maps.f32, n0 + h * 32, warp_row0);
+        }
+      }
+      if (p.out_hi) {
+        uint32_t hw[32], lw[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) split_bf16x2(f[2 * j], f[2 * j + 1], hw[j], lw[j]);
+        store_block_tma(stage, lane, hw, maps.hi, n0, warp_row0);
+        if (p.nsplit_out == 3) store_block_tma(stage, lane, lw, maps.lo, n0, warp_row0);
+      }
+      continue;
+    }
     if (p.out_f32) {
       // two 32-column fp32 blocks: 128 B per row each
-      const long long roff = out_row * (long long)p.ld_f32 * 4;
       const long long dup = (long long)p.dup_row_offset * p.ld_f32 * 4;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -160,8 +259,9 @@ __device__ __forceinline__ void epilogue_tile(const LinearParams& p, uint32_t tm
 #pragma unroll
         for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(f[h * 32 + j]);
         const int nb = n0 + h * 32;
-        const int chunks = (p.N - nb) / 4;  // 16-byte chunks (4 floats) still inside N; may be <= 0 or >= 8
-        store_block_coalesced(stage, lane, w, reinterpret_cast<char*>(p.out_f32 + nb), roff, valid, chunks, ncopies, dup);
+        // 16-byte chunks (4 floats) still inside N; may be <= 0 or >= 8
+        store_block_coalesced(stage, lane, w, reinterpret_cast<char*>(p.out_f32 + nb), rows, (long long)p.ld_f32 * 4,
+                              (p.N - nb) / 4, ncopies, dup);
       }
     }
     if (p.out_hi) {
@@ -169,12 +269,13 @@ __device__ __forceinline__ void epilogue_tile(const LinearParams& p, uint32_t tm
       uint32_t hw[32], lw[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) split_bf16x2(f[2 * j], f[2 * j + 1], hw[j], lw[j]);
-      const long long roff = out_row * (long long)p.ld_bf * 2;
       const long long dup = (long long)p.dup_row_offset * p.ld_bf * 2;
       const int chunks = (p.N - n0) / 8;  // 16-byte chunks (8 bf16) still inside N
-      store_block_coalesced(stage, lane, hw, reinterpret_cast<char*>(p.out_hi + n0), roff, valid, chunks, ncopies, dup);
+      store_block_coalesced(stage, lane, hw, reinterpret_cast<char*>(p.out_hi + n0), rows, (long long)p.ld_bf * 2, chunks,
+                            ncopies, dup);
       if (p.nsplit_out == 3)
-        store_block_coalesced(stage, lane, lw, reinterpret_cast<char*>(p.out_lo + n0), roff, valid, chunks, ncopies, dup);
+        store_block_coalesced(stage, lane, lw, reinterpret_cast<char*>(p.out_lo + n0), rows, (long long)p.ld_bf * 2,
+                              chunks, ncopies, dup);
     }
   }
 }

@@ -17,6 +17,14 @@ enum RowMap : int {
   ROWMAP_SEQ_TO_FRAMES = 2,  // A row b*(L+1) + s  -> out row b*L + s - 1, s=0 dropped (mdm.py:284 "[1:]")
 };
 
+// Output tensor maps for the TMA-store epilogue (identity row map only): bf16 planes with box {64, 32}, fp32 with
+// box {32, 32}; `rows` of each map must equal the number of valid output rows (TMA clips the M tail).
+struct LinearStoreMaps {
+  const CUtensorMap* hi = nullptr;
+  const CUtensorMap* lo = nullptr;
+  const CUtensorMap* f32 = nullptr;
+};
+
 struct LinearParams {
   int M;       // valid A rows
   int N;       // valid output columns
@@ -38,19 +46,21 @@ struct LinearParams {
   int ld_bf;
   int nsplit_out;  // 1 or 3: whether the consumer of out_hi/out_lo wants the lo plane
   int debug;       // bring-up only (CMDI_DEBUG): 1 = skip global stores, 2 = skip MMA issue, 4 = skip TMA loads
+  long long* dbg_cycles;  // bring-up only: per-CTA cycle counters [gridDim.x][16] (see gemm2.cu) or null
+  int tma_store;   // set by the launcher when LinearStoreMaps are given: outputs leave through cp.async.bulk.tensor stores
 };
 
 // block_n: 128 or 256. Tensor maps: bf16 row-major, box {64, 128} for A and {64, block_n} for W, 128B swizzle.
 cudaError_t configure_linear_kernels();
 cudaError_t launch_linear(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                           const CUtensorMap& w_lo, const LinearParams& p, int block_n, int num_sms,
-                          cudaStream_t stream);
+                          cudaStream_t stream, const LinearStoreMaps* st = nullptr);
 
 // CTA-pair (cta_group::2) version: 256-row tiles shared by two SMs of a cluster. W box is {64, block_n / 2}.   (gemm2.cu)
 cudaError_t configure_linear2_kernels();
 cudaError_t launch_linear_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                const CUtensorMap& w_lo, const LinearParams& p, int block_n, int num_sms,
-                               cudaStream_t stream);
+                               cudaStream_t stream, const LinearStoreMaps* st = nullptr);
 
 // ----------------------------------------------------------------------------------------------
 // self-attention core: O = softmax(Q K^T / sqrt(dh)) V per (sequence, head)      (attention.cu)
@@ -166,6 +176,9 @@ cudaError_t launch_split_planes(const float* in, int rows, int cols, int ld_in, 
 // bf16 row-major [rows, cols] with row pitch ld elements; box {box_cols (=64), box_rows}; 128 B swizzle.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
                       uint32_t box_rows);
+// generic: elem_bytes 2 (bf16) or 4 (fp32); box_cols * elem_bytes must be 128
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_cols, uint32_t box_rows);
 
 void set_last_error(const char* fmt, ...);
 const char* get_last_error();
