@@ -60,18 +60,21 @@ template <int CHUNK0, int NCHUNKS>
 __device__ __forceinline__ float softmax_half(uint32_t trow, int S, bool split, float c_scale, AttnBarriers* bars, int half,
                                               int row) {
   float s[NCHUNKS * 16];
+  {
+    // all TMEM reads in flight at once, one wait
+    uint32_t v[NCHUNKS][16];
 #pragma unroll
-  for (int c = 0; c < NCHUNKS; ++c) {
-    uint32_t v[16];
-    tmem_ld16(trow + kColS + (CHUNK0 + c) * 16, v);
+    for (int c = 0; c < NCHUNKS; ++c) tmem_ld16(trow + kColS + (CHUNK0 + c) * 16, v[c]);
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) s[c * 16 + j] = __uint_as_float(v[j]);
+    for (int c = 0; c < NCHUNKS; ++c)
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        s[c * 16 + j] = ((CHUNK0 + c) * 16 + j < S) ? __uint_as_float(v[c][j]) : -INFINITY;  // padded keys: exp2 -> 0
   }
   float mx = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < NCHUNKS * 16; ++i)
-    if ((CHUNK0 * 16 + i) < S) mx = fmaxf(mx, s[i]);
+  for (int i = 0; i < NCHUNKS * 16; ++i) mx = fmaxf(mx, s[i]);
   bars->red_max[half][row] = mx;
   // every S value is in registers now: after this barrier P may overwrite the S columns
   tc_fence_before();
@@ -85,9 +88,8 @@ __device__ __forceinline__ float softmax_half(uint32_t trow, int S, bool split, 
     uint32_t ph[8], pl[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int col = (CHUNK0 + c) * 16 + j * 2;
-      const float p0 = (col < S) ? exp2f(fmaf(s[c * 16 + j * 2], c_scale, -mc)) : 0.f;
-      const float p1 = (col + 1 < S) ? exp2f(fmaf(s[c * 16 + j * 2 + 1], c_scale, -mc)) : 0.f;
+      const float p0 = fast_exp2(fmaf(s[c * 16 + j * 2], c_scale, -mc));
+      const float p1 = fast_exp2(fmaf(s[c * 16 + j * 2 + 1], c_scale, -mc));
       sum += p0 + p1;
       split_bf16x2(p0, p1, ph[j], pl[j]);
     }
@@ -100,7 +102,9 @@ __device__ __forceinline__ float softmax_half(uint32_t trow, int S, bool split, 
 __global__ void __launch_bounds__(kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                  const __grid_constant__ CUtensorMap map_kv_hi, const __grid_constant__ CUtensorMap map_kv_lo,
+                 const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
                  const AttnParams p) {
+  griddep_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(smem + kSmemTiles);
@@ -135,6 +139,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  griddep_wait();
 
   if (warp_idx == 0) {
     if (lane == 0) {
@@ -168,8 +173,11 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
       constexpr uint32_t idesc_s = make_idesc_bf16(kQTile, kKeyPad, 0);
       uint32_t accum = 0;
       const int nterms = split ? 3 : 1;
+      long long tm[8];
+      tm[0] = clock64();
       for (int j = 0; j < 2; ++j) {
         mbar_wait(&bars->qk_full[j], 0);
+        tm[1 + j] = clock64();
         tc_fence_after();
         for (int term = 0; term < nterms; ++term) {
           // split order: Q_lo*K_hi, Q_hi*K_lo, Q_hi*K_hi ; fast mode: Q_hi*K_hi
@@ -185,10 +193,13 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
         }
       }
       umma_commit(&bars->s_full);
+      tm[3] = clock64();
       // ---------------- O = P V ----------------
       constexpr uint32_t idesc_o = make_idesc_bf16(kQTile, kHeadDim, 1);
       mbar_wait(&bars->p_full, 0);
+      tm[4] = clock64();
       mbar_wait(&bars->vhi_full, 0);
+      tm[5] = clock64();
       tc_fence_after();
       const uint64_t dv_hi = make_desc_mnmajor_sw128(sbase + kOffVHi, kKVBlockBytes);
       accum = 0;
@@ -204,6 +215,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
         umma_ts(tmem_base + kColO, tmem_base + kColPHi + ks * 8, desc_advance(dv_hi, ks * 2048), idesc_o, accum);
         accum = 1;
       }
+      tm[6] = clock64();
       if (split) {
         mbar_wait(&bars->vlo_full, 0);
         tc_fence_after();
@@ -213,6 +225,11 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
           umma_ts(tmem_base + kColO, tmem_base + kColPHi + ks * 8, desc_advance(dv_lo, ks * 2048), idesc_o, 1u);
       }
       umma_commit(&bars->o_full);
+      tm[7] = clock64();
+      if (p.dbg_cycles) {
+        long long* d = p.dbg_cycles + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16;
+        for (int i = 1; i < 8; ++i) d[i - 1] = tm[i] - tm[0];
+      }
     }
     __syncwarp();
   } else {
@@ -224,7 +241,9 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
     const uint32_t trow = tmem_base + ((uint32_t)(lane_group * 32) << 16);
     const float c_scale = 0.08838834764831845f * 1.4426950408889634f;  // 1/sqrt(128) * log2(e)
 
+    const long long ts0 = clock64();
     mbar_wait(&bars->s_full, 0);
+    const long long ts1 = clock64();
     tc_fence_after();
     float sum;
     if (half == 0) {
@@ -240,7 +259,9 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
     const float inv = 1.0f / (bars->red_sum[0][row] + bars->red_sum[1][row]);
 
     // ---------------- output: this thread's row, 64 of the 128 head-dim columns ----------------
+    const long long ts2 = clock64();
     mbar_wait(&bars->o_full, 0);
+    const long long ts3 = clock64();
     tc_fence_after();
     // all MMAs are complete: the Q tile region is free and becomes the store-staging area (8 x 4 KB)
     const uint32_t stage = smem_u32(smem + kOffQHi + sw * kEpiStageBytes);
@@ -263,11 +284,24 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
       split_bf16x2(__uint_as_float(v0[2 * j]) * inv, __uint_as_float(v0[2 * j + 1]) * inv, hw[j], lw[j]);
       split_bf16x2(__uint_as_float(v1[2 * j]) * inv, __uint_as_float(v1[2 * j + 1]) * inv, hw[16 + j], lw[16 + j]);
     }
-    char* dst_hi = reinterpret_cast<char*>(p.out_hi + head * kHeadDim + half * 64);
-    store_block_coalesced(stage, lane, hw, dst_hi, rows, pitch, 8, 1, 0);
-    if (p.nsplit_out == 3) {
-      char* dst_lo = reinterpret_cast<char*>(p.out_lo + head * kHeadDim + half * 64);
-      store_block_coalesced(stage, lane, lw, dst_lo, rows, pitch, 8, 1, 0);
+    const int group_row0 = qtile * kQTile + lane_group * 32;  // first query of this warp's 32 rows
+    if (group_row0 + 32 <= S) {
+      // all 32 rows belong to this sequence: one bulk tensor store per plane straight from the staging tile
+      store_block_tma(stage, lane, hw, &map_o_hi, head * kHeadDim + half * 64, row0 + group_row0);
+      if (p.nsplit_out == 3) store_block_tma(stage, lane, lw, &map_o_lo, head * kHeadDim + half * 64, row0 + group_row0);
+      if (lane == 0) tma_store_wait_read();
+    } else {
+      // the group straddles the end of the sequence: masked coalesced stores
+      char* dst_hi = reinterpret_cast<char*>(p.out_hi + head * kHeadDim + half * 64);
+      store_block_coalesced(stage, lane, hw, dst_hi, rows, pitch, 8, 1, 0);
+      if (p.nsplit_out == 3) {
+        char* dst_lo = reinterpret_cast<char*>(p.out_lo + head * kHeadDim + half * 64);
+        store_block_coalesced(stage, lane, lw, dst_lo, rows, pitch, 8, 1, 0);
+      }
+    }
+    if (p.dbg_cycles && sw == 0 && lane == 0) {
+      long long* d = p.dbg_cycles + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16;
+      d[8] = ts1 - ts0; d[9] = ts2 - ts1; d[10] = ts3 - ts2; d[11] = clock64() - ts3;
     }
   }
 
@@ -287,15 +321,15 @@ cudaError_t configure_attention_kernel() {
 }
 
 cudaError_t launch_attention(const CUtensorMap& q_hi, const CUtensorMap& q_lo, const CUtensorMap& kv_hi,
-                             const CUtensorMap& kv_lo, const AttnParams& p, cudaStream_t stream) {
+                             const CUtensorMap& kv_lo, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const AttnParams& p,
+                             cudaStream_t stream) {
   if (p.seq_len > kKeyPad || p.seq_len < 1 || (p.nsplit != 1 && p.nsplit != 3)) {
     set_last_error("launch_attention: unsupported seq_len=%d nsplit=%d", p.seq_len, p.nsplit);
     return cudaErrorInvalidValue;
   }
   const size_t smem = 1024 + kSmemTiles + sizeof(AttnBarriers);
   dim3 grid((p.seq_len + kQTile - 1) / kQTile, p.num_heads, p.num_seqs);
-  attention_kernel<<<grid, kThreads, smem, stream>>>(q_hi, q_lo, kv_hi, kv_lo, p);
-  return cudaGetLastError();
+  return launch_kernel(attention_kernel, grid, dim3(kThreads), smem, stream, q_hi, q_lo, kv_hi, kv_lo, o_hi, o_lo, p);
 }
 
 }  // namespace cmdi

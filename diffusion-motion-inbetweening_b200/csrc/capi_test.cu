@@ -152,11 +152,31 @@ extern "C" int cmdi_test_attention(const float* qkv, float* O, int num_seqs, int
   if (make_tmap_bf16_2d(&mq_lo, q_lo.p, rows_p, ld, ld, 64, 128)) return 1;
   if (make_tmap_bf16_2d(&mkv_hi, q_hi.p, rows_p, ld, ld, 64, kAttnKeyPad)) return 1;
   if (make_tmap_bf16_2d(&mkv_lo, q_lo.p, rows_p, ld, ld, 64, kAttnKeyPad)) return 1;
+  CUtensorMap mo_hi, mo_lo;
+  if (make_tmap_bf16_2d(&mo_hi, o_hi.p, rows_p, ldo, ldo, 64, 32)) return 1;
+  if (make_tmap_bf16_2d(&mo_lo, o_lo.p, rows_p, ldo, ldo, 64, 32)) return 1;
   CK(configure_attention_kernel());
   AttnParams p{};
   p.num_seqs = num_seqs; p.seq_len = S; p.num_heads = H; p.nsplit = precision; p.nsplit_out = 3;
   p.out_hi = o_hi.as<__nv_bfloat16>(); p.out_lo = o_lo.as<__nv_bfloat16>(); p.ld_out = ldo;
-  CK(launch_attention(mq_hi, mq_lo, mkv_hi, mkv_lo, p, stream));
+  DevBuf adbg;
+  const int nctas = ((S + 127) / 128) * H * num_seqs;
+  if (getenv("CMDI_TEST_DBG")) {
+    CK(adbg.alloc((size_t)nctas * 16 * 8));
+    p.dbg_cycles = adbg.as<long long>();
+    CK(launch_attention(mq_hi, mq_lo, mkv_hi, mkv_lo, mo_hi, mo_lo, p, stream));
+  }
+  CK(launch_attention(mq_hi, mq_lo, mkv_hi, mkv_lo, mo_hi, mo_lo, p, stream));
+  if (p.dbg_cycles) {
+    std::vector<long long> h((size_t)nctas * 16);
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaMemcpy(h.data(), adbg.p, h.size() * 8, cudaMemcpyDeviceToHost));
+    double a[16] = {0};
+    for (int c = 0; c < nctas; ++c) for (int k = 0; k < 12; ++k) a[k] += (double)h[(size_t)c * 16 + k] / nctas;
+    printf("attn dbg cycles (mean per CTA, MMA thread, since start): qk0=%.0f qk1=%.0f S-issued=%.0f P-ready=%.0f Vhi=%.0f PV1-issued=%.0f all-issued=%.0f | softmax warp: wait_S=%.0f softmax=%.0f wait_O=%.0f store=%.0f\n",
+           a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[8], a[9], a[10], a[11]);
+    fflush(stdout);
+  }
   // O = hi + lo (fp32) for the test
   {
     std::vector<uint16_t> hh((size_t)rows * ldo), hl((size_t)rows * ldo);

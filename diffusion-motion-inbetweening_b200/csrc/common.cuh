@@ -23,6 +23,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// 2^x on the SFU (ex2.approx.ftz: relative error ~2^-22, exp2(-inf) = 0)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // bf16 split of an fp32 value: v ~= hi + lo with |v - hi - lo| <= 2^-17 |v|.
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(v);
@@ -42,6 +49,13 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi_word
   const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
   lo_word = *reinterpret_cast<const uint32_t*>(&l);
 }
+
+// ----------------------------------------------------------------------------------------------
+// programmatic dependent launch: a kernel launched with programmaticStreamSerializationAllowed may start while its
+// predecessor drains; it must not touch global memory before griddep_wait() (no-op for ordinary launches)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
 // mbarrier

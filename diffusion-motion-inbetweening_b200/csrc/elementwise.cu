@@ -31,6 +31,8 @@ __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restri
                                                            const float* __restrict__ beta, float eps, int rows,
                                                            float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
                                                            __nv_bfloat16* __restrict__ out_lo) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -99,6 +101,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
 // conditioning token rows
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) token_rows_kernel(const TokenParams p) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int seq = blockIdx.x;
   int t = *p.step_ptr;
   if (p.timestep_map) t = p.timestep_map[t];
@@ -175,6 +179,8 @@ __global__ void fill_normal_ref_kernel(float* out, int B, size_t per_sample, uns
 // l fastest, through a padded smem tile.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) diffusion_step_kernel(const StepParams p) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ float s_noise[32][33];
   const int b = blockIdx.z;
   const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -395,8 +401,7 @@ inline int grid_for(size_t n, int block) {
 
 cudaError_t launch_layernorm512(const float* v, const float* gamma, const float* beta, float eps, int rows, float* out_f32,
                                 __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream) {
-  layernorm512_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(v, gamma, beta, eps, rows, out_f32, out_hi, out_lo);
-  return cudaGetLastError();
+  return launch_kernel(layernorm512_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, v, gamma, beta, eps, rows, out_f32, out_hi, out_lo);
 }
 
 cudaError_t launch_small_linear(const float* in, const float* W, const float* bias, float* out, int rows, int N, int K,
@@ -407,14 +412,12 @@ cudaError_t launch_small_linear(const float* in, const float* W, const float* bi
 }
 
 cudaError_t launch_token_rows(const TokenParams& p, cudaStream_t stream) {
-  token_rows_kernel<<<p.num_seqs, 128, 0, stream>>>(p);
-  return cudaGetLastError();
+  return launch_kernel(token_rows_kernel, dim3(p.num_seqs), dim3(128), 0, stream, p);
 }
 
 cudaError_t launch_diffusion_step(const StepParams& p, cudaStream_t stream) {
   dim3 grid((p.L + 31) / 32, (p.D_pad + 31) / 32, p.B), block(32, 8);
-  diffusion_step_kernel<<<grid, block, 0, stream>>>(p);
-  return cudaGetLastError();
+  return launch_kernel(diffusion_step_kernel, grid, block, 0, stream, p);
 }
 
 cudaError_t launch_ref_to_frames(const float* ref, int B, int D, int L, int D_pad, float* out_f32, __nv_bfloat16* out_hi,

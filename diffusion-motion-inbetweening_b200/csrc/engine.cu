@@ -235,7 +235,7 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
     AttnParams a{};
     a.num_seqs = nseq; a.seq_len = e->S; a.num_heads = e->H; a.nsplit = e->nsplit; a.nsplit_out = e->nsplit;
     a.out_hi = e->attn_p.hi; a.out_lo = e->attn_p.lo; a.ld_out = kDModel;
-    for (int r_ = 0; r_ < reps; ++r_) CK(launch_attention(e->q_map_hi, e->q_map_lo, e->kv_map_hi, e->kv_map_lo, a, s));
+    for (int r_ = 0; r_ < reps; ++r_) CK(launch_attention(e->q_map_hi, e->q_map_lo, e->kv_map_hi, e->kv_map_lo, e->attn_p.st_hi, e->attn_p.st_lo, a, s));
     CKI(mark());
     // out-proj + residual, then LayerNorm1
     LinearParams o{};
@@ -320,6 +320,7 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   if (const char* g = getenv("CMDI_GEMM")) e->use_pair = strcmp(g, "single") != 0;
   if (const char* g = getenv("CMDI_DEBUG")) e->debug = atoi(g);
   if (const char* g = getenv("CMDI_EPI")) e->tma_store = strcmp(g, "stg") != 0;
+  if (const char* g = getenv("CMDI_PDL")) g_use_pdl = atoi(g) != 0;
   e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount; e->nsplit = cfg->precision;
   e->D = cfg->njoints; e->D_pad = round_up(cfg->njoints, 8); e->L = cfg->nframes; e->S = cfg->nframes + 1;
   e->ff = cfg->ff_size; e->H = cfg->num_heads; e->layers = cfg->num_layers; e->maxB = cfg->max_batch;

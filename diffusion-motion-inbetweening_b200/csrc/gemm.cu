@@ -58,6 +58,7 @@ linear_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // 256 or 512 (power of two)
   static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
 
+  griddep_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -96,6 +97,7 @@ linear_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  griddep_wait();  // everything above overlapped the previous kernel's tail; global memory is touched from here on
 
   if (warp_idx == 0) {
     // ===================================== TMA producer =====================================
@@ -239,9 +241,8 @@ cudaError_t launch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const 
   const int num_n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m_blocks * num_n_blocks;
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  linear_kernel<BLOCK_N><<<grid, kNumThreads, smem, stream>>>(a_hi, a_lo, w_hi, w_lo, o_hi, o_lo, o_f32, p, num_stages, num_m_blocks,
-                                                            num_n_blocks);
-  return cudaGetLastError();
+  return launch_kernel(linear_kernel<BLOCK_N>, dim3(grid), dim3(kNumThreads), smem, stream, a_hi, a_lo, w_hi, w_lo, o_hi, o_lo,
+                       o_f32, p, num_stages, num_m_blocks, num_n_blocks);
 }
 
 }  // namespace

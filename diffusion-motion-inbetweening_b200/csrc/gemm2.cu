@@ -51,6 +51,7 @@ linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;       // double-buffered accumulator: 128 lanes x BLOCK_N fp32 each
   static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
 
+  griddep_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -89,6 +90,7 @@ linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   cluster_sync_all();  // barrier inits + TMEM allocation visible to both CTAs
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  griddep_wait();  // everything above overlapped the previous kernel's tail; global memory is touched from here on
 
   if (warp_idx == 0) {
     // ===================================== TMA producer (both CTAs) =====================================
@@ -249,9 +251,8 @@ cudaError_t launch_impl2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const
   const int num_tiles = num_m_pairs * num_n_blocks;
   int clusters = num_sms / 2;
   if (clusters > num_tiles) clusters = num_tiles;
-  linear2_kernel<BLOCK_N><<<2 * clusters, kNumThreads, smem, stream>>>(a_hi, a_lo, w_hi, w_lo, o_hi, o_lo, o_f32, p, num_stages, num_m_pairs,
-                                                                      num_n_blocks);
-  return cudaGetLastError();
+  return launch_kernel(linear2_kernel<BLOCK_N>, dim3(2 * clusters), dim3(kNumThreads), smem, stream, a_hi, a_lo, w_hi, w_lo,
+                       o_hi, o_lo, o_f32, p, num_stages, num_m_pairs, num_n_blocks);
 }
 
 }  // namespace

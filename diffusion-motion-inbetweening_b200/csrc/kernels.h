@@ -74,11 +74,14 @@ struct AttnParams {
   __nv_bfloat16* out_hi;  // [num_seqs*seq_len (+pad), H*128]
   __nv_bfloat16* out_lo;
   int ld_out;
+  long long* dbg_cycles;  // bring-up only: [num_ctas][16] cycle counters or null
 };
 // qkv maps: bf16 [rows, 3*H*128] row-major planes (hi, lo); box {64, 128} for Q, {64, 208} for K and V.
+// o maps: the output planes [rows, H*128] as TMA-store targets, box {64, 32}.
 cudaError_t configure_attention_kernel();
 cudaError_t launch_attention(const CUtensorMap& q_hi, const CUtensorMap& q_lo, const CUtensorMap& kv_hi,
-                             const CUtensorMap& kv_lo, const AttnParams& p, cudaStream_t stream);
+                             const CUtensorMap& kv_lo, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const AttnParams& p,
+                             cudaStream_t stream);
 constexpr int kAttnKeyPad = 208;
 
 // ----------------------------------------------------------------------------------------------
@@ -181,6 +184,25 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t ro
                  uint32_t box_cols, uint32_t box_rows);
 
 void set_last_error(const char* fmt, ...);
+
+// Launch helper: with `pdl` the kernel is allowed to overlap its prologue with the tail of the previous kernel in
+// the stream (programmatic dependent launch; every such kernel calls griddep_wait() before touching global memory).
+extern bool g_use_pdl;  // CMDI_PDL=0 turns it off
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 const char* get_last_error();
 
 }  // namespace cmdi

@@ -8,6 +8,8 @@
 
 namespace cmdi {
 
+bool g_use_pdl = true;
+
 namespace {
 thread_local char g_last_error[1024] = "";
 
