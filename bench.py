@@ -44,8 +44,10 @@ def flops_per_pass(batch: int) -> float:
 KERNEL_FLOPS = {  # algorithmic FLOPs per launch at `batch` sequences of S tokens
     "qkv": lambda b: 2.0 * S * b * D_MODEL * 3 * D_MODEL,
     "out_proj": lambda b: 2.0 * S * b * D_MODEL * D_MODEL,
+    "out_proj_ln1": lambda b: 2.0 * S * b * D_MODEL * D_MODEL,
     "ffn1": lambda b: 2.0 * S * b * D_MODEL * FF,
     "ffn2": lambda b: 2.0 * S * b * D_MODEL * FF,
+    "ffn2_ln2": lambda b: 2.0 * S * b * D_MODEL * FF,
     "attention": lambda b: 2.0 * 2 * S * S * D_MODEL * b,
     "frame_embed": lambda b: 2.0 * L * b * D * D_MODEL,
     "out_head": lambda b: 2.0 * L * b * D * D_MODEL,
@@ -308,7 +310,7 @@ def run_engine(args):
             "config": {"workload": "configs[1]: unconditional DDPM p_sample_loop, T=1000, B=64/GPU, L=196, D=263, MDM 8L/512d/ff1024/4h",
                        "global_batch": world * B, "parallelism": f"batch-sharded x{world}, one NCCL all-gather of finished samples",
                        "l2": "per-step working set (weights 70 MB as bf16 hi+lo, activations ~0.4 GB) exceeds the 126 MB L2; no explicit flush",
-                       "cuda_graph": "one captured 60-kernel step graph, replayed per step, step index on the device"},
+                       "cuda_graph": f"one captured {len(prof) + 1}-kernel step graph, replayed per step, step index on the device"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,6 +1,7 @@
 // Kernel-level C-ABI entry points used by the parity tests (declared in include/condmdi_b200.h).
 // They stage fp32 inputs into the bf16 hi/lo planes the kernels consume, build the TMA descriptors,
 // launch the production kernel and hand back fp32 results.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -200,5 +201,53 @@ extern "C" int cmdi_test_normal(float* out, int B, long long per_sample, unsigne
                                 unsigned long long sample_offset, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CK(launch_fill_normal_ref(out, B, (size_t)per_sample, seed, stream_id, sample_offset, stream));
+  return 0;
+}
+
+extern "C" int cmdi_test_linear_ln(const float* A, const float* W, const float* bias, const float* residual, const float* gamma,
+                                   const float* beta, float* out, int M, int K, int precision, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int N = 512, Kp = round_up(K, 8), Mp = round_up(M, 256);
+  DevBuf a_hi, a_lo, w_hi, w_lo, o_hi, o_lo;
+  CK(a_hi.alloc((size_t)Mp * Kp * 2)); CK(a_lo.alloc((size_t)Mp * Kp * 2));
+  CK(w_hi.alloc((size_t)N * Kp * 2)); CK(w_lo.alloc((size_t)N * Kp * 2));
+  CK(o_hi.alloc((size_t)Mp * N * 2)); CK(o_lo.alloc((size_t)Mp * N * 2));
+  CK(launch_split_planes(A, M, K, K, a_hi.as<__nv_bfloat16>(), a_lo.as<__nv_bfloat16>(), Kp, stream));
+  CK(launch_split_planes(W, N, K, K, w_hi.as<__nv_bfloat16>(), w_lo.as<__nv_bfloat16>(), Kp, stream));
+  CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mo_hi, mo_lo, mo_f32;
+  if (make_tmap_bf16_2d(&ma_hi, a_hi.p, Mp, Kp, Kp, 64, 128)) return 1;
+  if (make_tmap_bf16_2d(&ma_lo, a_lo.p, Mp, Kp, Kp, 64, 128)) return 1;
+  if (make_tmap_bf16_2d(&mw_hi, w_hi.p, N, Kp, Kp, 64, 128)) return 1;
+  if (make_tmap_bf16_2d(&mw_lo, w_lo.p, N, Kp, Kp, 64, 128)) return 1;
+  if (make_tmap_bf16_2d(&mo_hi, o_hi.p, Mp, N, N, 64, 32)) return 1;
+  if (make_tmap_bf16_2d(&mo_lo, o_lo.p, Mp, N, N, 64, 32)) return 1;
+  if (make_tmap_2d(&mo_f32, out, 4, M, N, N, 32, 32)) return 1;
+  CK(configure_linear_ln_kernel());
+  LinearLnParams p{};
+  p.M = M; p.K = K; p.nsplit = precision; p.nsplit_out = 3; p.bias = bias; p.residual = residual; p.gamma = gamma; p.beta = beta;
+  p.eps = 1e-5f;
+  CK(launch_linear_ln(ma_hi, ma_lo, mw_hi, mw_lo, mo_hi, mo_lo, mo_f32, p, num_sms_of_current_device(), stream));
+  CK(cudaStreamSynchronize(stream));
+  // the bf16 planes must reproduce the fp32 output: report the worst |f32 - (hi + lo)| through last_error when it is off
+  {
+    std::vector<uint16_t> hh((size_t)M * N), hl((size_t)M * N);
+    std::vector<float> ho((size_t)M * N);
+    CK(cudaMemcpy(hh.data(), o_hi.p, hh.size() * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hl.data(), o_lo.p, hl.size() * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ho.data(), out, ho.size() * 4, cudaMemcpyDeviceToHost));
+    double worst = 0;
+    for (size_t i = 0; i < ho.size(); ++i) {
+      uint32_t a = (uint32_t)hh[i] << 16, b = (uint32_t)hl[i] << 16;
+      float fa, fb;
+      memcpy(&fa, &a, 4);
+      memcpy(&fb, &b, 4);
+      const double d = fabs((double)ho[i] - ((double)fa + (double)fb)), tol = 1.6e-5 * fabs((double)ho[i]) + 1e-30;
+      if (d > tol && d > worst) worst = d;
+    }
+    if (worst > 0) {
+      set_last_error("linear_ln: bf16 planes disagree with the fp32 output by %.3e", worst);
+      return 1;
+    }
+  }
   return 0;
 }

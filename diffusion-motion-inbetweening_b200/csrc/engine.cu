@@ -51,6 +51,7 @@ struct Planes {  // a bf16 hi/lo operand: [rows, ld] row-major, with TMA maps fo
   CUtensorMap map_hi{}, map_lo{};
   CUtensorMap pair_hi{}, pair_lo{};  // same planes, box height halved: W operand of the CTA-pair kernel
   CUtensorMap st_hi{}, st_lo{};      // same planes as a TMA-store target: box {64, 32}
+  CUtensorMap ln_hi{}, ln_lo{};      // W operand of the fused linear+LayerNorm kernel: box {64, 128}
 };
 
 struct LayerW {
@@ -75,6 +76,7 @@ struct cmdi_engine {
   int device = 0, num_sms = 148;
   int nsplit = 3;
   int debug = 0, bn_wide = kBnWide, bn_narrow = kBnNarrow;  // CMDI_DEBUG / CMDI_BN_WIDE / CMDI_BN_NARROW (bring-up knobs)
+  bool fuse_ln = false;   // CMDI_FUSE_LN=1: out-proj+norm1 and linear2+norm2 as one kernel each (correct, but 2-10% slower at B=64: its 3-pass epilogue is exposed with 50 tiles on 74 clusters; kept for larger batches / later tuning)
   bool tma_store = true;  // CMDI_EPI=stg selects the coalesced-STG epilogue everywhere
   bool use_pair = true;  // CTA-pair (cta_group::2) linear kernels; CMDI_GEMM=single selects the 1-CTA kernels
   int D = 263, D_pad = 264, L = 196, S = 197, ff = 1024, H = 4, layers = 8, maxB = 0;
@@ -104,6 +106,7 @@ struct cmdi_engine {
   Planes xseq_p, x1_p, qkv_p, attn_p, ffh_p;
   CUtensorMap q_map_hi{}, q_map_lo{}, kv_map_hi{}, kv_map_lo{};
   CUtensorMap vsum_st{};  // fp32 TMA-store target for the pre-LayerNorm sums
+  CUtensorMap xseq_st{}, x1_st{};  // fp32 TMA-store targets of the fused linear+LayerNorm kernel
   uint8_t* obs_mask = nullptr;
   float *cond_emb = nullptr, *cond_proj = nullptr, *text_scale = nullptr;
   int* step_ctr = nullptr;  // [2]: step index, block-arrival counter
@@ -136,6 +139,8 @@ int alloc_planes(cmdi_engine* e, Planes* pl, int rows, int cols, int ld, int box
   CKI(make_tmap_bf16_2d(&pl->pair_lo, pl->lo, rows, cols, ld, 64, box_rows / 2));
   CKI(make_tmap_bf16_2d(&pl->st_hi, pl->hi, rows, cols, ld, 64, 32));
   CKI(make_tmap_bf16_2d(&pl->st_lo, pl->lo, rows, cols, ld, 64, 32));
+  CKI(make_tmap_bf16_2d(&pl->ln_hi, pl->hi, rows, cols, ld, 64, 128));
+  CKI(make_tmap_bf16_2d(&pl->ln_lo, pl->lo, rows, cols, ld, 64, 128));
   return 0;
 }
 
@@ -237,27 +242,49 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
     a.out_hi = e->attn_p.hi; a.out_lo = e->attn_p.lo; a.ld_out = kDModel;
     for (int r_ = 0; r_ < reps; ++r_) CK(launch_attention(e->q_map_hi, e->q_map_lo, e->kv_map_hi, e->kv_map_lo, e->attn_p.st_hi, e->attn_p.st_lo, a, s));
     CKI(mark());
-    // out-proj + residual, then LayerNorm1
-    LinearParams o{};
-    o.M = M; o.N = kDModel; o.K = kDModel; o.nsplit = e->nsplit; o.bias = w.bo; o.residual = e->xseq; o.ld_res = kDModel;
-    o.out_f32 = e->vsum; o.ld_f32 = kDModel; o.nsplit_out = e->nsplit;
-    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->attn_p, w.wo, o, kBnNarrow, s, nullptr, &e->vsum_st));
-    CKI(mark());
-    for (int r_ = 0; r_ < reps; ++r_) CK(launch_layernorm512(e->vsum, w.g1, w.be1, 1e-5f, M, e->x1, e->x1_p.hi, e->nsplit == 3 ? e->x1_p.lo : nullptr, s));
-    CKI(mark());
+    // out-proj + residual + LayerNorm1
+    if (e->fuse_ln) {
+      LinearLnParams o{};
+      o.M = M; o.K = kDModel; o.nsplit = e->nsplit; o.nsplit_out = e->nsplit; o.bias = w.bo; o.residual = e->xseq;
+      o.gamma = w.g1; o.beta = w.be1; o.eps = 1e-5f;
+      for (int r_ = 0; r_ < reps; ++r_)
+        CK(launch_linear_ln(e->attn_p.map_hi, e->attn_p.map_lo, w.wo.ln_hi, w.wo.ln_lo, e->x1_p.st_hi, e->x1_p.st_lo, e->x1_st, o,
+                            e->num_sms, s));
+      CKI(mark());
+    } else {
+      LinearParams o{};
+      o.M = M; o.N = kDModel; o.K = kDModel; o.nsplit = e->nsplit; o.bias = w.bo; o.residual = e->xseq; o.ld_res = kDModel;
+      o.out_f32 = e->vsum; o.ld_f32 = kDModel; o.nsplit_out = e->nsplit;
+      for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->attn_p, w.wo, o, kBnNarrow, s, nullptr, &e->vsum_st));
+      CKI(mark());
+      for (int r_ = 0; r_ < reps; ++r_)
+        CK(launch_layernorm512(e->vsum, w.g1, w.be1, 1e-5f, M, e->x1, e->x1_p.hi, e->nsplit == 3 ? e->x1_p.lo : nullptr, s));
+      CKI(mark());
+    }
     // FFN
     LinearParams f1{};
     f1.M = M; f1.N = e->ff; f1.K = kDModel; f1.nsplit = e->nsplit; f1.bias = w.b1; f1.act = 1;
     f1.out_hi = e->ffh_p.hi; f1.out_lo = e->ffh_p.lo; f1.ld_bf = e->ff; f1.nsplit_out = e->nsplit;
     for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->x1_p, w.w1, f1, kBnWide, s, &e->ffh_p));
     CKI(mark());
-    LinearParams f2{};
-    f2.M = M; f2.N = kDModel; f2.K = e->ff; f2.nsplit = e->nsplit; f2.bias = w.b2; f2.residual = e->x1; f2.ld_res = kDModel;
-    f2.out_f32 = e->vsum; f2.ld_f32 = kDModel; f2.nsplit_out = e->nsplit;
-    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->ffh_p, w.w2, f2, kBnNarrow, s, nullptr, &e->vsum_st));
-    CKI(mark());
-    for (int r_ = 0; r_ < reps; ++r_) CK(launch_layernorm512(e->vsum, w.g2, w.be2, 1e-5f, M, e->xseq, e->xseq_p.hi, e->nsplit == 3 ? e->xseq_p.lo : nullptr, s));
-    CKI(mark());
+    if (e->fuse_ln) {
+      LinearLnParams f2{};
+      f2.M = M; f2.K = e->ff; f2.nsplit = e->nsplit; f2.nsplit_out = e->nsplit; f2.bias = w.b2; f2.residual = e->x1;
+      f2.gamma = w.g2; f2.beta = w.be2; f2.eps = 1e-5f;
+      for (int r_ = 0; r_ < reps; ++r_)
+        CK(launch_linear_ln(e->ffh_p.map_hi, e->ffh_p.map_lo, w.w2.ln_hi, w.w2.ln_lo, e->xseq_p.st_hi, e->xseq_p.st_lo, e->xseq_st,
+                            f2, e->num_sms, s));
+      CKI(mark());
+    } else {
+      LinearParams f2{};
+      f2.M = M; f2.N = kDModel; f2.K = e->ff; f2.nsplit = e->nsplit; f2.bias = w.b2; f2.residual = e->x1; f2.ld_res = kDModel;
+      f2.out_f32 = e->vsum; f2.ld_f32 = kDModel; f2.nsplit_out = e->nsplit;
+      for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->ffh_p, w.w2, f2, kBnNarrow, s, nullptr, &e->vsum_st));
+      CKI(mark());
+      for (int r_ = 0; r_ < reps; ++r_)
+        CK(launch_layernorm512(e->vsum, w.g2, w.be2, 1e-5f, M, e->xseq, e->xseq_p.hi, e->nsplit == 3 ? e->xseq_p.lo : nullptr, s));
+      CKI(mark());
+    }
   }
   // output head on tokens 1.. (mdm.py:284 "[1:]", :304-305)
   LinearParams h{};
@@ -267,7 +294,7 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
   CKI(mark());
   return 0;
 }
-int launches_per_pass(const cmdi_engine* e) { return 1 + 1 + e->layers * 7 + 1; }
+int launches_per_pass(const cmdi_engine* e) { return 1 + 1 + e->layers * (e->fuse_ln ? 5 : 7) + 1; }
 
 int check_ready(cmdi_engine* e, int B, bool need_schedule) {
   if (!e->weights_loaded) {
@@ -315,12 +342,14 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   }
   CK(configure_linear_kernels());
   CK(configure_linear2_kernels());
+  CK(configure_linear_ln_kernel());
   CK(configure_attention_kernel());
   cmdi_engine* e = new cmdi_engine();
   if (const char* g = getenv("CMDI_GEMM")) e->use_pair = strcmp(g, "single") != 0;
   if (const char* g = getenv("CMDI_DEBUG")) e->debug = atoi(g);
   if (const char* g = getenv("CMDI_EPI")) e->tma_store = strcmp(g, "stg") != 0;
   if (const char* g = getenv("CMDI_PDL")) g_use_pdl = atoi(g) != 0;
+  if (const char* g = getenv("CMDI_FUSE_LN")) e->fuse_ln = atoi(g) != 0;
   e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount; e->nsplit = cfg->precision;
   e->D = cfg->njoints; e->D_pad = round_up(cfg->njoints, 8); e->L = cfg->nframes; e->S = cfg->nframes + 1;
   e->ff = cfg->ff_size; e->H = cfg->num_heads; e->layers = cfg->num_layers; e->maxB = cfg->max_batch;
@@ -369,6 +398,8 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   A(make_tmap_bf16_2d(&e->kv_map_hi, e->qkv_p.hi, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, kAttnKeyPad));
   A(make_tmap_bf16_2d(&e->kv_map_lo, e->qkv_p.lo, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, kAttnKeyPad));
   A(make_tmap_2d(&e->vsum_st, e->vsum, 4, e->seq_rows_pad, kDModel, kDModel, 32, 32));
+  A(make_tmap_2d(&e->xseq_st, e->xseq, 4, e->seq_rows_pad, kDModel, kDModel, 32, 32));
+  A(make_tmap_2d(&e->x1_st, e->x1, 4, e->seq_rows_pad, kDModel, kDModel, 32, 32));
   A(dev_alloc(e, &e->model_out, (size_t)2 * e->frame_rows_pad * e->D_pad));
   A(dev_alloc(e, &e->pred_x0, (size_t)e->frame_rows_pad * e->D_pad));
   A(dev_alloc(e, &e->x_obs, (size_t)e->frame_rows_pad * e->D_pad));

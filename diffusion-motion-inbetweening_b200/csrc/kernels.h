@@ -62,6 +62,22 @@ cudaError_t launch_linear_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                                const CUtensorMap& w_lo, const LinearParams& p, int block_n, int num_sms,
                                cudaStream_t stream, const LinearStoreMaps* st = nullptr);
 
+// Linear + residual + LayerNorm over full 512-wide rows (out-proj + norm1, linear2 + norm2).   (gemm2_ln.cu)
+struct LinearLnParams {
+  int M, K;               // rows, reduction extent; N is fixed at 512
+  int nsplit, nsplit_out;
+  const float* bias;      // [512]
+  const float* residual;  // fp32 [M, 512]
+  const float* gamma;     // [512]
+  const float* beta;      // [512]
+  float eps;
+};
+cudaError_t configure_linear_ln_kernel();
+// W map: box {64, 128} over [512, K]; o_*: TMA-store targets [rows, 512] (bf16 box {64, 32}, fp32 box {32, 32})
+cudaError_t launch_linear_ln(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+                             const CUtensorMap& o_hi, const CUtensorMap& o_lo, const CUtensorMap& o_f32,
+                             const LinearLnParams& p, int num_sms, cudaStream_t stream);
+
 // ----------------------------------------------------------------------------------------------
 // self-attention core: O = softmax(Q K^T / sqrt(dh)) V per (sequence, head)      (attention.cu)
 // ----------------------------------------------------------------------------------------------

@@ -173,9 +173,12 @@ class Engine:
         with torch.cuda.device(self.device):
             capi.check(self.lib.cmdi_profile_pass(self._h, batch, int(cfg), int(repeats), ms, cap, ctypes.byref(count), _stream_ptr(self.device)),
                        "cmdi_profile_pass")
+        fused = count.value == 2 + 5 * self.cfg.num_layers + 1
+        per_layer = ["qkv", "attention", "out_proj_ln1", "ffn1", "ffn2_ln2"] if fused else \
+            ["qkv", "attention", "out_proj", "ln1", "ffn1", "ffn2", "ln2"]
         names = ["token_rows", "frame_embed"]
         for _ in range(self.cfg.num_layers):
-            names += ["qkv", "attention", "out_proj", "ln1", "ffn1", "ffn2", "ln2"]
+            names += per_layer
         names += ["out_head"]
         return list(zip(names, [ms[i] for i in range(count.value)]))
 

@@ -77,6 +77,23 @@ def test_linear_large_magnitudes_and_zero_rows():
     assert torch.equal(out, torch.zeros_like(out))
 
 
+@pytest.mark.parametrize("M,K", [(256, 512), (300, 512), (12608, 512), (12608, 1024), (25216, 1024)])
+def test_linear_layernorm_fused_meets_fp32_gate(M, K):
+    """out-proj + norm1 / linear2 + norm2 as one kernel: LayerNorm(residual + A W^T + b) * gamma + beta"""
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(512, K, device="cuda", generator=g) / K ** 0.5
+    b, gamma, beta = (torch.randn(512, device="cuda", generator=g) for _ in range(3))
+    res = torch.randn(M, 512, device="cuda", generator=g) * 2 + 0.3
+    out = torch.full((M, 512), float("nan"), device="cuda")
+    C.capi.check(_lib().cmdi_test_linear_ln(_p(A), _p(W), _p(b), _p(res), _p(gamma), _p(beta), _p(out), M, K, 3, None))
+    torch.cuda.synchronize()
+    v = res.double() + A.double() @ W.double().t() + b.double()
+    ref = torch.nn.functional.layer_norm(v, (512,), gamma.double(), beta.double(), 1e-5)
+    assert torch.allclose(out.double(), ref, **GATE)
+    assert (out.double() - ref).abs().max() < 1e-4
+
+
 def ref_attention(qkv, nseq, S, H):
     x = qkv.double().view(nseq, S, 3, H, 128)
     q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
