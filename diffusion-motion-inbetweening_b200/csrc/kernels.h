@@ -190,6 +190,36 @@ cudaError_t launch_split_planes(const float* in, int rows, int cols, int ld_in, 
                                 int ld_out, cudaStream_t stream);
 
 // ----------------------------------------------------------------------------------------------
+// backward pieces for reconstruction guidance      (backward.cu)
+// ----------------------------------------------------------------------------------------------
+struct GuidanceSeedParams {
+  int B, L, D, D_pad, cfg;
+  const float* model_out;    // [B*L (x2 when cfg), D_pad] raw denoiser outputs (uncond half at +B*L rows)
+  const float* text_scale;   // [B]
+  const float* x_obs;        // [B*L, D_pad]
+  const uint8_t* obs_mask;   // [B*L, D_pad]
+  __nv_bfloat16* seed_hi;    // [B*L (x2), D_pad] dL/d(model output rows)
+  __nv_bfloat16* seed_lo;
+};
+cudaError_t launch_guidance_seed(const GuidanceSeedParams& p, cudaStream_t stream);
+cudaError_t launch_layernorm512_bwd(const float* dy, const float* v, const float* gamma, float eps, int rows, float* dv,
+                                    __nv_bfloat16* dv_hi, __nv_bfloat16* dv_lo, cudaStream_t stream);
+struct AttnBwdParams {
+  int num_seqs, seq_len, num_heads;
+  const __nv_bfloat16* qkv_hi;   // stashed forward Q|K|V planes [rows, 3*H*128]
+  const __nv_bfloat16* qkv_lo;
+  const __nv_bfloat16* do_hi;    // dO planes [rows, H*128]
+  const __nv_bfloat16* do_lo;
+  int ld_do;
+  __nv_bfloat16* dqkv_hi;        // out: dQ|dK|dV planes [rows, 3*H*128]
+  __nv_bfloat16* dqkv_lo;
+};
+cudaError_t configure_attention_bwd_kernel();
+cudaError_t launch_attention_bwd(const AttnBwdParams& p, cudaStream_t stream);
+cudaError_t launch_transpose_split(const float* w, int R, int C, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_out,
+                                   cudaStream_t stream);
+
+// ----------------------------------------------------------------------------------------------
 // TMA descriptor creation (tma_host.cu)
 // ----------------------------------------------------------------------------------------------
 // bf16 row-major [rows, cols] with row pitch ld elements; box {box_cols (=64), box_rows}; 128 B swizzle.
