@@ -19,7 +19,7 @@ SAMPLER_DDIM = 1
 EXPORTS = [
     "cmdi_engine_create", "cmdi_engine_destroy", "cmdi_load_weights", "cmdi_set_schedule", "cmdi_model_forward",
     "cmdi_sample", "cmdi_launch_count", "cmdi_last_error", "cmdi_version", "cmdi_test_linear", "cmdi_test_attention",
-    "cmdi_test_layernorm", "cmdi_test_step", "cmdi_test_normal", "cmdi_profile_pass", "cmdi_test_linear_ln",
+    "cmdi_test_layernorm", "cmdi_test_step", "cmdi_test_normal", "cmdi_profile_pass", "cmdi_test_linear_ln", "cmdi_test_layernorm_bwd", "cmdi_test_attention_bwd",
 ]
 
 
@@ -43,7 +43,8 @@ class SampleArgs(Structure):
                 ("init_image", c_void_p), ("x_T", c_void_p), ("noise_tape", c_void_p), ("seed", c_uint64),
                 ("sample_offset", c_uint64), ("cond_emb", c_void_p), ("uncond", c_int32), ("cfg", c_int32), ("text_scale", c_void_p),
                 ("y_mask", c_void_p), ("imputate", c_int32), ("stop_imputation_at", c_int32),
-                ("inpainted_motion", c_void_p), ("inpainting_mask", c_void_p), ("pred_xstart_out", c_void_p),
+                ("inpainted_motion", c_void_p), ("inpainting_mask", c_void_p), ("recon_guidance", c_int32),
+                ("stop_recguidance_at", c_int32), ("recon_coef", POINTER(c_float)), ("pred_xstart_out", c_void_p),
                 ("dump_xstart", c_void_p), ("dump_steps", POINTER(c_int32)), ("n_dump", c_int32),
                 ("host_buffers", c_int32), ("use_graph", c_int32)]
 
@@ -88,6 +89,8 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.cmdi_test_normal.argtypes = [c_void_p, c_int, ctypes.c_longlong, c_uint64, c_uint64, c_uint64, c_void_p]
     lib.cmdi_profile_pass.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_float), c_int, POINTER(c_int), c_void_p]
     lib.cmdi_test_linear_ln.argtypes = [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p]
+    lib.cmdi_test_layernorm_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    lib.cmdi_test_attention_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     _lib = lib
     return lib
 

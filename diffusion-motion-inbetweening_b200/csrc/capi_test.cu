@@ -251,3 +251,44 @@ extern "C" int cmdi_test_linear_ln(const float* A, const float* W, const float* 
   }
   return 0;
 }
+
+extern "C" int cmdi_test_layernorm_bwd(const float* dy, const float* v, const float* gamma, float* dv, int rows, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DevBuf hi;
+  CK(hi.alloc((size_t)rows * 512 * 2));
+  CK(launch_layernorm512_bwd(dy, v, gamma, 1e-5f, rows, dv, hi.as<__nv_bfloat16>(), nullptr, stream));
+  CK(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+// qkv: fp32 [num_seqs*S, 3*H*128], dO: fp32 [num_seqs*S, H*128] -> dqkv fp32 (hi + lo of the kernel's planes)
+extern "C" int cmdi_test_attention_bwd(const float* qkv, const float* dO, float* dqkv, int num_seqs, int S, int H, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int rows = num_seqs * S, ld = 3 * H * 128, ldo = H * 128;
+  DevBuf q_hi, q_lo, d_hi, d_lo, g_hi, g_lo;
+  CK(q_hi.alloc((size_t)rows * ld * 2)); CK(q_lo.alloc((size_t)rows * ld * 2));
+  CK(d_hi.alloc((size_t)rows * ldo * 2)); CK(d_lo.alloc((size_t)rows * ldo * 2));
+  CK(g_hi.alloc((size_t)rows * ld * 2)); CK(g_lo.alloc((size_t)rows * ld * 2));
+  CK(launch_split_planes(qkv, rows, ld, ld, q_hi.as<__nv_bfloat16>(), q_lo.as<__nv_bfloat16>(), ld, stream));
+  CK(launch_split_planes(dO, rows, ldo, ldo, d_hi.as<__nv_bfloat16>(), d_lo.as<__nv_bfloat16>(), ldo, stream));
+  CK(configure_attention_bwd_kernel());
+  AttnBwdParams p{};
+  p.num_seqs = num_seqs; p.seq_len = S; p.num_heads = H; p.qkv_hi = q_hi.as<__nv_bfloat16>(); p.qkv_lo = q_lo.as<__nv_bfloat16>();
+  p.do_hi = d_hi.as<__nv_bfloat16>(); p.do_lo = d_lo.as<__nv_bfloat16>(); p.ld_do = ldo;
+  p.dqkv_hi = g_hi.as<__nv_bfloat16>(); p.dqkv_lo = g_lo.as<__nv_bfloat16>();
+  CK(launch_attention_bwd(p, stream));
+  CK(cudaStreamSynchronize(stream));
+  std::vector<uint16_t> hh((size_t)rows * ld), hl((size_t)rows * ld);
+  std::vector<float> ho((size_t)rows * ld);
+  CK(cudaMemcpy(hh.data(), g_hi.p, hh.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hl.data(), g_lo.p, hl.size() * 2, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < ho.size(); ++i) {
+    uint32_t a = (uint32_t)hh[i] << 16, b = (uint32_t)hl[i] << 16;
+    float fa, fb;
+    memcpy(&fa, &a, 4);
+    memcpy(&fb, &b, 4);
+    ho[i] = fa + fb;
+  }
+  CK(cudaMemcpy(dqkv, ho.data(), ho.size() * 4, cudaMemcpyHostToDevice));
+  return 0;
+}

@@ -236,8 +236,17 @@ __global__ void __launch_bounds__(256) diffusion_step_kernel(const StepParams p)
         const float u = p.model_out[idx + (size_t)p.B * p.L * p.D_pad];
         out = __fadd_rn(u, __fmul_rn(text_scale, __fsub_rn(out, u)));
       }
-      // imputation: (hat_x * ~M) + (x_obs * M)   (gaussian_diffusion.py:435)
-      if (do_impute) {
+      if (p.guided) {
+        // reconstruction guidance (:416-425): cond_grad = grad * ~M ; tilde = hat - (w_r sqrt(abar) / 2) cond_grad ;
+        // output = tilde * ~M + (imputing ? x_obs : hat) * M
+        const float m = p.obs_mask[idx] ? 1.0f : 0.0f;
+        float g = p.guide_grad[idx];
+        if (p.cfg) g = __fadd_rn(g, p.guide_grad[idx + (size_t)p.B * p.L * p.D_pad]);
+        g = __fmul_rn(g, 1.0f - m);
+        const float tilde = __fsub_rn(out, __fmul_rn(p.guide_coef[t], g));
+        out = __fadd_rn(__fmul_rn(tilde, 1.0f - m), __fmul_rn(do_impute ? p.x_obs[idx] : out, m));
+      } else if (do_impute) {
+        // imputation: (hat_x * ~M) + (x_obs * M)   (gaussian_diffusion.py:435)
         const float m = p.obs_mask[idx] ? 1.0f : 0.0f;
         out = __fadd_rn(__fmul_rn(out, 1.0f - m), __fmul_rn(p.x_obs[idx], m));
       }

@@ -60,12 +60,21 @@ struct LayerW {
   float *g1 = nullptr, *be1 = nullptr, *g2 = nullptr, *be2 = nullptr;
 };
 
+struct LayerWT {  // transposed weight planes for dX = dY W
+  Planes wqkvT, woT, w1T, w2T;
+};
+struct LayerStash {  // forward values the backward pass of one layer needs
+  Planes qkv;
+  CUtensorMap q_hi{}, q_lo{}, kv_hi{}, kv_lo{};
+  float *v1 = nullptr, *v2 = nullptr, *pre = nullptr;
+};
+
 struct GraphKey {
   int B, cfg, sampler, impute, stop_at, tape_mode, has_cond;
   float eta;
   const void* tape;
   unsigned long long seed, sample_offset;
-  int t0, uncond;
+  int t0, uncond, guided;
   bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
 };
 
@@ -112,6 +121,14 @@ struct cmdi_engine {
   int* step_ctr = nullptr;  // [2]: step index, block-arrival counter
   float *ref_a = nullptr, *ref_b = nullptr;  // reference-layout staging [maxB, D, L]
   uint8_t *ref_mask = nullptr, *ymask = nullptr;
+  // reconstruction guidance
+  std::vector<LayerWT> lwt;
+  Planes w_inT, w_outT;
+  std::vector<LayerStash> stash;
+  bool stash_ready = false;
+  Planes seed_p;               // dL/d(model output rows), frame-major [2*frame_rows_pad, D_pad]
+  float* guide_grad = nullptr; // dL/dz per pass, frame-major [2*frame_rows_pad, D_pad]
+  float* guide_coef = nullptr; // [T] w_r[t] * sqrt(alpha_bar_t) / 2
   std::map<GraphKey, cudaGraphExec_t> graphs;
   int64_t launches = 0;
 };
@@ -155,7 +172,8 @@ int upload_f32(cmdi_engine* e, float* dst, const cmdi_tensor_desc& t, size_t cou
 }
 
 // fp32 [rows, cols] source -> bf16 planes (zero padded to pl.ld / pl.rows)
-int upload_planes(cmdi_engine* e, Planes& pl, const cmdi_tensor_desc& t, int rows, int cols, float* scratch, cudaStream_t s) {
+int upload_planes(cmdi_engine* e, Planes& pl, const cmdi_tensor_desc& t, int rows, int cols, float* scratch, cudaStream_t s,
+                  Planes* transposed = nullptr) {
   if ((size_t)t.numel != (size_t)rows * cols) {
     set_last_error("tensor %s: expected %d x %d elements, got %lld", t.name, rows, cols, (long long)t.numel);
     return 1;
@@ -166,6 +184,7 @@ int upload_planes(cmdi_engine* e, Planes& pl, const cmdi_tensor_desc& t, int row
     src = scratch;
   }
   CK(launch_split_planes(src, rows, cols, cols, pl.hi, pl.lo, pl.ld, s));
+  if (transposed) CK(launch_transpose_split(src, rows, cols, transposed->hi, transposed->lo, transposed->ld, s));
   return 0;
 }
 
@@ -199,7 +218,7 @@ int run_linear(cmdi_engine* e, const Planes& a, const Planes& w, const LinearPar
 // One denoiser pass over `nseq` sequences whose frame features are in x_state planes (first B sequences;
 // with dup the frame embedding is written for sequences [0,B) and [B,2B)).
 int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond, const int* tmap_dev, cudaStream_t s,
-                 std::vector<cudaEvent_t>* evs = nullptr, int reps = 1) {
+                 std::vector<cudaEvent_t>* evs = nullptr, int reps = 1, std::vector<LayerStash>* stash = nullptr) {
   auto mark = [&]() -> int {
     if (!evs) return 0;
     cudaEvent_t ev;
@@ -228,22 +247,28 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
   for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->x_state_p, e->w_in, p, kBnNarrow, s));
   CKI(mark());
 
+  const bool fuse_ln = e->fuse_ln && !stash;
   for (int l = 0; l < e->layers; ++l) {
     const LayerW& w = e->lw[l];
+    LayerStash* ls = stash ? &(*stash)[l] : nullptr;  // guided steps keep what the backward pass needs, per layer
+    Planes& qkv_out = ls ? ls->qkv : e->qkv_p;
+    float* v1_out = ls ? ls->v1 : e->vsum;
+    float* v2_out = ls ? ls->v2 : e->vsum;
     // QKV projection
     LinearParams q{};
     q.M = M; q.N = 3 * kDModel; q.K = kDModel; q.nsplit = e->nsplit; q.bias = w.bqkv;
-    q.out_hi = e->qkv_p.hi; q.out_lo = e->qkv_p.lo; q.ld_bf = 3 * kDModel; q.nsplit_out = e->nsplit;
-    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->xseq_p, w.wqkv, q, kBnWide, s, &e->qkv_p));
+    q.out_hi = qkv_out.hi; q.out_lo = qkv_out.lo; q.ld_bf = 3 * kDModel; q.nsplit_out = e->nsplit;
+    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->xseq_p, w.wqkv, q, kBnWide, s, &qkv_out));
     CKI(mark());
     // attention core
     AttnParams a{};
     a.num_seqs = nseq; a.seq_len = e->S; a.num_heads = e->H; a.nsplit = e->nsplit; a.nsplit_out = e->nsplit;
     a.out_hi = e->attn_p.hi; a.out_lo = e->attn_p.lo; a.ld_out = kDModel;
-    for (int r_ = 0; r_ < reps; ++r_) CK(launch_attention(e->q_map_hi, e->q_map_lo, e->kv_map_hi, e->kv_map_lo, e->attn_p.st_hi, e->attn_p.st_lo, a, s));
+    for (int r_ = 0; r_ < reps; ++r_) CK(launch_attention(ls ? ls->q_hi : e->q_map_hi, ls ? ls->q_lo : e->q_map_lo, ls ? ls->kv_hi : e->kv_map_hi,
+                                                         ls ? ls->kv_lo : e->kv_map_lo, e->attn_p.st_hi, e->attn_p.st_lo, a, s));
     CKI(mark());
     // out-proj + residual + LayerNorm1
-    if (e->fuse_ln) {
+    if (fuse_ln) {
       LinearLnParams o{};
       o.M = M; o.K = kDModel; o.nsplit = e->nsplit; o.nsplit_out = e->nsplit; o.bias = w.bo; o.residual = e->xseq;
       o.gamma = w.g1; o.beta = w.be1; o.eps = 1e-5f;
@@ -254,20 +279,21 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
     } else {
       LinearParams o{};
       o.M = M; o.N = kDModel; o.K = kDModel; o.nsplit = e->nsplit; o.bias = w.bo; o.residual = e->xseq; o.ld_res = kDModel;
-      o.out_f32 = e->vsum; o.ld_f32 = kDModel; o.nsplit_out = e->nsplit;
-      for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->attn_p, w.wo, o, kBnNarrow, s, nullptr, &e->vsum_st));
+      o.out_f32 = v1_out; o.ld_f32 = kDModel; o.nsplit_out = e->nsplit;
+      for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->attn_p, w.wo, o, kBnNarrow, s, nullptr, ls ? nullptr : &e->vsum_st));
       CKI(mark());
       for (int r_ = 0; r_ < reps; ++r_)
-        CK(launch_layernorm512(e->vsum, w.g1, w.be1, 1e-5f, M, e->x1, e->x1_p.hi, e->nsplit == 3 ? e->x1_p.lo : nullptr, s));
+        CK(launch_layernorm512(v1_out, w.g1, w.be1, 1e-5f, M, e->x1, e->x1_p.hi, e->nsplit == 3 ? e->x1_p.lo : nullptr, s));
       CKI(mark());
     }
     // FFN
     LinearParams f1{};
     f1.M = M; f1.N = e->ff; f1.K = kDModel; f1.nsplit = e->nsplit; f1.bias = w.b1; f1.act = 1;
     f1.out_hi = e->ffh_p.hi; f1.out_lo = e->ffh_p.lo; f1.ld_bf = e->ff; f1.nsplit_out = e->nsplit;
+    if (ls) { f1.out_f32 = ls->pre; f1.ld_f32 = e->ff; f1.f32_pre = 1; }  // pre-activation for the GELU backward
     for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->x1_p, w.w1, f1, kBnWide, s, &e->ffh_p));
     CKI(mark());
-    if (e->fuse_ln) {
+    if (fuse_ln) {
       LinearLnParams f2{};
       f2.M = M; f2.K = e->ff; f2.nsplit = e->nsplit; f2.nsplit_out = e->nsplit; f2.bias = w.b2; f2.residual = e->x1;
       f2.gamma = w.g2; f2.beta = w.be2; f2.eps = 1e-5f;
@@ -278,11 +304,11 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
     } else {
       LinearParams f2{};
       f2.M = M; f2.N = kDModel; f2.K = e->ff; f2.nsplit = e->nsplit; f2.bias = w.b2; f2.residual = e->x1; f2.ld_res = kDModel;
-      f2.out_f32 = e->vsum; f2.ld_f32 = kDModel; f2.nsplit_out = e->nsplit;
-      for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->ffh_p, w.w2, f2, kBnNarrow, s, nullptr, &e->vsum_st));
+      f2.out_f32 = v2_out; f2.ld_f32 = kDModel; f2.nsplit_out = e->nsplit;
+      for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->ffh_p, w.w2, f2, kBnNarrow, s, nullptr, ls ? nullptr : &e->vsum_st));
       CKI(mark());
       for (int r_ = 0; r_ < reps; ++r_)
-        CK(launch_layernorm512(e->vsum, w.g2, w.be2, 1e-5f, M, e->xseq, e->xseq_p.hi, e->nsplit == 3 ? e->xseq_p.lo : nullptr, s));
+        CK(launch_layernorm512(v2_out, w.g2, w.be2, 1e-5f, M, e->xseq, e->xseq_p.hi, e->nsplit == 3 ? e->xseq_p.lo : nullptr, s));
       CKI(mark());
     }
   }
@@ -294,6 +320,93 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
   CKI(mark());
   return 0;
 }
+int ensure_stash(cmdi_engine* e) {
+  if (e->stash_ready) return 0;
+  if (e->S > 197) {
+    set_last_error("reconstruction guidance supports nframes <= 196 (attention backward tile)");
+    return 1;
+  }
+  CK(configure_attention_bwd_kernel());
+  e->stash.resize(e->layers);
+  int rc = 0;
+  for (auto& ls : e->stash) {
+    rc = rc || alloc_planes(e, &ls.qkv, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 128);
+    rc = rc || make_tmap_bf16_2d(&ls.q_hi, ls.qkv.hi, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, 128);
+    rc = rc || make_tmap_bf16_2d(&ls.q_lo, ls.qkv.lo, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, 128);
+    rc = rc || make_tmap_bf16_2d(&ls.kv_hi, ls.qkv.hi, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, kAttnKeyPad);
+    rc = rc || make_tmap_bf16_2d(&ls.kv_lo, ls.qkv.lo, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, kAttnKeyPad);
+    rc = rc || dev_alloc(e, &ls.v1, (size_t)e->seq_rows_pad * kDModel);
+    rc = rc || dev_alloc(e, &ls.v2, (size_t)e->seq_rows_pad * kDModel);
+    rc = rc || dev_alloc(e, &ls.pre, (size_t)e->seq_rows_pad * e->ff);
+  }
+  rc = rc || alloc_planes(e, &e->seed_p, 2 * e->frame_rows_pad, e->D_pad, e->D_pad, 128);
+  rc = rc || dev_alloc(e, &e->guide_grad, (size_t)2 * e->frame_rows_pad * e->D_pad);
+  if (rc) return 1;
+  e->stash_ready = true;
+  return 0;
+}
+
+// Backward pass of the (CFG-wrapped) denoiser w.r.t. its input, seeded with dL/dx0_hat of the reconstruction loss
+// (gaussian_diffusion.py:415-416).  Result: guide_grad[nseq * L, D_pad] (cond rows, then uncond rows under CFG).
+// Scratch: xseq / x1 (fp32 + planes) carry the running gradients; qkv_p / attn_p / ffh_p the per-layer ones.
+constexpr int kBackwardLaunchesPerLayer = 7;
+int run_backward(cmdi_engine* e, int B, bool cfg, cudaStream_t s) {
+  const int nseq = cfg ? 2 * B : B;
+  const int M = nseq * e->S, MF = nseq * e->L;
+  GuidanceSeedParams gp{};
+  gp.B = B; gp.L = e->L; gp.D = e->D; gp.D_pad = e->D_pad; gp.cfg = cfg; gp.model_out = e->model_out;
+  gp.text_scale = e->text_scale; gp.x_obs = e->x_obs; gp.obs_mask = e->obs_mask; gp.seed_hi = e->seed_p.hi; gp.seed_lo = e->seed_p.lo;
+  CK(launch_guidance_seed(gp, s));
+  // output head backward: d(xseq) rows s >= 1; the token rows receive no gradient from the head
+  CK(cudaMemsetAsync(e->xseq, 0, (size_t)M * kDModel * 4, s));
+  LinearParams h{};
+  h.M = MF; h.N = kDModel; h.K = e->D_pad; h.nsplit = e->nsplit; h.rowmap = ROWMAP_FRAMES_TO_SEQ; h.frames = e->L;
+  h.out_f32 = e->xseq; h.ld_f32 = kDModel; h.nsplit_out = e->nsplit;
+  CKI(run_linear(e, e->seed_p, e->w_outT, h, kBnNarrow, s));
+  for (int l = e->layers - 1; l >= 0; --l) {
+    const LayerW& w = e->lw[l];
+    const LayerWT& wt = e->lwt[l];
+    LayerStash& ls = e->stash[l];
+    // LayerNorm2 backward: xseq (dY) -> x1 (dV2)
+    CK(launch_layernorm512_bwd(e->xseq, ls.v2, w.g2, 1e-5f, M, e->x1, e->x1_p.hi, e->x1_p.lo, s));
+    // linear2 backward fused with the GELU backward: dPre = (dV2 W2) * gelu'(pre)
+    LinearParams b2{};
+    b2.M = M; b2.N = e->ff; b2.K = kDModel; b2.nsplit = e->nsplit; b2.grad_aux = ls.pre; b2.ld_aux = e->ff;
+    b2.out_hi = e->ffh_p.hi; b2.out_lo = e->ffh_p.lo; b2.ld_bf = e->ff; b2.nsplit_out = e->nsplit;
+    CKI(run_linear(e, e->x1_p, wt.w2T, b2, kBnWide, s, &e->ffh_p));
+    // linear1 backward + the skip path: dX1 = dPre W1 + dV2
+    LinearParams b1{};
+    b1.M = M; b1.N = kDModel; b1.K = e->ff; b1.nsplit = e->nsplit; b1.residual = e->x1; b1.ld_res = kDModel;
+    b1.out_f32 = e->xseq; b1.ld_f32 = kDModel; b1.nsplit_out = e->nsplit;
+    CKI(run_linear(e, e->ffh_p, wt.w1T, b1, kBnNarrow, s, nullptr, &e->xseq_st));
+    // LayerNorm1 backward: xseq (dX1) -> x1 (dV1)
+    CK(launch_layernorm512_bwd(e->xseq, ls.v1, w.g1, 1e-5f, M, e->x1, e->x1_p.hi, e->x1_p.lo, s));
+    // out-proj backward: dAttn = dV1 Wo
+    LinearParams bo{};
+    bo.M = M; bo.N = kDModel; bo.K = kDModel; bo.nsplit = e->nsplit;
+    bo.out_hi = e->attn_p.hi; bo.out_lo = e->attn_p.lo; bo.ld_bf = kDModel; bo.nsplit_out = e->nsplit;
+    CKI(run_linear(e, e->x1_p, wt.woT, bo, kBnNarrow, s, &e->attn_p));
+    // attention backward: (Q, K, V, dAttn) -> dQ | dK | dV
+    AttnBwdParams ab{};
+    ab.num_seqs = nseq; ab.seq_len = e->S; ab.num_heads = e->H; ab.qkv_hi = ls.qkv.hi; ab.qkv_lo = ls.qkv.lo;
+    ab.do_hi = e->attn_p.hi; ab.do_lo = e->attn_p.lo; ab.ld_do = kDModel; ab.dqkv_hi = e->qkv_p.hi; ab.dqkv_lo = e->qkv_p.lo;
+    CK(launch_attention_bwd(ab, s));
+    // QKV projection backward + the skip path: dX = dQKV Wqkv + dV1
+    LinearParams bq{};
+    bq.M = M; bq.N = kDModel; bq.K = 3 * kDModel; bq.nsplit = e->nsplit; bq.residual = e->x1; bq.ld_res = kDModel;
+    bq.out_f32 = e->xseq; bq.ld_f32 = kDModel; bq.nsplit_out = e->nsplit;
+    if (l == 0) { bq.out_hi = e->xseq_p.hi; bq.out_lo = e->xseq_p.lo; bq.ld_bf = kDModel; }
+    CKI(run_linear(e, e->qkv_p, wt.wqkvT, bq, kBnNarrow, s, l == 0 ? &e->xseq_p : nullptr, &e->xseq_st));
+  }
+  // frame embedding backward: dz rows (frame-major); the token rows of dxseq are dropped
+  LinearParams fi{};
+  fi.M = M; fi.N = e->D_pad; fi.K = kDModel; fi.nsplit = e->nsplit; fi.rowmap = ROWMAP_SEQ_TO_FRAMES; fi.frames = e->L;
+  fi.out_f32 = e->guide_grad; fi.ld_f32 = e->D_pad; fi.nsplit_out = e->nsplit;
+  CKI(run_linear(e, e->xseq_p, e->w_inT, fi, kBnNarrow, s));
+  return 0;
+}
+int launches_per_backward(const cmdi_engine* e) { return 3 + e->layers * kBackwardLaunchesPerLayer + 1; }
+
 int launches_per_pass(const cmdi_engine* e) { return 1 + 1 + e->layers * (e->fuse_ln ? 5 : 7) + 1; }
 
 int check_ready(cmdi_engine* e, int B, bool need_schedule) {
@@ -376,6 +489,15 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
     A(dev_alloc(e, &w.g1, kDModel)); A(dev_alloc(e, &w.be1, kDModel));
     A(dev_alloc(e, &w.g2, kDModel)); A(dev_alloc(e, &w.be2, kDModel));
   }
+  e->lwt.resize(e->layers);
+  for (auto& t : e->lwt) {
+    A(alloc_planes(e, &t.wqkvT, kDModel, 3 * kDModel, 3 * kDModel, kBnNarrow));
+    A(alloc_planes(e, &t.woT, kDModel, kDModel, kDModel, kBnNarrow));
+    A(alloc_planes(e, &t.w1T, kDModel, e->ff, e->ff, kBnNarrow));
+    A(alloc_planes(e, &t.w2T, e->ff, kDModel, kDModel, kBnWide));
+  }
+  A(alloc_planes(e, &e->w_inT, round_up(e->D_pad, kBnNarrow), kDModel, kDModel, kBnNarrow));
+  A(alloc_planes(e, &e->w_outT, kDModel, e->D_pad, e->D_pad, kBnNarrow));
   A(dev_alloc(e, &e->pe, (size_t)5000 * kDModel));
   A(dev_alloc(e, &e->te_w0, (size_t)kDModel * kDModel)); A(dev_alloc(e, &e->te_b0, kDModel));
   A(dev_alloc(e, &e->te_w2, (size_t)kDModel * kDModel)); A(dev_alloc(e, &e->te_b2, kDModel));
@@ -440,6 +562,7 @@ extern "C" int cmdi_engine_destroy(cmdi_engine* e) {
   for (void* p : e->allocs) cudaFree(p);
   if (e->tables) cudaFree(e->tables);
   if (e->d_tmap) cudaFree(e->d_tmap);
+  if (e->guide_coef) cudaFree(e->guide_coef);
   delete e;
   return 0;
 }
@@ -472,14 +595,14 @@ extern "C" int cmdi_load_weights(cmdi_engine* e, const cmdi_tensor_desc* tensors
     const cmdi_tensor_desc* t_ = get(key);                \
     if (t_) rc = rc || upload_f32(e, dst, *t_, count, s); \
   } while (0)
-#define LOAD_PL(pl, key, rows, cols)                                        \
-  do {                                                                      \
-    const cmdi_tensor_desc* t_ = get(key);                                  \
-    if (t_) rc = rc || upload_planes(e, pl, *t_, rows, cols, scratch, s);   \
+#define LOAD_PL(pl, key, rows, cols, tr)                                        \
+  do {                                                                          \
+    const cmdi_tensor_desc* t_ = get(key);                                      \
+    if (t_) rc = rc || upload_planes(e, pl, *t_, rows, cols, scratch, s, tr);   \
   } while (0)
-  LOAD_PL(e->w_in, "input_process.poseEmbedding.weight", kDModel, e->D);
+  LOAD_PL(e->w_in, "input_process.poseEmbedding.weight", kDModel, e->D, &e->w_inT);
   LOAD_F32(e->b_in, "input_process.poseEmbedding.bias", kDModel);
-  LOAD_PL(e->w_out, "output_process.poseFinal.weight", e->D, kDModel);
+  LOAD_PL(e->w_out, "output_process.poseFinal.weight", e->D, kDModel, &e->w_outT);
   LOAD_F32(e->b_out, "output_process.poseFinal.bias", (size_t)e->D);
   LOAD_F32(e->te_w0, "embed_timestep.time_embed.0.weight", (size_t)kDModel * kDModel);
   LOAD_F32(e->te_b0, "embed_timestep.time_embed.0.bias", kDModel);
@@ -493,13 +616,13 @@ extern "C" int cmdi_load_weights(cmdi_engine* e, const cmdi_tensor_desc* tensors
   for (int l = 0; l < e->layers; ++l) {
     LayerW& w = e->lw[l];
     const std::string p = "seqTransEncoder.layers." + std::to_string(l) + ".";
-    LOAD_PL(w.wqkv, p + "self_attn.in_proj_weight", 3 * kDModel, kDModel);
+    LOAD_PL(w.wqkv, p + "self_attn.in_proj_weight", 3 * kDModel, kDModel, &e->lwt[l].wqkvT);
     LOAD_F32(w.bqkv, p + "self_attn.in_proj_bias", (size_t)3 * kDModel);
-    LOAD_PL(w.wo, p + "self_attn.out_proj.weight", kDModel, kDModel);
+    LOAD_PL(w.wo, p + "self_attn.out_proj.weight", kDModel, kDModel, &e->lwt[l].woT);
     LOAD_F32(w.bo, p + "self_attn.out_proj.bias", kDModel);
-    LOAD_PL(w.w1, p + "linear1.weight", e->ff, kDModel);
+    LOAD_PL(w.w1, p + "linear1.weight", e->ff, kDModel, &e->lwt[l].w1T);
     LOAD_F32(w.b1, p + "linear1.bias", (size_t)e->ff);
-    LOAD_PL(w.w2, p + "linear2.weight", kDModel, e->ff);
+    LOAD_PL(w.w2, p + "linear2.weight", kDModel, e->ff, &e->lwt[l].w2T);
     LOAD_F32(w.b2, p + "linear2.bias", kDModel);
     LOAD_F32(w.g1, p + "norm1.weight", kDModel);
     LOAD_F32(w.be1, p + "norm1.bias", kDModel);
@@ -675,9 +798,18 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
     set_last_error("cfg sampling needs cond_emb and text_scale (cfg_sampler.py:26, :35)");
     return 1;
   }
-  if (a->imputate && (!a->inpainted_motion || !a->inpainting_mask)) {
-    set_last_error("imputate needs inpainted_motion and inpainting_mask (editing_util.py:343)");
+  if ((a->imputate || a->recon_guidance) && (!a->inpainted_motion || !a->inpainting_mask)) {
+    set_last_error("imputate / reconstruction_guidance need inpainted_motion and inpainting_mask (editing_util.py:330, :343)");
     return 1;
+  }
+  if (a->recon_guidance) {
+    if (!a->recon_coef) {
+      set_last_error("reconstruction_guidance needs recon_coef");
+      return 1;
+    }
+    CKI(ensure_stash(e));
+    if (!e->guide_coef) CK(cudaMalloc(&e->guide_coef, (size_t)5000 * 4));
+    CK(cudaMemcpyAsync(e->guide_coef, a->recon_coef, (size_t)e->T * 4, cudaMemcpyHostToDevice, s));
   }
   if (a->skip_timesteps < 0 || a->skip_timesteps >= e->T) {
     set_last_error("skip_timesteps %d outside [0, %d)", a->skip_timesteps, e->T);
@@ -713,7 +845,7 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
   CK(launch_ref_to_frames(xT, B, e->D, e->L, e->D_pad, e->x_state, e->x_state_p.hi, e->x_state_p.lo, s));
   e->launches += 1;
   // ---- keyframes ----
-  if (a->imputate) {
+  if (a->imputate || a->recon_guidance) {
     const float* obs = (const float*)stage_in(a->inpainted_motion, e->ref_b, n * 4, host, s, &rc);
     const uint8_t* msk = (const uint8_t*)stage_in(a->inpainting_mask, e->ref_mask, n, host, s, &rc);
     const uint8_t* ym = (const uint8_t*)stage_in(a->y_mask, e->ymask, (size_t)B * e->L, host, s, &rc);
@@ -734,13 +866,16 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
     return 1;
   }
   const bool has_cond = a->cond_emb != nullptr;
-  auto enqueue_step = [&](cudaStream_t st) -> int {
-    CKI(run_denoiser(e, B, a->cfg != 0, (a->uncond && !a->cfg) ? 0 : B, has_cond, e->d_tmap, st));
+  auto enqueue_step = [&](cudaStream_t st, bool guided) -> int {
+    CKI(run_denoiser(e, B, a->cfg != 0, (a->uncond && !a->cfg) ? 0 : B, has_cond, e->d_tmap, st, nullptr, 1,
+                     guided ? &e->stash : nullptr));
+    if (guided) CKI(run_backward(e, B, a->cfg != 0, st));
     StepParams sp{};
     sp.tab = e->tab; sp.step_ptr = e->step_ctr; sp.advance = 1; sp.B = B; sp.L = e->L; sp.D = e->D; sp.D_pad = e->D_pad;
     sp.sampler = a->sampler; sp.eta = a->eta; sp.model_out = e->model_out; sp.cfg = a->cfg != 0; sp.text_scale = e->text_scale;
     sp.x_t = e->x_state; sp.impute = a->imputate != 0; sp.stop_imputation_at = a->stop_imputation_at;
     sp.x_obs = e->x_obs; sp.obs_mask = e->obs_mask;
+    sp.guided = guided; sp.guide_grad = e->guide_grad; sp.guide_coef = e->guide_coef;
     sp.noise_ref = tape; sp.tape_t0 = t0; sp.seed = a->seed; sp.sample_offset = a->sample_offset;
     sp.x_next = e->x_state; sp.x_next_hi = e->x_state_p.hi; sp.x_next_lo = e->nsplit == 3 ? e->x_state_p.lo : nullptr;
     sp.pred_xstart = e->pred_x0;
@@ -748,45 +883,53 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
     return 0;
   };
 
-  cudaGraphExec_t exec = nullptr;
-  if (a->use_graph) {
+  auto get_exec = [&](bool guided, cudaGraphExec_t* out_exec) -> int {
     GraphKey key{};
     memset(&key, 0, sizeof(key));
     key.B = B; key.cfg = a->cfg != 0; key.sampler = a->sampler; key.impute = a->imputate != 0;
     key.stop_at = a->stop_imputation_at; key.tape_mode = tape != nullptr; key.has_cond = has_cond; key.eta = a->eta;
     key.tape = tape; key.seed = a->seed; key.sample_offset = a->sample_offset; key.t0 = t0; key.uncond = a->uncond != 0;
+    key.guided = guided;
     auto it = e->graphs.find(key);
-    if (it == e->graphs.end()) {
-      // capture on a private stream so a caller's legacy/default stream is never put into capture mode
-      cudaStream_t cs = nullptr;
-      CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-      cudaGraph_t graph = nullptr;
-      CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-      const int erc = enqueue_step(cs);
-      cudaError_t ce = cudaStreamEndCapture(cs, &graph);
-      cudaStreamDestroy(cs);
-      if (erc) return 1;
-      CK(ce);
-      CK(cudaGraphInstantiate(&exec, graph, 0));
-      cudaGraphDestroy(graph);
-      if (e->graphs.size() > 16) {  // bounded cache
-        for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
-        e->graphs.clear();
-      }
-      e->graphs[key] = exec;
-    } else {
-      exec = it->second;
+    if (it != e->graphs.end()) {
+      *out_exec = it->second;
+      return 0;
     }
-  }
+    // capture on a private stream so a caller's legacy/default stream is never put into capture mode
+    cudaStream_t cs = nullptr;
+    CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    const int erc = enqueue_step(cs, guided);
+    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    cudaStreamDestroy(cs);
+    if (erc) return 1;
+    CK(ce);
+    cudaGraphExec_t ex = nullptr;
+    CK(cudaGraphInstantiate(&ex, graph, 0));
+    cudaGraphDestroy(graph);
+    if (e->graphs.size() > 16) {  // bounded cache
+      for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+      e->graphs.clear();
+    }
+    e->graphs[key] = ex;
+    *out_exec = ex;
+    return 0;
+  };
+  cudaGraphExec_t exec_plain = nullptr, exec_guided = nullptr;
 
   int dump_i = 0;
   for (int k = 0; k < nsteps; ++k) {
-    if (exec) {
-      CK(cudaGraphLaunch(exec, s));
+    // utils/editing_util.py:325-333: guidance is active while t >= stop_recguidance_at (t is uniform over the batch)
+    const bool guided = a->recon_guidance && (t0 - k) >= a->stop_recguidance_at;
+    if (a->use_graph) {
+      cudaGraphExec_t& ex = guided ? exec_guided : exec_plain;
+      if (!ex) CKI(get_exec(guided, &ex));
+      CK(cudaGraphLaunch(ex, s));
     } else {
-      CKI(enqueue_step(s));
+      CKI(enqueue_step(s, guided));
     }
-    e->launches += launches_per_pass(e) + 1;
+    e->launches += launches_per_pass(e) + 1 + (guided ? launches_per_backward(e) : 0);
     if (a->dump_xstart && dump_i < a->n_dump && a->dump_steps[dump_i] == k) {
       if (host) {
         CK(launch_frames_to_ref(e->pred_x0, B, e->D, e->L, e->D_pad, e->ref_b, s));

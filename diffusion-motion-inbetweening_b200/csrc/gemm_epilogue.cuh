@@ -25,6 +25,11 @@ constexpr int kEpiStageBytes = 32 * 128;  // per epilogue warp
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// d/dx [0.5 x (1 + erf(x / sqrt 2))]
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -225,14 +230,42 @@ __device__ __forceinline__ void epilogue_tile(const LinearParams& p, const EpiSt
         for (int j = 0; j < 32; ++j) f[h * 32 + j] += __uint_as_float(r[j]);
       }
     }
+    if (p.grad_aux) {
+      // GELU backward: dPre = dH * gelu'(pre), pre stashed by the forward pass
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[32];
+        load_block_coalesced(stage, lane, r, reinterpret_cast<const char*>(p.grad_aux + n0 + h * 32), rows,
+                             (long long)p.ld_aux * 4, (p.N - n0 - h * 32) / 4);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[h * 32 + j] *= gelu_erf_grad(__uint_as_float(r[j]));
+      }
+    }
+    if (ncopies == 0) continue;
+    if (p.f32_pre && p.out_f32) {
+      // stash the pre-activation value (fp32) before the activation is applied
+      const long long dup = (long long)p.dup_row_offset * p.ld_f32 * 4;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t w[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(f[h * 32 + j]);
+        const int nb = n0 + h * 32;
+        if (p.tma_store) {
+          if (nb < p.N) store_block_tma(stage, lane, w, maps.f32, nb, warp_row0);
+        } else {
+          store_block_coalesced(stage, lane, w, reinterpret_cast<char*>(p.out_f32 + nb), rows, (long long)p.ld_f32 * 4,
+                                (p.N - nb) / 4, ncopies, dup);
+        }
+      }
+    }
     if (p.act == 1) {
 #pragma unroll
       for (int j = 0; j < 64; ++j) f[j] = gelu_erf(f[j]);
     }
-    if (ncopies == 0) continue;
     if (p.tma_store) {
       // identity row map: the staging tile goes out as one bulk tensor store per 32 x 128 B block
-      if (p.out_f32) {
+      if (p.out_f32 && !p.f32_pre) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t w[32];
@@ -250,7 +283,7 @@ __device__ __forceinline__ void epilogue_tile(const LinearParams& p, const EpiSt
       }
       continue;
     }
-    if (p.out_f32) {
+    if (p.out_f32 && !p.f32_pre) {
       // two 32-column fp32 blocks: 128 B per row each
       const long long dup = (long long)p.dup_row_offset * p.ld_f32 * 4;
 #pragma unroll

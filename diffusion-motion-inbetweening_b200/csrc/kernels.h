@@ -36,6 +36,9 @@ struct LinearParams {
   int ld_res;
   const float* pos_enc;  // fp32 [L+1, N] table added per output sequence position (ROWMAP_FRAMES_TO_SEQ); or null
   int act;               // 0 none, 1 exact erf GELU
+  int f32_pre;           // 1: out_f32 receives the value BEFORE the activation (stash for the GELU backward)
+  const float* grad_aux; // fp32 [rows, ld_aux] or null: multiply by gelu'(grad_aux[row, col])  (GELU backward)
+  int ld_aux;
   int rowmap;            // RowMap
   int frames;            // L for the two sequence row maps
   int dup_row_offset;    // >0: also store every output row at (row + dup_row_offset)  (CFG: cond + uncond copies)
@@ -157,6 +160,10 @@ struct StepParams {
   int stop_imputation_at;
   const float* x_obs;          // [B*L, D_pad] frame-major
   const uint8_t* obs_mask;     // [B*L, D_pad] frame-major, already AND-ed with y.mask
+  // reconstruction guidance (gaussian_diffusion.py:418-425): x0_tilde = x0_hat - coef[t] * (grad * ~M)
+  int guided;
+  const float* guide_grad;     // [B*L (x2 when cfg), D_pad] dL/dz of the cond (and uncond) pass
+  const float* guide_coef;     // [T] w_r[t] * sqrt(alpha_bar_t) / 2
   // noise
   const float* noise_ref;      // tape base, reference layout [steps][B, D, 1, L]; slice (tape_t0 - t) is this step's
                                // randn_like draw; null -> in-kernel Philox

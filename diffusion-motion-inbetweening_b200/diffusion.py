@@ -14,7 +14,7 @@ Python, no per-step H2D table copies, no per-step host sync (the reference syncs
 
 Not accelerated (raise NotImplementedError, like the reference does for its own unsupported branches):
 cond_fn / 'gmd' classifier guidance, learned variances, EPSILON/PREVIOUS_X parametrisations,
-`reconstruction_guidance` (needs the denoiser's input-VJP), const_noise.
+const_noise.  `reconstruction_guidance` runs a backward pass through the denoiser on the GPU (csrc/backward.cu).
 """
 from __future__ import annotations
 
@@ -27,6 +27,7 @@ import numpy as np
 import torch
 
 from . import capi
+from .editing_util import get_gradient_schedule
 from .model import resolve_model
 
 
@@ -138,9 +139,8 @@ class GaussianDiffusion:
         if "gmd" in y.keys():
             raise NotImplementedError("'gmd' selects p_sample_with_grad (classifier guidance): out of scope")
         if y.get("reconstruction_guidance", False):
-            assert "stop_recguidance_at" in y.keys()
+            assert "stop_recguidance_at" in y.keys()  # utils/editing_util.py:329-330
             assert "inpainting_mask" in y.keys() and "inpainted_motion" in y.keys()
-            raise NotImplementedError("reconstruction_guidance needs the denoiser input-VJP on the GPU (not built yet)")
         return y
 
     def _run(self, sampler, model, shape, noise, cond_fn, model_kwargs, device, skip_timesteps, init_image, randomize_class,
@@ -188,6 +188,22 @@ class GaussianDiffusion:
                 pass  # the reference's 'marginal' branch only calls the model (:437-439)
             else:
                 raise NotImplementedError
+        # ---- reconstruction guidance (gaussian_diffusion.py:405-425, editing_util.py:325-333) ----
+        recon, stop_rg, coef = False, 0, None
+        if y.get("reconstruction_guidance", False):
+            recon, stop_rg = True, int(y["stop_recguidance_at"])
+            if obs is None:
+                obs = y["inpainted_motion"].to(device=device, dtype=torch.float32)
+                mask = y["inpainting_mask"].to(device=device)
+                assert obs.shape == mask.shape == tuple(shape)  # :414
+                y_mask = y["mask"].to(device=device).reshape(B, -1)
+            # w_r[t] * sqrt(alpha_bar_t) / 2, in fp32 exactly as the reference forms it (:418-422); the schedule is
+            # indexed by the sampler step t like _extract_into_tensor(grad_ws, t, ...) does
+            ws = get_gradient_schedule(y["gradient_schedule"], y["diffusion_steps"])
+            tt = torch.arange(self.num_timesteps)
+            w_r = torch.from_numpy(ws)[tt].float() * y["reconstruction_weight"]
+            sab = torch.from_numpy(self.sqrt_alphas_cumprod)[tt].float()
+            coef = (w_r * sab / 2).float().cpu().numpy()
         # ---- noise ----
         tape = self.noise_tape  # tape[0]: the initial randn(*shape) draw; tape[1 + k]: the k-th randn_like draw
         if noise is not None:
@@ -209,7 +225,8 @@ class GaussianDiffusion:
             init_image = init_image.to(device=device, dtype=torch.float32)
         common = dict(batch=B, sampler=sampler, eta=eta, cond_emb=cond_emb, uncond=uncond, cfg=is_cfg, text_scale=text_scale,
                       y_mask=y_mask, imputate=imputate, stop_imputation_at=stop_at, inpainted_motion=obs,
-                      inpainting_mask=mask, seed=seed, sample_offset=self.sample_offset, use_graph=self.use_graph)
+                      inpainting_mask=mask, seed=seed, sample_offset=self.sample_offset, use_graph=self.use_graph,
+                      recon_guidance=recon, stop_recguidance_at=stop_rg, recon_coef=coef)
         if not progressive:
             res = eng.sample(skip_timesteps=skip_timesteps, init_image=init_image, x_T=x_T,
                              noise_tape=None if tape is None else tape, want_pred_xstart=False, dump_steps=dump_steps, **common)

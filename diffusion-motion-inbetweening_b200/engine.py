@@ -110,6 +110,7 @@ class Engine:
                cond_emb: Optional[torch.Tensor] = None, cfg: bool = False, text_scale: Optional[torch.Tensor] = None,
                y_mask: Optional[torch.Tensor] = None, imputate: bool = False, stop_imputation_at: int = 0,
                inpainted_motion: Optional[torch.Tensor] = None, inpainting_mask: Optional[torch.Tensor] = None,
+               recon_guidance: bool = False, stop_recguidance_at: int = 0, recon_coef: Optional[Sequence[float]] = None,
                want_pred_xstart: bool = False, dump_steps: Optional[Sequence[int]] = None, host_buffers: bool = False,
                use_graph: bool = True, out: Optional[torch.Tensor] = None):
         """The whole sampling loop in one native call. Tensors are in the reference layout (B, njoints, 1, nframes).
@@ -150,10 +151,17 @@ class Engine:
             n_dump = len(steps_sorted)
             dump_arr = (ctypes.c_int32 * max(n_dump, 1))(*steps_sorted)
             dump = torch.empty((max(n_dump, 1),) + shape, dtype=torch.float32, device=dev, pin_memory=host_buffers)
+        coef_arr = None
+        if recon_guidance:
+            coef = np.ascontiguousarray(np.asarray(recon_coef, dtype=np.float32))
+            if coef.shape != (self.num_timesteps,):
+                raise ValueError(f"recon_coef must have one entry per sampler step ({self.num_timesteps})")
+            coef_arr = coef.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
         a = capi.SampleArgs(batch, sampler, float(eta), int(skip_timesteps), int(num_steps), int(resume), _ptr(init_image), _ptr(x_T), _ptr(noise_tape),
                             int(seed) & (2 ** 64 - 1), int(sample_offset), _ptr(cond_emb), int(uncond), int(cfg), _ptr(text_scale),
                             _ptr(y_mask), int(imputate), int(stop_imputation_at), _ptr(inpainted_motion),
-                            _ptr(inpainting_mask), _ptr(pred), _ptr(dump), dump_arr, n_dump, int(host_buffers),
+                            _ptr(inpainting_mask), int(recon_guidance), int(stop_recguidance_at), coef_arr, _ptr(pred), _ptr(dump),
+                            dump_arr, n_dump, int(host_buffers),
                             int(use_graph))
         with torch.cuda.device(self.device):
             capi.check(self.lib.cmdi_sample(self._h, ctypes.byref(a), out.data_ptr(), _stream_ptr(self.device)),

@@ -108,6 +108,11 @@ typedef struct {
   int32_t stop_imputation_at;
   const float* inpainted_motion;   /* ref layout */
   const uint8_t* inpainting_mask;  /* ref layout, bool bytes */
+  /* reconstruction guidance, gaussian_diffusion.py:405-425 + utils/editing_util.py:325-333: at steps t >= stop_recguidance_at
+   * x0_hat is moved along -d/dz sum((inpainted_motion - x0_hat(z))^2 * M) (a backward pass through the denoiser) */
+  int32_t recon_guidance;
+  int32_t stop_recguidance_at;
+  const float* recon_coef;         /* HOST array [T]: w_r[t] * reconstruction_weight * sqrt(alphas_cumprod[t]) / 2, fp32 */
   /* outputs */
   float* pred_xstart_out;       /* ref layout, last step's pred_xstart, or NULL */
   float* dump_xstart;           /* (n_dump, B, 263, 1, 196) pred_xstart at the loop iterations listed in dump_steps, or NULL */
@@ -144,6 +149,9 @@ CMDI_API int cmdi_test_step(cmdi_engine* e, int sampler, float eta, int t, int B
                    const float* text_scale, const float* x_t, const float* noise, int impute, int stop_imputation_at,
                    const float* x_obs, const uint8_t* mask, float* x_next, float* pred_xstart, void* stream);
 
+/* backward pieces of reconstruction guidance (fp32 in / out) */
+CMDI_API int cmdi_test_layernorm_bwd(const float* dy, const float* v, const float* gamma, float* dv, int rows, void* stream);
+CMDI_API int cmdi_test_attention_bwd(const float* qkv, const float* dO, float* dqkv, int num_seqs, int S, int H, void* stream);
 /* per-launch device times (ms, mean over `repeats` back-to-back launches of each kernel) of one denoiser pass at
  * `batch` (x2 sequences when cfg), in launch order:
  * token_rows, frame_embed, {qkv, attention, out_proj, ln1, ffn1, ffn2, ln2} x num_layers, out_head */

@@ -138,6 +138,37 @@ def test_layernorm():
     assert torch.allclose(out.double(), ref, rtol=1e-5, atol=1e-5)
 
 
+def test_layernorm_backward_matches_autograd():
+    g = torch.Generator(device="cuda").manual_seed(2)
+    v32 = torch.randn(777, 512, device="cuda", generator=g) * 2 + 0.3
+    gamma32 = torch.randn(512, device="cuda", generator=g)
+    dy32 = torch.randn(777, 512, device="cuda", generator=g)
+    v = v32.double().requires_grad_(True)
+    y = torch.nn.functional.layer_norm(v, (512,), gamma32.double(), torch.zeros(512, device="cuda", dtype=torch.float64), 1e-5)
+    (ref,) = torch.autograd.grad(y, v, dy32.double())
+    out = torch.empty(777, 512, device="cuda")
+    C.capi.check(_lib().cmdi_test_layernorm_bwd(_p(dy32), _p(v32), _p(gamma32), _p(out), 777, None))
+    torch.cuda.synchronize()
+    err = (out.double() - ref).abs().max().item()
+    assert err < 2e-5, err  # fp32 kernel vs fp64 autograd on identical fp32 inputs (|dV| up to ~4)
+
+
+@pytest.mark.parametrize("nseq,S,H", [(1, 197, 1), (3, 197, 4), (2, 50, 4), (2, 5, 2)])
+def test_attention_backward_matches_autograd(nseq, S, H):
+    g = torch.Generator(device="cuda").manual_seed(S)
+    qkv = torch.randn(nseq * S, 3 * H * 128, device="cuda", generator=g)
+    dO = torch.randn(nseq * S, H * 128, device="cuda", generator=g)
+    x = qkv.double().requires_grad_(True)
+    out = ref_attention(x, nseq, S, H)
+    (ref,) = torch.autograd.grad(out, x, dO.double())
+    got = torch.full_like(qkv, float("nan"))
+    C.capi.check(_lib().cmdi_test_attention_bwd(_p(qkv), _p(dO), _p(got), nseq, S, H, None))
+    torch.cuda.synchronize()
+    # inputs are rounded to bf16 hi+lo (2^-17) on the way in, fp32 arithmetic inside
+    assert torch.allclose(got.double(), ref, rtol=1e-3, atol=1e-4)
+    assert (got.double() - ref).abs().max() < 1e-4
+
+
 def test_counter_based_normal_generator():
     n = 263 * 196
     a = torch.empty(8, n, device="cuda")

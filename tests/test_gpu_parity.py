@@ -142,6 +142,49 @@ def test_cfg_imputation_loop_vs_reference_golden(texty, gi, gold):
     assert len(dump) == 2 and torch.equal(dump[1], outs[2]["pred_xstart"]) and torch.equal(dump[0], outs[0]["pred_xstart"])
 
 
+def test_reconstruction_guidance_vs_reference_golden(texty, gi, gold):
+    """config 4 of BASELINE.json: CFG + imputation + reconstruction guidance (weight 20), first 2 steps (t = 999, 998)"""
+    m, sd = texty
+    w = C.ClassifierFreeSampleModel(m)
+    diff = C.create_gaussian_diffusion()
+    diff.noise_tape = gi["tape"].to(DEV)
+    x_obs, kf = gi["x_obs"].to(DEV), gi["kf_mask"].to(DEV)
+    ykw = {"text": ["a", "b"], "text_scale": gi["text_scale"].to(DEV), "mask": gi["y_mask"].to(DEV), "lengths": gi["lengths"],
+           "imputate": 1, "stop_imputation_at": 1, "replacement_distribution": "conditional", "inpainted_motion": x_obs,
+           "inpainting_mask": kf, "reconstruction_guidance": True, "reconstruction_weight": 20.0, "gradient_schedule": None,
+           "diffusion_steps": 1000, "stop_recguidance_at": 0}
+    outs = []
+    for k, o in enumerate(diff.p_sample_loop_progressive(w, (B, D, 1, L), model_kwargs={"y": ykw})):
+        outs.append(o)
+        if k == 1:
+            break
+    assert close(outs[1]["sample"], gold["recon.sample"], **GATE)
+    assert close(outs[1]["pred_xstart"], gold["recon.pred_xstart"], **GATE)
+    # and against the oracle's autograd implementation, one more step further
+    c = O.Conditioning(cond_emb=gi["cond"], cfg=True, text_scale=gi["text_scale"], y_mask=gi["y_mask"], imputate=True,
+                       stop_imputation_at=1, inpainted_motion=gi["x_obs"], inpainting_mask=gi["kf_mask"],
+                       reconstruction_guidance=True, reconstruction_weight=20.0)
+    ref = O.sample_loop(sd, O.make_tables(""), (B, D, 1, L), c, gi["tape"], "ddpm", max_steps=2, return_all=True)
+    assert close(outs[1]["sample"], ref[-1]["sample"], **GATE)
+
+
+def test_reconstruction_guidance_without_imputation_and_stop_step(texty, gi):
+    """guidance only (no imputation), no CFG wrapper, exponential schedule, stop_recguidance_at inside the run"""
+    m, sd = texty
+    diff = C.create_gaussian_diffusion()
+    diff.noise_tape = gi["tape"].to(DEV)
+    x_obs, kf = gi["x_obs"].to(DEV), gi["kf_mask"].to(DEV)
+    ykw = {"text": ["a", "b"], "mask": gi["y_mask"].to(DEV), "inpainted_motion": x_obs, "inpainting_mask": kf,
+           "reconstruction_guidance": True, "reconstruction_weight": 5.0, "gradient_schedule": "exponential",
+           "diffusion_steps": 1000, "stop_recguidance_at": 2}
+    got = diff.p_sample_loop(m, (B, D, 1, L), model_kwargs={"y": ykw}, skip_timesteps=996, init_image=x_obs)  # t = 3, 2, 1, 0
+    c = O.Conditioning(cond_emb=gi["cond"], y_mask=gi["y_mask"], inpainted_motion=gi["x_obs"], inpainting_mask=gi["kf_mask"],
+                       reconstruction_guidance=True, reconstruction_weight=5.0, gradient_schedule="exponential",
+                       stop_recguidance_at=2)
+    ref = O.sample_loop(sd, O.make_tables(""), (B, D, 1, L), c, gi["tape"], "ddpm", skip_timesteps=996, init_image=gi["x_obs"])
+    assert close(got, ref, **GATE)
+
+
 def test_marginal_replacement_is_plain_sampling(texty, gi):
     """gaussian_diffusion.py:437-439: the 'marginal' branch only calls the model."""
     m, sd = texty
