@@ -291,8 +291,17 @@ def run_engine(args):
     dom_ms = by_kind[dom][0] / by_kind[dom][1]
     achieved = KERNEL_FLOPS[dom](B) / (dom_ms * 1e-3) / 1e12
     split = 3 if precision == C.capi.PRECISION_BF16X3 else 1
-    roofline = {"bound": "tensor", "kernel": f"linear_kernel ({dom}), {by_kind[dom][1]} launches/step", "achieved": achieved,
-                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture (per launch, like `achieved`)
+        with open(os.path.join(ROOT, "profiles", "r01c_dominant_kernel_traffic.json")) as f:
+            tr = json.load(f)
+        if tr.get("kernel") == dom:
+            traffic, traffic_src = tr["dram_bytes_read"] + tr["dram_bytes_write"], tr["source"]
+    except (OSError, ValueError, KeyError):
+        pass
+    roofline = {"bound": "tensor", "kernel": f"linear2_kernel ({dom}), {by_kind[dom][1]} launches/step", "achieved": achieved,
+                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
+                "traffic_unit": "bytes of DRAM read + written per launch", "traffic_source": traffic_src,
                 "peak_source": peaks["source"], "launch_ms": dom_ms, "share_of_step": by_kind[dom][0] / step_ms,
                 "mma_terms_per_product": split, "tensor_pipe_frac_incl_split": split * achieved / peaks["bf16_tflops"],
                 "whole_step_algorithmic_tflops": flops_per_pass(B) * args.steps / (ms * 1e-3) / 1e12,

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libcondmdi_b200.so")
 
 PRECISION_BF16X3 = 3
 PRECISION_BF16 = 1
+RNG_ENGINE, RNG_TORCH = 0, 1
 SAMPLER_DDPM = 0
 SAMPLER_DDIM = 1
 
@@ -20,6 +21,7 @@ EXPORTS = [
     "cmdi_engine_create", "cmdi_engine_destroy", "cmdi_load_weights", "cmdi_set_schedule", "cmdi_model_forward",
     "cmdi_sample", "cmdi_launch_count", "cmdi_last_error", "cmdi_version", "cmdi_test_linear", "cmdi_test_attention",
     "cmdi_test_layernorm", "cmdi_test_step", "cmdi_test_normal", "cmdi_profile_pass", "cmdi_test_linear_ln", "cmdi_test_layernorm_bwd", "cmdi_test_attention_bwd",
+    "cmdi_test_normal_aten",
 ]
 
 
@@ -41,7 +43,8 @@ class ForwardArgs(Structure):
 class SampleArgs(Structure):
     _fields_ = [("batch", c_int32), ("sampler", c_int32), ("eta", c_float), ("skip_timesteps", c_int32), ("num_steps", c_int32), ("resume", c_int32),
                 ("init_image", c_void_p), ("x_T", c_void_p), ("noise_tape", c_void_p), ("seed", c_uint64),
-                ("sample_offset", c_uint64), ("cond_emb", c_void_p), ("uncond", c_int32), ("cfg", c_int32), ("text_scale", c_void_p),
+                ("sample_offset", c_uint64), ("rng_mode", c_int32), ("aten_offset", c_uint64), ("aten_increment", c_uint64),
+                ("aten_threads", ctypes.c_uint32), ("cond_emb", c_void_p), ("uncond", c_int32), ("cfg", c_int32), ("text_scale", c_void_p),
                 ("y_mask", c_void_p), ("imputate", c_int32), ("stop_imputation_at", c_int32),
                 ("inpainted_motion", c_void_p), ("inpainting_mask", c_void_p), ("recon_guidance", c_int32),
                 ("stop_recguidance_at", c_int32), ("recon_coef", POINTER(c_float)), ("pred_xstart_out", c_void_p),
@@ -87,6 +90,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.cmdi_test_step.argtypes = [c_void_p, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.cmdi_test_normal.argtypes = [c_void_p, c_int, ctypes.c_longlong, c_uint64, c_uint64, c_uint64, c_void_p]
+    lib.cmdi_test_normal_aten.argtypes = [c_void_p, ctypes.c_longlong, c_uint64, c_uint64, ctypes.c_uint32, c_void_p]
     lib.cmdi_profile_pass.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_float), c_int, POINTER(c_int), c_void_p]
     lib.cmdi_test_linear_ln.argtypes = [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p]
     lib.cmdi_test_layernorm_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]

@@ -197,6 +197,17 @@ extern "C" int cmdi_test_attention(const float* qkv, float* O, int num_seqs, int
   return 0;
 }
 
+extern "C" int cmdi_test_normal_aten(float* out, long long numel, unsigned long long seed, unsigned long long offset,
+                                     unsigned int threads, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (threads == 0 || (offset & 3) || numel < 0) {
+    set_last_error("cmdi_test_normal_aten: threads must be > 0 and offset a multiple of 4");
+    return 1;
+  }
+  CK(launch_fill_normal_aten(out, (size_t)numel, seed, offset, threads, stream));
+  return 0;
+}
+
 extern "C" int cmdi_test_normal(float* out, int B, long long per_sample, unsigned long long seed, unsigned long long stream_id,
                                 unsigned long long sample_offset, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

@@ -11,6 +11,8 @@
 // The step kernel uses explicit non-contracted fp32 intrinsics (__fmul_rn/__fadd_rn) in the
 // reference's operation order so that, given the same denoiser output, it is bit-identical to
 // the PyTorch CPU reference.
+#include <curand_kernel.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -159,6 +161,30 @@ __device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned
   return v[idx & 3];
 }
 
+// ---------------------------------------------------------------------------------------------
+// torch.randn-compatible stream.  ATen's normal_ kernel (aten/src/ATen/native/cuda/DistributionTemplates.h) runs
+// G = 256 * grid threads; thread i initialises Philox4x32-10 with (seed, subsequence i, offset) and its j-th
+// curand_normal4 call fills elements i + G * (4j + {0,1,2,3}).  So element e is component (e / G) & 3 of call
+// (e / G) >> 2 of thread e % G: counter = (offset / 4 + call, thread), Box-Muller exactly as curand_normal4
+// (the toolkit's own device functions are used so the bits match).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float aten_normal(unsigned long long seed, unsigned long long offset, unsigned int threads,
+                                             unsigned long long e) {
+  const unsigned long long thread = e % threads, r = e / threads;
+  const unsigned long long blk = (offset >> 2) + (r >> 2);
+  const uint4 ctr = make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)thread, (uint32_t)(thread >> 32));
+  const uint4 x = curand_Philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const int comp = (int)(r & 3);
+  const float2 n = comp < 2 ? _curand_box_muller(x.x, x.y) : _curand_box_muller(x.z, x.w);
+  return (comp & 1) ? n.y : n.x;
+}
+__global__ void fill_normal_aten_kernel(float* out, size_t numel, unsigned long long seed, unsigned long long offset,
+                                        unsigned int threads) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = aten_normal(seed, offset, threads, i);
+}
+__global__ void set_rng_kernel(RngState* dst, const RngState value) { *dst = value; }
+
 __global__ void fill_normal_ref_kernel(float* out, int B, size_t per_sample, unsigned long long seed,
                                        unsigned long long stream_id, unsigned long long sample_offset) {
   const size_t quads = (per_sample + 3) / 4;
@@ -190,13 +216,25 @@ __global__ void __launch_bounds__(256) diffusion_step_kernel(const StepParams p)
   // ---- noise tile (reference layout [b][c][l], l contiguous) ----
   const bool want_noise = p.sampler != 2;  // the reference draws noise at every step, including t == 0
   if (want_noise) {
-    if (!p.noise_ref && (p.L & 3) == 0) {
+    RngState rng{};
+    if (!p.noise_ref && p.rng) rng = *p.rng;
+    if (!p.noise_ref && rng.mode == 1) {
+      // torch.randn_like stream: draw number (tape_t0 - t) of this loop, element index in the (B, D, 1, L) layout
+      const unsigned long long off = rng.aten_offset + (unsigned long long)(p.tape_t0 - t) * rng.aten_increment;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + i * 8, l = l0 + tx;
+        float nz = 0.f;
+        if (c < p.D && l < p.L) nz = aten_normal(rng.seed, off, rng.aten_threads, ((size_t)b * p.D + c) * p.L + l);
+        s_noise[ty + i * 8][tx] = nz;
+      }
+    } else if (!p.noise_ref && (p.L & 3) == 0) {
       // engine generator: one Philox call yields the 4 consecutive frames of a quad (l0 and L are multiples of 4)
       const int q = ty * 32 + tx;          // 256 quads = 32 features x 8 frame-quads
       const int cl = q >> 3, lq = (q & 7) * 4;
       const int c = c0 + cl, l = l0 + lq;
       float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (c < p.D && l < p.L) philox_normal4(p.seed, (unsigned long long)(t + 1), p.sample_offset + b, ((size_t)c * p.L + l) >> 2, v);
+      if (c < p.D && l < p.L) philox_normal4(rng.seed, (unsigned long long)(t + 1), rng.sample_offset + b, ((size_t)c * p.L + l) >> 2, v);
 #pragma unroll
       for (int j = 0; j < 4; ++j) s_noise[cl][lq + j] = v[j];
     } else {
@@ -207,7 +245,7 @@ __global__ void __launch_bounds__(256) diffusion_step_kernel(const StepParams p)
         if (c < p.D && l < p.L) {
           const size_t e = (size_t)c * p.L + l;
           nz = p.noise_ref ? p.noise_ref[((size_t)(p.tape_t0 - t) * p.B + b) * p.D * p.L + e]
-                           : philox_normal(p.seed, (unsigned long long)(t + 1), p.sample_offset + b, e);
+                           : philox_normal(rng.seed, (unsigned long long)(t + 1), rng.sample_offset + b, e);
         }
         s_noise[ty + i * 8][tx] = nz;
       }
@@ -454,6 +492,16 @@ cudaError_t launch_axpby(const float* x, const float* y, float a, float b, float
   return cudaGetLastError();
 }
 
+cudaError_t launch_set_rng(RngState* dst, const RngState& value, cudaStream_t stream) {
+  set_rng_kernel<<<1, 1, 0, stream>>>(dst, value);
+  return cudaGetLastError();
+}
+cudaError_t launch_fill_normal_aten(float* out, size_t numel, unsigned long long seed, unsigned long long offset,
+                                    unsigned int threads, cudaStream_t stream) {
+  if (threads == 0 || (offset & 3)) return cudaErrorInvalidValue;
+  fill_normal_aten_kernel<<<grid_for(numel, 256), 256, 0, stream>>>(out, numel, seed, offset, threads);
+  return cudaGetLastError();
+}
 cudaError_t launch_fill_normal_ref(float* out, int B, size_t per_sample, unsigned long long seed, unsigned long long stream_id,
                                    unsigned long long sample_offset, cudaStream_t stream) {
   fill_normal_ref_kernel<<<grid_for((size_t)B * per_sample, 256), 256, 0, stream>>>(out, B, per_sample, seed, stream_id,

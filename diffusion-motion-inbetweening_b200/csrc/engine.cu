@@ -73,7 +73,6 @@ struct GraphKey {
   int B, cfg, sampler, impute, stop_at, tape_mode, has_cond;
   float eta;
   const void* tape;
-  unsigned long long seed, sample_offset;
   int t0, uncond, guided;
   bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
 };
@@ -119,6 +118,7 @@ struct cmdi_engine {
   uint8_t* obs_mask = nullptr;
   float *cond_emb = nullptr, *cond_proj = nullptr, *text_scale = nullptr;
   int* step_ctr = nullptr;  // [2]: step index, block-arrival counter
+  RngState* rng = nullptr;  // generator state of the running loop (device-resident: step graphs do not depend on it)
   float *ref_a = nullptr, *ref_b = nullptr;  // reference-layout staging [maxB, D, L]
   uint8_t *ref_mask = nullptr, *ymask = nullptr;
   // reconstruction guidance
@@ -530,6 +530,7 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   A(dev_alloc(e, &e->cond_proj, (size_t)e->maxB * kDModel));
   A(dev_alloc(e, &e->text_scale, e->maxB));
   A(dev_alloc(e, &e->step_ctr, 2));
+  A(dev_alloc(e, &e->rng, 1));
   A(dev_alloc(e, &e->ref_a, (size_t)e->maxB * e->D * e->L));
   A(dev_alloc(e, &e->ref_b, (size_t)e->maxB * e->D * e->L));
   A(dev_alloc(e, &e->ref_mask, (size_t)e->maxB * e->D * e->L));
@@ -825,11 +826,30 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
   // ---- x_T (gaussian_diffusion.py:1245-1248) ----
   const float* xT = (const float*)stage_in(a->x_T, e->ref_a, n * 4, host, s, &rc);
   if (rc) return 1;
+  RngState rng{};
+  rng.seed = a->seed; rng.sample_offset = a->sample_offset; rng.mode = a->rng_mode;
+  rng.aten_offset = a->aten_offset; rng.aten_increment = a->aten_increment; rng.aten_threads = a->aten_threads;
+  if (a->rng_mode == CMDI_RNG_TORCH) {
+    if (a->aten_threads == 0 || a->aten_increment == 0 || (a->aten_increment & 3) || (a->aten_offset & 3)) {
+      set_last_error("rng_mode=CMDI_RNG_TORCH needs aten_threads > 0 and aten_offset / aten_increment multiples of 4");
+      return 1;
+    }
+  } else if (a->rng_mode != CMDI_RNG_ENGINE) {
+    set_last_error("unknown rng_mode %d", a->rng_mode);
+    return 1;
+  }
   if (!xT) {
-    CK(launch_fill_normal_ref(e->ref_a, B, (size_t)e->D * e->L, a->seed, 0ull, a->sample_offset, s));
+    if (a->rng_mode == CMDI_RNG_TORCH) {
+      CK(launch_fill_normal_aten(e->ref_a, n, a->seed, a->aten_offset, a->aten_threads, s));
+      rng.aten_offset += a->aten_increment;  // the per-step draws follow the x_T draw in the stream
+    } else {
+      CK(launch_fill_normal_ref(e->ref_a, B, (size_t)e->D * e->L, a->seed, 0ull, a->sample_offset, s));
+    }
     xT = e->ref_a;
     e->launches += 1;
   }
+  CK(launch_set_rng(e->rng, rng, s));
+  e->launches += 1;
   // ---- init_image / skip_timesteps: img = q_sample(init_image, t0, img) (:1252-1260) ----
   if (!a->resume && (a->init_image || a->skip_timesteps)) {
     const float* init = (const float*)stage_in(a->init_image, e->ref_b, n * 4, host, s, &rc);
@@ -876,7 +896,7 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
     sp.x_t = e->x_state; sp.impute = a->imputate != 0; sp.stop_imputation_at = a->stop_imputation_at;
     sp.x_obs = e->x_obs; sp.obs_mask = e->obs_mask;
     sp.guided = guided; sp.guide_grad = e->guide_grad; sp.guide_coef = e->guide_coef;
-    sp.noise_ref = tape; sp.tape_t0 = t0; sp.seed = a->seed; sp.sample_offset = a->sample_offset;
+    sp.noise_ref = tape; sp.tape_t0 = t0; sp.rng = e->rng;
     sp.x_next = e->x_state; sp.x_next_hi = e->x_state_p.hi; sp.x_next_lo = e->nsplit == 3 ? e->x_state_p.lo : nullptr;
     sp.pred_xstart = e->pred_x0;
     CK(launch_diffusion_step(sp, st));
@@ -888,7 +908,7 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
     memset(&key, 0, sizeof(key));
     key.B = B; key.cfg = a->cfg != 0; key.sampler = a->sampler; key.impute = a->imputate != 0;
     key.stop_at = a->stop_imputation_at; key.tape_mode = tape != nullptr; key.has_cond = has_cond; key.eta = a->eta;
-    key.tape = tape; key.seed = a->seed; key.sample_offset = a->sample_offset; key.t0 = t0; key.uncond = a->uncond != 0;
+    key.tape = tape; key.t0 = t0; key.uncond = a->uncond != 0;
     key.guided = guided;
     auto it = e->graphs.find(key);
     if (it != e->graphs.end()) {

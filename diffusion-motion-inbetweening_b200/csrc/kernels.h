@@ -143,6 +143,14 @@ struct StepTables {            // device pointers, each [T] fp32, indexed by sam
   const float* acp;               // alphas_cumprod
   const float* acp_prev;          // alphas_cumprod_prev
 };
+struct RngState {
+  unsigned long long seed;           // Philox key
+  unsigned long long sample_offset;  // mode 0: global index of local sample 0 (results independent of sharding)
+  unsigned long long aten_offset;    // mode 1: philox offset (in 32-bit outputs, multiple of 4) of the first per-step draw
+  unsigned long long aten_increment; // mode 1: offset consumed by one randn_like of B*D*L elements
+  unsigned int aten_threads;         // mode 1: grid.x * 256 of ATen's distribution kernel for that numel
+  int mode;
+};
 struct StepParams {
   StepTables tab;
   int* step_ptr;            // device: current step t; decremented by the kernel's last block when advance != 0
@@ -168,8 +176,11 @@ struct StepParams {
   const float* noise_ref;      // tape base, reference layout [steps][B, D, 1, L]; slice (tape_t0 - t) is this step's
                                // randn_like draw; null -> in-kernel Philox
   int tape_t0;
-  unsigned long long seed;     // Philox key
-  unsigned long long sample_offset;  // global index of local sample 0 (multi-GPU: results independent of sharding)
+  // generator state, device-resident so a captured step graph does not depend on it (RngState below).
+  // rng_mode 0: engine generator keyed by (seed, t + 1, global sample index, element quad);
+  // rng_mode 1: the stream of torch.randn_like on this device (ATen's Philox offsets / thread mapping), draw
+  //             number (tape_t0 - t) after `aten_offset`
+  const RngState* rng;
   // outputs
   float* x_next;               // [B*L, D_pad]
   __nv_bfloat16* x_next_hi;
@@ -177,6 +188,12 @@ struct StepParams {
   float* pred_xstart;          // [B*L, D_pad] or null
 };
 cudaError_t launch_diffusion_step(const StepParams& p, cudaStream_t stream);
+
+cudaError_t launch_set_rng(RngState* dst, const RngState& value, cudaStream_t stream);
+// out[i] = the i-th element torch.randn(numel, device=cuda) would produce with generator (seed, offset), where
+// `threads` is ATen's launch width for that numel (256 * min(SMs * maxThreadsPerSM / 256, ceil(numel / 256)))
+cudaError_t launch_fill_normal_aten(float* out, size_t numel, unsigned long long seed, unsigned long long offset,
+                                    unsigned int threads, cudaStream_t stream);
 
 // layout converters between the reference layout [B, D, 1, L] and frame-major [B*L, D_pad]
 cudaError_t launch_ref_to_frames(const float* ref, int B, int D, int L, int D_pad, float* out_f32, __nv_bfloat16* out_hi,

@@ -23,6 +23,8 @@ import math
 from dataclasses import dataclass, field
 from typing import List, Optional
 
+import warnings
+
 import numpy as np
 import torch
 
@@ -115,6 +117,11 @@ class GaussianDiffusion:
         self.noise_tape = None         # test aid: (1 + num_steps, B, njoints, 1, nframes) on the device
         self.use_graph = True
         self.sample_offset = 0         # global index of local sample 0 (multi-GPU sharding)
+        # per-step noise: "torch" = the exact stream torch.randn_like would produce on this device from torch's CUDA
+        # generator (a reference GPU run with the same seed draws the same noise; the generator is advanced as the
+        # reference loop would advance it); "engine" = the engine's own counter-based generator keyed by the global
+        # sample index (sharding-independent; used by distributed.sharded_sample)
+        self.rng = "torch"
 
     # ------------------------------------------------------------------------------------------
     def q_sample(self, x_start, t, noise=None):
@@ -214,11 +221,16 @@ class GaussianDiffusion:
             x_T = torch.randn(*shape, device=device)  # the reference's first draw (:1248)
         if tape is not None:
             tape = tape[1:]
-        seed = 0
+        seed, rng_args = 0, {}
         if tape is None:
-            # per-step noise comes from the engine's counter-based generator, keyed by a draw from torch's
-            # global generator so `fixseed` still makes runs reproducible
-            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            n_draws = self.num_timesteps - skip_timesteps  # one randn_like per loop iteration (:696, :1407)
+            rng_args = _torch_stream_args(device, int(np.prod(shape)), n_draws) if self.rng == "torch" else None
+            if rng_args is None:
+                # per-step noise comes from the engine's counter-based generator, keyed by a draw from torch's
+                # global generator so `fixseed` still makes runs reproducible
+                seed, rng_args = int(torch.randint(0, 2 ** 62, (1,)).item()), {}
+            else:
+                seed = rng_args.pop("seed")
         if skip_timesteps and init_image is None:
             init_image = torch.zeros_like(x_T)
         if init_image is not None:
@@ -226,7 +238,7 @@ class GaussianDiffusion:
         common = dict(batch=B, sampler=sampler, eta=eta, cond_emb=cond_emb, uncond=uncond, cfg=is_cfg, text_scale=text_scale,
                       y_mask=y_mask, imputate=imputate, stop_imputation_at=stop_at, inpainted_motion=obs,
                       inpainting_mask=mask, seed=seed, sample_offset=self.sample_offset, use_graph=self.use_graph,
-                      recon_guidance=recon, stop_recguidance_at=stop_rg, recon_coef=coef)
+                      recon_guidance=recon, stop_recguidance_at=stop_rg, recon_coef=coef, **rng_args)
         if not progressive:
             res = eng.sample(skip_timesteps=skip_timesteps, init_image=init_image, x_T=x_T,
                              noise_tape=None if tape is None else tape, want_pred_xstart=False, dump_steps=dump_steps, **common)
@@ -237,7 +249,11 @@ class GaussianDiffusion:
         """Generator form: one native call per step (slower than the fused loop; kept for API parity)."""
         n = self.num_timesteps - skip_timesteps
         state = x_T
+        common = dict(common)
+        off0, inc = common.pop("aten_offset", 0), common.get("aten_increment", 0)
         for k in range(n):
+            if common.get("rng_mode", capi.RNG_ENGINE) == capi.RNG_TORCH:
+                common["aten_offset"] = off0 + k * inc  # each one-step call starts at its own draw of the stream
             res = eng.sample(skip_timesteps=skip_timesteps + k, num_steps=1, resume=(k > 0), init_image=init_image if k == 0 else None,
                              x_T=state, noise_tape=None if tape is None else tape[k:], want_pred_xstart=True, **common)
             state = res["sample"]
@@ -361,6 +377,54 @@ def from_reference_diffusion(ref_diffusion) -> SpacedDiffusion:
     for hook in ("data_transform_fn", "data_inv_transform_fn", "data_get_mean_fn", "log_trajectory_fn"):
         setattr(d, hook, getattr(ref_diffusion, hook, None))
     return d
+
+
+_warned_policy = False
+_policy_ok = {}
+
+
+def aten_launch_policy(numel: int, device) -> tuple:
+    """(threads, philox offset increment) of ATen's CUDA `normal_` kernel for `numel` elements on `device`
+    (aten/src/ATen/native/cuda/DistributionTemplates.h: calc_execution_policy, block 256, unroll 4)."""
+    prop = torch.cuda.get_device_properties(device)
+    blocks = min(prop.multi_processor_count * (prop.max_threads_per_multi_processor // 256), (numel + 255) // 256)
+    threads = 256 * blocks
+    return threads, ((numel - 1) // (threads * 4) + 1) * 4
+
+
+def _cuda_rng_state(device) -> tuple:
+    st = torch.cuda.get_rng_state(device)
+    if st.numel() != 16:
+        raise NotImplementedError("unexpected CUDA generator state layout")
+    raw = bytes(st.tolist())
+    return int.from_bytes(raw[:8], "little"), int.from_bytes(raw[8:], "little")
+
+
+def _torch_stream_args(device, numel: int, n_draws: int):
+    """Engine arguments that continue torch's CUDA generator stream for `n_draws` randn_like draws of `numel`
+    elements, and advance torch's generator past them.  None (with one warning) if this torch build's launch policy
+    is not the one `aten_launch_policy` models -- verified by drawing one element block and watching the offset."""
+    global _warned_policy
+    key = (str(device), numel)
+    try:
+        threads, inc = aten_launch_policy(numel, device)
+        seed, off = _cuda_rng_state(device)
+        if key not in _policy_ok:
+            probe = torch.cuda.get_rng_state(device)
+            torch.empty(numel, device=device).normal_()
+            _policy_ok[key] = _cuda_rng_state(device) == (seed, off + inc)
+            torch.cuda.set_rng_state(probe, device)
+        ok = _policy_ok[key]
+    except Exception:  # noqa: BLE001  (state layout / property names differ in this torch build)
+        ok = False
+    if not ok or off % 4:
+        if not _warned_policy:
+            warnings.warn("torch-compatible noise stream unavailable for this torch build; using the engine generator")
+            _warned_policy = True
+        return None
+    new_state = torch.tensor(list(seed.to_bytes(8, "little") + (off + n_draws * inc).to_bytes(8, "little")), dtype=torch.uint8)
+    torch.cuda.set_rng_state(new_state, device)
+    return dict(seed=seed, rng_mode=capi.RNG_TORCH, aten_offset=off, aten_increment=inc, aten_threads=threads)
 
 
 def _extract_into_tensor(arr, timesteps, broadcast_shape):

@@ -46,7 +46,9 @@ def sharded_sample(diffusion, model, shape, model_kwargs: Optional[dict] = None,
     local_noise = None if noise is None else noise[lo:hi]
     prev_offset = getattr(diffusion, "sample_offset", 0)
     prev_tape = getattr(diffusion, "noise_tape", None)
+    prev_rng = getattr(diffusion, "rng", "engine")
     diffusion.sample_offset = lo
+    diffusion.rng = "engine"  # keyed by global sample index: the result does not depend on the number of ranks
     if prev_tape is not None:
         diffusion.noise_tape = prev_tape[:, lo:hi].contiguous()
     try:
@@ -54,6 +56,7 @@ def sharded_sample(diffusion, model, shape, model_kwargs: Optional[dict] = None,
                                            **kwargs)
     finally:
         diffusion.sample_offset = prev_offset
+        diffusion.rng = prev_rng
         diffusion.noise_tape = prev_tape
     if world == 1 or not gather:
         return local

@@ -107,6 +107,7 @@ class Engine:
                num_steps: int = 0, resume: bool = False, uncond: bool = False,
                init_image: Optional[torch.Tensor] = None, x_T: Optional[torch.Tensor] = None,
                noise_tape: Optional[torch.Tensor] = None, seed: int = 0, sample_offset: int = 0,
+               rng_mode: int = capi.RNG_ENGINE, aten_offset: int = 0, aten_increment: int = 0, aten_threads: int = 0,
                cond_emb: Optional[torch.Tensor] = None, cfg: bool = False, text_scale: Optional[torch.Tensor] = None,
                y_mask: Optional[torch.Tensor] = None, imputate: bool = False, stop_imputation_at: int = 0,
                inpainted_motion: Optional[torch.Tensor] = None, inpainting_mask: Optional[torch.Tensor] = None,
@@ -158,7 +159,8 @@ class Engine:
                 raise ValueError(f"recon_coef must have one entry per sampler step ({self.num_timesteps})")
             coef_arr = coef.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
         a = capi.SampleArgs(batch, sampler, float(eta), int(skip_timesteps), int(num_steps), int(resume), _ptr(init_image), _ptr(x_T), _ptr(noise_tape),
-                            int(seed) & (2 ** 64 - 1), int(sample_offset), _ptr(cond_emb), int(uncond), int(cfg), _ptr(text_scale),
+                            int(seed) & (2 ** 64 - 1), int(sample_offset), int(rng_mode), int(aten_offset), int(aten_increment),
+                            int(aten_threads), _ptr(cond_emb), int(uncond), int(cfg), _ptr(text_scale),
                             _ptr(y_mask), int(imputate), int(stop_imputation_at), _ptr(inpainted_motion),
                             _ptr(inpainting_mask), int(recon_guidance), int(stop_recguidance_at), coef_arr, _ptr(pred), _ptr(dump),
                             dump_arr, n_dump, int(host_buffers),

@@ -49,6 +49,7 @@ enum {
 };
 
 enum { CMDI_SAMPLER_DDPM = 0, CMDI_SAMPLER_DDIM = 1 };
+enum { CMDI_RNG_ENGINE = 0, CMDI_RNG_TORCH = 1 };
 
 typedef struct {
   int32_t njoints;     /* 263 (input_feats = njoints * nfeats, nfeats == 1)                      mdm.py:64 */
@@ -97,6 +98,12 @@ typedef struct {
                                    (k = 0 is the first, i.e. largest-t, step), or NULL */
   uint64_t seed;                /* used when x_T / noise_tape are NULL */
   uint64_t sample_offset;       /* global index of local sample 0: results are independent of how a batch is sharded */
+  int32_t rng_mode;             /* CMDI_RNG_ENGINE (seed / sample_offset above) or CMDI_RNG_TORCH: reproduce the stream of
+                                   torch.randn / randn_like on this device (gaussian_diffusion.py:696, :1248, :1407) from
+                                   generator state (seed, aten_offset): x_T first when x_T is NULL, then one draw per step */
+  uint64_t aten_offset;         /* philox offset of torch's CUDA generator at loop entry (multiple of 4) */
+  uint64_t aten_increment;      /* offset one randn of B*263*196 elements consumes (ATen: calls per thread x 4) */
+  uint32_t aten_threads;        /* 256 x grid of ATen's distribution kernel for that numel on this device */
   /* conditioning */
   const float* cond_emb;        /* (B, 512) or NULL */
   int32_t uncond;               /* y['uncond'] on a plain (non-CFG) model: zero the text embedding (mdm.py:188-191) */
@@ -159,6 +166,11 @@ CMDI_API int cmdi_profile_pass(cmdi_engine* e, int batch, int cfg, int repeats, 
 /* the engine's counter-based N(0,1) generator: out[b, i] depends only on (seed, stream_id, sample_offset + b, i) */
 CMDI_API int cmdi_test_normal(float* out, int B, long long per_sample, unsigned long long seed, unsigned long long stream_id,
                      unsigned long long sample_offset, void* stream);
+
+/* out[i] = element i of torch.randn(numel, device=this GPU) under generator state (seed, offset); `threads` as
+ * cmdi_sample_args.aten_threads */
+CMDI_API int cmdi_test_normal_aten(float* out, long long numel, unsigned long long seed, unsigned long long offset,
+                          unsigned int threads, void* stream);
 
 #ifdef __cplusplus
 }

@@ -185,6 +185,25 @@ def test_counter_based_normal_generator():
     assert torch.isfinite(a).all() and a.abs().max() < 7
 
 
+@pytest.mark.parametrize("numel", [1000, 4 * 263 * 196, 64 * 263 * 196, 5_000_003])
+def test_torch_compatible_normal_stream_is_bit_exact(numel):
+    """CMDI_RNG_TORCH: the engine regenerates torch.randn's CUDA stream from (seed, philox offset) -- the noise a
+    reference GPU run draws at gaussian_diffusion.py:696 / :1248 / :1407."""
+    from condmdi_b200.diffusion import _cuda_rng_state, aten_launch_policy
+    dev = torch.device("cuda:0")
+    torch.manual_seed(20240917)
+    torch.randn(12345, device=dev)  # move the generator off offset 0
+    threads, inc = aten_launch_policy(numel, dev)
+    for _ in range(2):              # two consecutive draws: the offset bookkeeping matters for the second
+        seed, off = _cuda_rng_state(dev)
+        ref = torch.randn(numel, device=dev)
+        assert _cuda_rng_state(dev) == (seed, off + inc)
+        out = torch.empty(numel, device=dev)
+        C.capi.check(_lib().cmdi_test_normal_aten(_p(out), numel, seed, off, threads, None))
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref), f"max |d| = {(out - ref).abs().max().item()}"
+
+
 # ---------------------------------------------------------------------------------------------------
 # the diffusion-step kernel against the oracle's formulas evaluated by torch on the CPU
 # ---------------------------------------------------------------------------------------------------

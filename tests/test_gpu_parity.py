@@ -236,6 +236,40 @@ def test_torch_seed_reproducibility_through_public_api(plain):
     assert torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("sampler", ["p_sample_loop", "ddim_sample_loop"])
+def test_torch_stream_mode_draws_what_the_reference_loop_would(plain, sampler):
+    """rng='torch' (the default): after torch.manual_seed(s) the loop consumes exactly the noise the reference's loop
+    would draw on this GPU -- randn(*shape) then one randn_like per step (gaussian_diffusion.py:1248, :696, :1407) --
+    and leaves torch's generator where the reference would leave it."""
+    from condmdi_b200.diffusion import _cuda_rng_state
+    m, _ = plain
+    shape, skip = (B, D, 1, L), 44
+    diff = C.create_gaussian_diffusion(timestep_respacing="ddim50")
+    assert diff.rng == "torch"
+    n_steps = diff.num_timesteps - skip
+    torch.manual_seed(31)
+    tape = torch.stack([torch.randn(*shape, device=DEV)] + [torch.randn(*shape, device=DEV) for _ in range(n_steps)])
+    state_after = _cuda_rng_state(torch.device(DEV))
+    diff.noise_tape = tape
+    want = getattr(diff, sampler)(m, shape, model_kwargs={"y": {}}, skip_timesteps=skip)
+    diff.noise_tape = None
+    torch.manual_seed(31)
+    got = getattr(diff, sampler)(m, shape, model_kwargs={"y": {}}, skip_timesteps=skip)
+    assert torch.equal(got, want)
+    assert _cuda_rng_state(torch.device(DEV)) == state_after
+    # the generator form consumes the same stream one step at a time
+    torch.manual_seed(31)
+    last = None
+    for last in getattr(diff, sampler + "_progressive")(m, shape, model_kwargs={"y": {}}, skip_timesteps=skip):
+        pass
+    assert torch.equal(last["sample"], want)
+    # and the engine generator is still selectable
+    diff.rng = "engine"
+    torch.manual_seed(31)
+    other = getattr(diff, sampler)(m, shape, model_kwargs={"y": {}}, skip_timesteps=skip)
+    assert torch.isfinite(other).all() and not torch.equal(other, want)
+
+
 # ------------------------------------------------------------------------------------------------
 # full benchmark size: properties that need no CPU-sized reference
 # ------------------------------------------------------------------------------------------------
