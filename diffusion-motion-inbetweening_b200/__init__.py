@@ -13,3 +13,4 @@ from .adapter import accelerate, install  # noqa: F401
 from .distributed import sharded_sample  # noqa: F401
 
 __version__ = "0.1.0"
+from .motion_process import recover_from_ric, sample_to_joints  # noqa: F401

@@ -21,7 +21,7 @@ EXPORTS = [
     "cmdi_engine_create", "cmdi_engine_destroy", "cmdi_load_weights", "cmdi_set_schedule", "cmdi_model_forward",
     "cmdi_sample", "cmdi_launch_count", "cmdi_last_error", "cmdi_version", "cmdi_test_linear", "cmdi_test_attention",
     "cmdi_test_layernorm", "cmdi_test_step", "cmdi_test_normal", "cmdi_profile_pass", "cmdi_test_linear_ln", "cmdi_test_layernorm_bwd", "cmdi_test_attention_bwd",
-    "cmdi_test_normal_aten",
+    "cmdi_test_normal_aten", "cmdi_recover_from_ric",
 ]
 
 
@@ -91,6 +91,9 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
                                    c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.cmdi_test_normal.argtypes = [c_void_p, c_int, ctypes.c_longlong, c_uint64, c_uint64, c_uint64, c_void_p]
     lib.cmdi_test_normal_aten.argtypes = [c_void_p, ctypes.c_longlong, c_uint64, c_uint64, ctypes.c_uint32, c_void_p]
+    ll = ctypes.c_longlong
+    lib.cmdi_recover_from_ric.argtypes = [c_void_p, ll, ll, ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                          ll, ll, ll, ll, c_void_p]
     lib.cmdi_profile_pass.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_float), c_int, POINTER(c_int), c_void_p]
     lib.cmdi_test_linear_ln.argtypes = [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p]
     lib.cmdi_test_layernorm_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]

@@ -437,6 +437,108 @@ __global__ void split_planes_kernel(const float* __restrict__ in, int rows, int 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// HumanML3D vector -> joint positions (data_loaders/humanml/scripts/motion_process.py:402-441 recover_root_rot_pos,
+// :474-489 recover_from_ric), optionally fused with the dataset de-normalisation x * std + mean
+// (data_loaders/humanml/data/dataset.py:378-382) and the layout permutes sample/synthesize.py:153-157 does on the
+// CPU.  One block per sequence; the two prefix sums over frames run sequentially on one thread, in the order
+// torch.cumsum uses on the CPU, everything else is per (frame, joint).
+// ---------------------------------------------------------------------------------------------
+struct RicParams {
+  const float* data;
+  long long sb, sf, sc;      // input strides (elements): sequence, frame, feature
+  const float* mean;         // [nfeats] or null
+  const float* stdv;
+  int B, L, joints, abs_3d;
+  float* out;
+  long long ob, of, oj, oc;  // output strides: sequence, frame, joint, coordinate
+};
+__global__ void __launch_bounds__(256) recover_from_ric_kernel(const RicParams p) {
+  extern __shared__ float ric_smem[];
+  float* ang = ric_smem;            // root heading per frame
+  float* px = ang + p.L;            // root x, y, z per frame
+  float* py = px + p.L;
+  float* pz = py + p.L;
+  float* vx = pz + p.L;             // (abs_3d == 0) de-normalised planar velocity
+  float* vz = vx + p.L;
+  const float* d = p.data + (long long)blockIdx.x * p.sb;
+  auto feat = [&](int f, int c) -> float {
+    const float v = d[f * p.sf + c * p.sc];
+    return p.mean ? __fadd_rn(__fmul_rn(v, p.stdv[c]), p.mean[c]) : v;
+  };
+  for (int f = threadIdx.x; f < p.L; f += blockDim.x) {
+    ang[f] = feat(f, 0);
+    vx[f] = feat(f, 1);
+    vz[f] = feat(f, 2);
+    py[f] = feat(f, 3);
+  }
+  __syncthreads();
+  if (!p.abs_3d) {
+    if (threadIdx.x == 0) {  // r_rot_ang = cumsum([0, w_0, ..., w_{L-2}])
+      float acc = 0.f, prev = ang[0];
+      ang[0] = 0.f;
+      for (int f = 1; f < p.L; ++f) {
+        acc = __fadd_rn(acc, prev);
+        prev = ang[f];
+        ang[f] = acc;
+      }
+    }
+    __syncthreads();
+    // r_pos[f] = qrot(qinv(q_f), (vx[f-1], 0, vz[f-1])), q_f = (cos a, 0, sin a, 0); r_pos[0] = 0
+    for (int f = threadIdx.x; f < p.L; f += blockDim.x) {
+      float rx = 0.f, rz = 0.f;
+      if (f > 0) {
+        const float c = cosf(ang[f]), qy = -sinf(ang[f]);
+        const float x = vx[f - 1], z = vz[f - 1];
+        const float uv0 = __fmul_rn(qy, z), uv2 = -__fmul_rn(qy, x);
+        const float uuv0 = __fmul_rn(qy, uv2), uuv2 = -__fmul_rn(qy, uv0);
+        rx = __fadd_rn(x, __fmul_rn(2.f, __fadd_rn(__fmul_rn(c, uv0), uuv0)));
+        rz = __fadd_rn(z, __fmul_rn(2.f, __fadd_rn(__fmul_rn(c, uv2), uuv2)));
+      }
+      px[f] = rx;
+      pz[f] = rz;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {  // cumsum over frames, x on thread 0 and z on thread 1
+      float* a = threadIdx.x == 0 ? px : pz;
+      float acc = a[0];
+      for (int f = 1; f < p.L; ++f) {
+        acc = __fadd_rn(acc, a[f]);
+        a[f] = acc;
+      }
+    }
+    __syncthreads();
+  } else {
+    for (int f = threadIdx.x; f < p.L; f += blockDim.x) {
+      px[f] = vx[f];
+      pz[f] = vz[f];
+    }
+    __syncthreads();
+  }
+  float* o = p.out + (long long)blockIdx.x * p.ob;
+  const int per_frame = p.joints;  // joint 0 = root, joints 1.. = rotation-invariant coordinates 4 + 3(j-1)
+  for (int i = threadIdx.x; i < p.L * per_frame; i += blockDim.x) {
+    const int f = i / per_frame, j = i - f * per_frame;
+    float x, y, z;
+    if (j == 0) {
+      x = px[f]; y = py[f]; z = pz[f];
+    } else {
+      const float c = cosf(ang[f]), qy = -sinf(ang[f]);
+      const float lx = feat(f, 4 + 3 * (j - 1)), ly = feat(f, 5 + 3 * (j - 1)), lz = feat(f, 6 + 3 * (j - 1));
+      const float uv0 = __fmul_rn(qy, lz), uv2 = -__fmul_rn(qy, lx);
+      const float uuv0 = __fmul_rn(qy, uv2), uuv2 = -__fmul_rn(qy, uv0);
+      x = __fadd_rn(__fadd_rn(lx, __fmul_rn(2.f, __fadd_rn(__fmul_rn(c, uv0), uuv0))), px[f]);
+      y = ly;
+      z = __fadd_rn(__fadd_rn(lz, __fmul_rn(2.f, __fadd_rn(__fmul_rn(c, uv2), uuv2))), pz[f]);
+    }
+    float* dst = o + f * p.of + j * p.oj;
+    dst[0] = x;
+    dst[p.oc] = y;
+    dst[2 * p.oc] = z;
+  }
+}
+
 inline int grid_for(size_t n, int block) {
   size_t g = (n + block - 1) / block;
   if (g > 148 * 16) g = 148 * 16;
@@ -506,6 +608,17 @@ cudaError_t launch_fill_normal_ref(float* out, int B, size_t per_sample, unsigne
                                    unsigned long long sample_offset, cudaStream_t stream) {
   fill_normal_ref_kernel<<<grid_for((size_t)B * per_sample, 256), 256, 0, stream>>>(out, B, per_sample, seed, stream_id,
                                                                                   sample_offset);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_recover_from_ric(const float* data, long long sb, long long sf, long long sc, const float* mean,
+                                    const float* stdv, int B, int L, int joints, int abs_3d, float* out, long long ob,
+                                    long long of, long long oj, long long oc, cudaStream_t stream) {
+  RicParams p{data, sb, sf, sc, mean, stdv, B, L, joints, abs_3d, out, ob, of, oj, oc};
+  const size_t smem = (size_t)6 * L * sizeof(float);
+  if (B <= 0) return cudaSuccess;
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  recover_from_ric_kernel<<<B, 256, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -1015,6 +1015,22 @@ extern "C" int cmdi_test_step(cmdi_engine* e, int sampler, float eta, int t, int
   return 0;
 }
 
+extern "C" int cmdi_recover_from_ric(const float* data, long long stride_seq, long long stride_frame, long long stride_feat,
+                                     const float* mean, const float* std, int num_seqs, int nframes, int nfeats,
+                                     int joints_num, int abs_3d, float* out, long long ostride_seq, long long ostride_frame,
+                                     long long ostride_joint, long long ostride_coord, void* stream_) {
+  if (!data || !out || num_seqs < 0 || nframes < 1 || nframes > 2048 || joints_num < 2 || nfeats < 4 + 3 * (joints_num - 1) ||
+      ((mean == nullptr) != (std == nullptr))) {
+    set_last_error("cmdi_recover_from_ric: bad arguments (need 1 <= nframes <= 2048, nfeats >= 4 + 3*(joints_num-1), "
+                   "mean and std both set or both NULL)");
+    return 1;
+  }
+  CK(launch_recover_from_ric(data, stride_seq, stride_frame, stride_feat, mean, std, num_seqs, nframes, joints_num, abs_3d != 0,
+                             out, ostride_seq, ostride_frame, ostride_joint, ostride_coord,
+                             reinterpret_cast<cudaStream_t>(stream_)));
+  return 0;
+}
+
 // Per-kernel device times of one denoiser pass (plain launches with CUDA events between them, on the caller's
 // stream; each launch is issued `repeats` times back to back and the mean is reported, which hides the host's
 // launch latency behind queued work): ms[i] is the i-th launch of the pass in order

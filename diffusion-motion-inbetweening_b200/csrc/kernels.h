@@ -189,6 +189,10 @@ struct StepParams {
 };
 cudaError_t launch_diffusion_step(const StepParams& p, cudaStream_t stream);
 
+// HumanML3D vectors -> joint positions (recover_from_ric), strides in elements; mean/stdv null = already de-normalised
+cudaError_t launch_recover_from_ric(const float* data, long long sb, long long sf, long long sc, const float* mean,
+                                    const float* stdv, int B, int L, int joints, int abs_3d, float* out, long long ob,
+                                    long long of, long long oj, long long oc, cudaStream_t stream);
 cudaError_t launch_set_rng(RngState* dst, const RngState& value, cudaStream_t stream);
 // out[i] = the i-th element torch.randn(numel, device=cuda) would produce with generator (seed, offset), where
 // `threads` is ATen's launch width for that numel (256 * min(SMs * maxThreadsPerSM / 256, ceil(numel / 256)))

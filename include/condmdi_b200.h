@@ -167,6 +167,20 @@ CMDI_API int cmdi_profile_pass(cmdi_engine* e, int batch, int cfg, int repeats, 
 CMDI_API int cmdi_test_normal(float* out, int B, long long per_sample, unsigned long long seed, unsigned long long stream_id,
                      unsigned long long sample_offset, void* stream);
 
+/* HumanML3D feature vectors -> joint positions: recover_root_rot_pos + recover_from_ric
+ * (data_loaders/humanml/scripts/motion_process.py:402-441, :474-489), optionally fused with the de-normalisation
+ * data * std + mean (data_loaders/humanml/data/dataset.py:378-382) and the permutes around them
+ * (sample/synthesize.py:153-157).  Device pointers; strides in elements.
+ *   data : element (sequence b, frame f, feature c) at data[b*stride_seq + f*stride_frame + c*stride_feat]
+ *          -- (B,263,1,196) sampler output: strides (263*196, 1, 196); (B,1,196,263) reference input: (196*263, 263, 1)
+ *   mean, std : [nfeats] or both NULL (data already de-normalised)
+ *   out  : joints_num x 3 positions per frame, element (b, f, joint j, coordinate k) at
+ *          out[b*ostride_seq + f*ostride_frame + j*ostride_joint + k*ostride_coord]
+ *   joints_num : 22 (HumanML3D, 263 features) or 21 (KIT, 251); nfeats >= 4 + 3*(joints_num-1); nframes <= 2048 */
+CMDI_API int cmdi_recover_from_ric(const float* data, long long stride_seq, long long stride_frame, long long stride_feat,
+                          const float* mean, const float* std, int num_seqs, int nframes, int nfeats, int joints_num,
+                          int abs_3d, float* out, long long ostride_seq, long long ostride_frame, long long ostride_joint,
+                          long long ostride_coord, void* stream);
 /* out[i] = element i of torch.randn(numel, device=this GPU) under generator state (seed, offset); `threads` as
  * cmdi_sample_args.aten_threads */
 CMDI_API int cmdi_test_normal_aten(float* out, long long numel, unsigned long long seed, unsigned long long offset,

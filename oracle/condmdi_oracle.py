@@ -475,3 +475,55 @@ def golden_inputs(B: int = 2, D: int = 263, L: int = 196) -> Dict[str, torch.Ten
     y_mask = (torch.arange(L)[None, :] < lengths[:, None]).view(B, 1, 1, L)
     kf_mask = get_keyframes_mask(x_obs, lengths, "benchmark_sparse", trans_length=5)
     return dict(x=x, cond=cond, x_obs=x_obs, tape=tape, text_scale=scale, lengths=lengths, y_mask=y_mask, kf_mask=kf_mask)
+
+
+# ---------------------------------------------------------------------------------------------------
+# post-processing: HumanML3D vectors -> joint positions
+# (data_loaders/humanml/scripts/motion_process.py:402-441 recover_root_rot_pos, :474-489 recover_from_ric,
+#  data_loaders/humanml/common/quaternion.py:16-20 qinv, :54-73 qrot; caller sample/synthesize.py:153-157)
+# ---------------------------------------------------------------------------------------------------
+def _rotate_about_y(cos_a: torch.Tensor, sin_a: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """qrot(qinv(q), v) for q = (cos a, 0, sin a, 0), written out in qrot's operation order
+    (v + 2 * (w * cross(u, v) + cross(u, cross(u, v))) with u = (0, -sin a, 0))."""
+    uy = -sin_a
+    x, y, z = v.unbind(-1)
+    uv_x, uv_z = uy * z, -(uy * x)
+    uuv_x, uuv_z = uy * uv_z, -(uy * uv_x)
+    return torch.stack((x + 2 * (cos_a * uv_x + uuv_x), y, z + 2 * (cos_a * uv_z + uuv_z)), -1)
+
+
+def recover_from_ric(data: torch.Tensor, joints_num: int, abs_3d: bool = False) -> torch.Tensor:
+    """data (..., frames, feats) de-normalised -> (..., frames, joints_num, 3)."""
+    data = data.float()
+    if abs_3d:
+        ang = data[..., 0]
+    else:
+        ang = torch.zeros_like(data[..., 0])
+        ang[..., 1:] = data[..., :-1, 0]
+        ang = torch.cumsum(ang, dim=-1)                    # :413-414
+    cos_a, sin_a = torch.cos(ang), torch.sin(ang)
+    root = torch.zeros(data.shape[:-1] + (3,))
+    if abs_3d:
+        root[..., 0], root[..., 2] = data[..., 1], data[..., 2]      # :425
+    else:
+        root[..., 1:, 0], root[..., 1:, 2] = data[..., :-1, 1], data[..., :-1, 2]   # :433
+        root = torch.cumsum(_rotate_about_y(cos_a, sin_a, root), dim=-2)             # :434-435
+    root[..., 1] = data[..., 3]                              # :437
+    local = data[..., 4:(joints_num - 1) * 3 + 4].reshape(data.shape[:-1] + (joints_num - 1, 3))
+    pos = _rotate_about_y(cos_a[..., None], sin_a[..., None], local)                # :480
+    pos = torch.stack((pos[..., 0] + root[..., None, 0], pos[..., 1], pos[..., 2] + root[..., None, 2]), -1)  # :483-484
+    return torch.cat((root[..., None, :], pos), dim=-2)     # :487
+
+
+def sample_to_joints(sample: torch.Tensor, mean, std, joints_num: int = 22, abs_3d: bool = False) -> torch.Tensor:
+    """sample/synthesize.py:153-157: (B, feats, 1, frames) normalised -> (B, joints_num, 3, frames)."""
+    x = sample.float().permute(0, 2, 3, 1) * torch.as_tensor(std).float() + torch.as_tensor(mean).float()
+    pos = recover_from_ric(x, joints_num, abs_3d)           # (B, 1, frames, J, 3)
+    return pos.reshape(-1, *pos.shape[2:]).permute(0, 2, 3, 1)
+
+
+def postprocess_inputs(B: int = 3, D: int = 263, L: int = 196) -> Dict[str, torch.Tensor]:
+    """Seeded sampler-output-like tensors for the post-processing fixtures (tests/golden/postprocess.npz holds the
+    dataset statistics used and the REFERENCE's outputs)."""
+    g = torch.Generator().manual_seed(4321)
+    return dict(sample=torch.randn(B, D, 1, L, generator=g), ragged=torch.randn(2, 1, 57, D, generator=g))

@@ -191,6 +191,31 @@ def golden_model_and_sampler():
     np.savez_compressed(os.path.join(GOLDEN, "sampler.npz"), **out)
 
 
+def golden_postprocess():
+    """recover_from_ric + inv_transform as sample/synthesize.py:153-157 chains them (CPU reference)."""
+    print("post-processing (recover_from_ric)")
+    RH.import_reference()
+    from data_loaders.humanml.scripts.motion_process import recover_from_ric as ref_ric  # noqa: E402
+    inp = O.postprocess_inputs()
+    out = {}
+    for tag, mean_f, std_f, abs_3d in (("rel", "t2m_mean.npy", "t2m_std.npy", False),
+                                       ("abs", "HumanML3D_abs/Mean_abs_3d.npy", "HumanML3D_abs/Std_abs_3d.npy", True)):
+        mean = np.load(os.path.join(RH.REFERENCE_ROOT, "dataset", mean_f))
+        std = np.load(os.path.join(RH.REFERENCE_ROOT, "dataset", std_f))
+        sample = inp["sample"].clone()
+        x = sample.cpu().permute(0, 2, 3, 1)
+        x = (x * std + mean).float()                        # t2m_dataset.inv_transform (dataset.py:378-382)
+        ref = ref_ric(x, 22, abs_3d=abs_3d)
+        ref = ref.view(-1, *ref.shape[2:]).permute(0, 2, 3, 1)
+        close(ref, O.sample_to_joints(inp["sample"], mean, std, 22, abs_3d), 2e-4, f"sample_to_joints[{tag}]")
+        out[f"{tag}.mean"], out[f"{tag}.std"] = mean.astype(np.float32), std.astype(np.float32)
+        out[f"{tag}.joints"] = ref.numpy()
+        rag = ref_ric(inp["ragged"].clone(), 22, abs_3d=abs_3d)
+        close(rag, O.recover_from_ric(inp["ragged"], 22, abs_3d), 1e-4, f"recover_from_ric[{tag}] 57 frames")
+        out[f"{tag}.ragged"] = rag.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "postprocess.npz"), **out)
+
+
 def main():
     if not RH.available():
         raise SystemExit("the reference tree is required to (re)generate golden vectors")
@@ -199,6 +224,7 @@ def main():
     golden_schedules()
     golden_masks()
     golden_model_and_sampler()
+    golden_postprocess()
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)) // 1024, "KiB")
 

@@ -112,3 +112,17 @@ def test_ddim50_full_loop_matches_reference(samp):
     tape50 = gi["tape"][torch.arange(51) % 8]
     out = O.sample_loop(sd, O.make_tables("ddim50"), (B, D, 1, L), O.Conditioning(), tape50, "ddim")
     assert torch.allclose(out, torch.tensor(samp["ddim50.sample"]), rtol=1e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("tag,abs_3d", [("rel", False), ("abs", True)])
+def test_recover_from_ric_matches_reference(golden_dir, tag, abs_3d):
+    """Post-processing row: the restatement of recover_from_ric / inv_transform against the
+    reference's own output (sample/synthesize.py:153-157 chain)."""
+    g = np.load(os.path.join(golden_dir, "postprocess.npz"))
+    inp = O.postprocess_inputs()
+    got = O.sample_to_joints(inp["sample"], g[f"{tag}.mean"], g[f"{tag}.std"], 22, abs_3d)
+    assert got.shape == (3, 22, 3, 196)
+    assert torch.allclose(got, torch.from_numpy(g[f"{tag}.joints"]), rtol=1e-5, atol=2e-5)
+    rag = O.recover_from_ric(inp["ragged"], 22, abs_3d)
+    assert rag.shape == (2, 1, 57, 22, 3)
+    assert torch.allclose(rag, torch.from_numpy(g[f"{tag}.ragged"]), rtol=1e-6, atol=1e-6)
