@@ -164,6 +164,7 @@ extern "C" int cmdi_test_attention(const float* qkv, float* O, int num_seqs, int
   const int nctas = ((S + 127) / 128) * H * num_seqs;
   if (getenv("CMDI_TEST_DBG")) {
     CK(adbg.alloc((size_t)nctas * 16 * 8));
+    CK(cudaMemset(adbg.p, 0, (size_t)nctas * 16 * 8));
     p.dbg_cycles = adbg.as<long long>();
     CK(launch_attention(mq_hi, mq_lo, mkv_hi, mkv_lo, mo_hi, mo_lo, p, stream));
   }
@@ -171,6 +172,22 @@ extern "C" int cmdi_test_attention(const float* qkv, float* O, int num_seqs, int
   if (p.dbg_cycles) {
     std::vector<long long> h((size_t)nctas * 16);
     CK(cudaStreamSynchronize(stream));
+    CK(cudaMemcpy(h.data(), adbg.p, h.size() * 8, cudaMemcpyDeviceToHost));
+    double a[16] = {0};
+    if (g_attn_persistent) {
+      // persistent kernel: per-CTA sums over its items; slot 7 = item count
+      double items = 0;
+      for (int c = 0; c < nctas; ++c) items += (double)h[(size_t)c * 16 + 7];
+      for (int c = 0; c < nctas; ++c) for (int k = 0; k < 12; ++k) a[k] += (double)h[(size_t)c * 16 + k] / items;
+      printf("attn2 dbg cycles (mean per item): MMA thread wait_q=%.0f wait_k=%.0f S-issue=%.0f wait_P=%.0f wait_Vhi=%.0f PV-issue=%.0f wait_Vlo=%.0f | "
+             "softmax warp: wait_S=%.0f softmax=%.0f wait_O=%.0f epilogue=%.0f (items %.0f)\n",
+             a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[8], a[9], a[10], a[11], items);
+      fflush(stdout);
+      p.dbg_cycles = nullptr;
+    }
+  }
+  if (p.dbg_cycles) {
+    std::vector<long long> h((size_t)nctas * 16);
     CK(cudaMemcpy(h.data(), adbg.p, h.size() * 8, cudaMemcpyDeviceToHost));
     double a[16] = {0};
     for (int c = 0; c < nctas; ++c) for (int k = 0; k < 12; ++k) a[k] += (double)h[(size_t)c * 16 + k] / nctas;

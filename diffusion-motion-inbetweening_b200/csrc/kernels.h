@@ -102,6 +102,7 @@ cudaError_t launch_attention(const CUtensorMap& q_hi, const CUtensorMap& q_lo, c
                              const CUtensorMap& kv_lo, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const AttnParams& p,
                              cudaStream_t stream);
 constexpr int kAttnKeyPad = 208;
+extern bool g_attn_persistent;  // persistent (one CTA per SM, prefetching) vs one CTA per item
 
 // ----------------------------------------------------------------------------------------------
 // elementwise / row kernels      (elementwise.cu)

@@ -352,8 +352,10 @@ def test_sample_to_joints_full_batch_vs_oracle_and_cpu_tensor_raises():
     sample = torch.randn(64, D, 1, L, generator=gen)
     mean, std = torch.randn(D, generator=gen) * 0.3, torch.rand(D, generator=gen) * 0.2 + 0.01
     want = O.sample_to_joints(sample, mean, std, 22, False)
-    got = C.sample_to_joints(sample.to(DEV), mean, std, 22, False)
-    assert close(got, want, rtol=1e-4, atol=1e-4)
+    got = C.sample_to_joints(sample.to(DEV), mean, std, 22, False).cpu()
+    # prefix sums over 196 frames of O(1) steps: compare against the trajectory's scale (ulp-level sin/cos differences
+    # between the CPU and GPU math libraries are integrated along the path)
+    assert (got - want).abs().max() <= 2e-5 * want.abs().max() + 1e-5, (got - want).abs().max()
     kit = torch.randn(5, 40, 251, generator=gen)                  # KIT layout: 21 joints, 251 features
     assert close(C.recover_from_ric(kit.to(DEV), 21), O.recover_from_ric(kit, 21), rtol=1e-4, atol=1e-4)
     with pytest.raises(RuntimeError):
