@@ -337,6 +337,9 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap map_q_hi, const 
                             const __grid_constant__ CUtensorMap map_kv_hi, const __grid_constant__ CUtensorMap map_kv_lo,
                             const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
                             const AttnParams p, const int num_items, const int q_tiles) {
+  const long long t_entry = clock64();
+  unsigned long long ns_entry;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_entry));
   griddep_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -438,6 +441,7 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap map_q_hi, const 
       const int nterms = split ? 3 : 1;
       uint32_t it = 0;
       long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const long long t_loop = clock64();
       for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
         const uint32_t ph = it & 1;
         long long t0 = clock64(), t1;
@@ -497,8 +501,15 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap map_q_hi, const 
         umma_commit(&bars->o_done);
         acc[7] += 1;
       }
-      if (p.dbg_cycles)
+      if (p.dbg_cycles) {
         for (int i = 0; i < 8; ++i) p.dbg_cycles[(size_t)blockIdx.x * 16 + i] = acc[i];
+        unsigned long long ns_now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_now));
+        p.dbg_cycles[(size_t)blockIdx.x * 16 + 12] = t_loop - t_entry;
+        p.dbg_cycles[(size_t)blockIdx.x * 16 + 13] = clock64() - t_entry;
+        p.dbg_cycles[(size_t)blockIdx.x * 16 + 14] = (long long)(ns_now - ns_entry);
+        p.dbg_cycles[(size_t)blockIdx.x * 16 + 15] = (long long)ns_entry;
+      }
     }
     __syncwarp();
   } else {

@@ -182,6 +182,20 @@ extern "C" int cmdi_test_attention(const float* qkv, float* O, int num_seqs, int
       printf("attn2 dbg cycles (mean per item): MMA thread wait_q=%.0f wait_k=%.0f S-issue=%.0f wait_P=%.0f wait_Vhi=%.0f PV-issue=%.0f wait_Vlo=%.0f | "
              "softmax warp: wait_S=%.0f softmax=%.0f wait_O=%.0f epilogue=%.0f (items %.0f)\n",
              a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[8], a[9], a[10], a[11], items);
+      double pro = 0, tot_max = 0, ns_max = 0, n = 0;
+      long long first = 0, last_end = 0;
+      for (int c = 0; c < nctas; ++c) {
+        if (h[(size_t)c * 16 + 7] == 0) continue;
+        n += 1;
+        pro += (double)h[(size_t)c * 16 + 12];
+        if ((double)h[(size_t)c * 16 + 13] > tot_max) tot_max = (double)h[(size_t)c * 16 + 13];
+        if ((double)h[(size_t)c * 16 + 14] > ns_max) ns_max = (double)h[(size_t)c * 16 + 14];
+        const long long b = h[(size_t)c * 16 + 15], e_ = b + h[(size_t)c * 16 + 14];
+        if (first == 0 || b < first) first = b;
+        if (e_ > last_end) last_end = e_;
+      }
+      printf("attn2 dbg: ctas=%.0f prologue=%.0f cycles, longest CTA (MMA thread) %.0f cycles = %.0f ns, first entry -> last MMA-thread exit %.0f ns\n",
+             n, pro / n, tot_max, ns_max, (double)(last_end - first));
       fflush(stdout);
       p.dbg_cycles = nullptr;
     }

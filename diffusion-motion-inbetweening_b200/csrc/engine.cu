@@ -83,6 +83,7 @@ struct cmdi_engine {
   cmdi_model_cfg cfg{};
   int device = 0, num_sms = 148;
   int nsplit = 3;
+  int bn_qkv = kBnWide;
   int debug = 0, bn_wide = kBnWide, bn_narrow = kBnNarrow;  // CMDI_DEBUG / CMDI_BN_WIDE / CMDI_BN_NARROW (bring-up knobs)
   bool fuse_ln = false;   // CMDI_FUSE_LN=1: out-proj+norm1 and linear2+norm2 as one kernel each (correct, but 2-10% slower at B=64: its 3-pass epilogue is exposed with 50 tiles on 74 clusters; kept for larger batches / later tuning)
   bool tma_store = true;  // CMDI_EPI=stg selects the coalesced-STG epilogue everywhere
@@ -258,7 +259,7 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
     LinearParams q{};
     q.M = M; q.N = 3 * kDModel; q.K = kDModel; q.nsplit = e->nsplit; q.bias = w.bqkv;
     q.out_hi = qkv_out.hi; q.out_lo = qkv_out.lo; q.ld_bf = 3 * kDModel; q.nsplit_out = e->nsplit;
-    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->xseq_p, w.wqkv, q, kBnWide, s, &qkv_out));
+    for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->xseq_p, w.wqkv, q, e->bn_qkv, s, &qkv_out));
     CKI(mark());
     // attention core
     AttnParams a{};
@@ -462,6 +463,8 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   if (const char* g = getenv("CMDI_DEBUG")) e->debug = atoi(g);
   if (const char* g = getenv("CMDI_EPI")) e->tma_store = strcmp(g, "stg") != 0;
   if (const char* g = getenv("CMDI_PDL")) g_use_pdl = atoi(g) != 0;
+  e->bn_qkv = kBnWide;  // 256 x 192 pair tiles (CMDI_BN_QKV=192) measured no faster than 256 x 256 despite the better round count
+  if (const char* g = getenv("CMDI_BN_QKV")) e->bn_qkv = atoi(g);
   if (const char* g = getenv("CMDI_ATTN")) g_attn_persistent = strcmp(g, "oneshot") != 0;
   if (const char* g = getenv("CMDI_FUSE_LN")) e->fuse_ln = atoi(g) != 0;
   e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount; e->nsplit = cfg->precision;
@@ -481,7 +484,7 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   A(dev_alloc(e, &e->b_out, round_up(e->D_pad, kBnNarrow)));
   e->lw.resize(e->layers);
   for (auto& w : e->lw) {
-    A(alloc_planes(e, &w.wqkv, 3 * kDModel, kDModel, kDModel, kBnWide));
+    A(alloc_planes(e, &w.wqkv, 3 * kDModel, kDModel, kDModel, e->bn_qkv));
     A(alloc_planes(e, &w.wo, kDModel, kDModel, kDModel, kBnNarrow));
     A(alloc_planes(e, &w.w1, e->ff, kDModel, kDModel, kBnWide));
     A(alloc_planes(e, &w.w2, kDModel, e->ff, e->ff, kBnNarrow));

@@ -48,8 +48,9 @@ linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                const LinearParams p, const int num_stages, const int num_m_pairs, const int num_n_blocks) {
   constexpr int kHalfN = BLOCK_N / 2;               // W rows this CTA loads
   constexpr int kBBytes = kHalfN * kBlockK * 2;
-  constexpr uint32_t kTmemCols = 2 * BLOCK_N;       // double-buffered accumulator: 128 lanes x BLOCK_N fp32 each
-  static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+  // double-buffered accumulator: 128 lanes x BLOCK_N fp32 each (allocation rounded up to a power of two)
+  constexpr uint32_t kTmemCols = BLOCK_N == 128 ? 256 : 512;
+  static_assert(BLOCK_N == 128 || BLOCK_N == 192 || BLOCK_N == 256, "BLOCK_N");
 
   griddep_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
@@ -260,6 +261,8 @@ cudaError_t launch_impl2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const
 cudaError_t configure_linear2_kernels() {
   cudaError_t e = cudaFuncSetAttribute(linear2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(linear2_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(linear2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
 }
 
@@ -272,6 +275,7 @@ cudaError_t launch_linear_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo,
     return cudaErrorInvalidValue;
   }
   if (block_n == 256) return launch_impl2<256>(a_hi, a_lo, w_hi, w_lo, p, num_sms, stream, st);
+  if (block_n == 192) return launch_impl2<192>(a_hi, a_lo, w_hi, w_lo, p, num_sms, stream, st);
   if (block_n == 128) return launch_impl2<128>(a_hi, a_lo, w_hi, w_lo, p, num_sms, stream, st);
   set_last_error("launch_linear_pair: unsupported block_n %d", block_n);
   return cudaErrorInvalidValue;

@@ -147,7 +147,10 @@ template <int BLOCK_N>
 __device__ __forceinline__ void epilogue_tile(const LinearParams& p, const EpiStoreMaps& maps, uint32_t tmem_base, int acc,
                                               int m_blk, int n_blk, int lane_group, int col_part, int lane, uint32_t stage) {
   constexpr int kBlockM = kEpiBlockM;
-  constexpr int kColsPerPart = BLOCK_N / 2;
+  // the two column parts of a tile: halves, except BLOCK_N = 192 -> 128 + 64 (whole 64-column chunks per warp)
+  constexpr int kPart0Cols = (BLOCK_N == 192) ? 128 : BLOCK_N / 2;
+  const int col_start = col_part == 0 ? 0 : kPart0Cols;
+  const int part_cols = col_part == 0 ? kPart0Cols : BLOCK_N - kPart0Cols;
   const int warp_row0 = m_blk * kBlockM + lane_group * 32;
   RowSlots rows;
   rows.ok = 0;
@@ -169,13 +172,13 @@ __device__ __forceinline__ void epilogue_tile(const LinearParams& p, const EpiSt
   // issued before the accumulator is touched; consumers fetch it by shuffle
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
   {
-    const int nb = n_blk * BLOCK_N + col_part * kColsPerPart + lane * 4;
-    if (p.bias && lane * 4 < kColsPerPart && nb < p.N) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb));
+    const int nb = n_blk * BLOCK_N + col_start + lane * 4;
+    if (p.bias && lane * 4 < part_cols && nb < p.N) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb));
   }
 
 #pragma unroll 1
-  for (int c64 = 0; c64 < kColsPerPart / 64; ++c64) {
-    const int col_in_tile = col_part * kColsPerPart + c64 * 64;
+  for (int c64 = 0; c64 < part_cols / 64; ++c64) {
+    const int col_in_tile = col_start + c64 * 64;
     const int n0 = n_blk * BLOCK_N + col_in_tile;
     if (p.tma_store) {
       // the staging tile is about to be rewritten by ordinary shared-memory stores (residual fetch): the bulk store
