@@ -307,18 +307,40 @@ extern "C" int cmdi_test_layernorm_bwd(const float* dy, const float* v, const fl
 extern "C" int cmdi_test_attention_bwd(const float* qkv, const float* dO, float* dqkv, int num_seqs, int S, int H, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int rows = num_seqs * S, ld = 3 * H * 128, ldo = H * 128;
-  DevBuf q_hi, q_lo, d_hi, d_lo, g_hi, g_lo;
-  CK(q_hi.alloc((size_t)rows * ld * 2)); CK(q_lo.alloc((size_t)rows * ld * 2));
-  CK(d_hi.alloc((size_t)rows * ldo * 2)); CK(d_lo.alloc((size_t)rows * ldo * 2));
-  CK(g_hi.alloc((size_t)rows * ld * 2)); CK(g_lo.alloc((size_t)rows * ld * 2));
+  const int rows_p = round_up(rows, 128) + 256;  // tiles of the last sequence read past its end
+  DevBuf q_hi, q_lo, d_hi, d_lo, g_hi, g_lo, stats;
+  CK(q_hi.alloc((size_t)rows_p * ld * 2)); CK(q_lo.alloc((size_t)rows_p * ld * 2));
+  CK(d_hi.alloc((size_t)rows_p * ldo * 2)); CK(d_lo.alloc((size_t)rows_p * ldo * 2));
+  CK(g_hi.alloc((size_t)rows_p * ld * 2)); CK(g_lo.alloc((size_t)rows_p * ld * 2));
+  CK(stats.alloc((size_t)rows_p * H * sizeof(float2)));
+  CK(cudaMemsetAsync(q_hi.p, 0, (size_t)rows_p * ld * 2, stream)); CK(cudaMemsetAsync(q_lo.p, 0, (size_t)rows_p * ld * 2, stream));
+  CK(cudaMemsetAsync(d_hi.p, 0, (size_t)rows_p * ldo * 2, stream)); CK(cudaMemsetAsync(d_lo.p, 0, (size_t)rows_p * ldo * 2, stream));
   CK(launch_split_planes(qkv, rows, ld, ld, q_hi.as<__nv_bfloat16>(), q_lo.as<__nv_bfloat16>(), ld, stream));
   CK(launch_split_planes(dO, rows, ldo, ldo, d_hi.as<__nv_bfloat16>(), d_lo.as<__nv_bfloat16>(), ldo, stream));
-  CK(configure_attention_bwd_kernel());
   AttnBwdParams p{};
   p.num_seqs = num_seqs; p.seq_len = S; p.num_heads = H; p.qkv_hi = q_hi.as<__nv_bfloat16>(); p.qkv_lo = q_lo.as<__nv_bfloat16>();
   p.do_hi = d_hi.as<__nv_bfloat16>(); p.do_lo = d_lo.as<__nv_bfloat16>(); p.ld_do = ldo;
   p.dqkv_hi = g_hi.as<__nv_bfloat16>(); p.dqkv_lo = g_lo.as<__nv_bfloat16>();
-  CK(launch_attention_bwd(p, stream));
+  p.ld_dqkv = ld; p.nsplit = 3; p.stats = stats.as<float2>();
+  if (g_attn_bwd_tc && !getenv("CMDI_TEST_ATTN_BWD_SIMT")) {
+    CUtensorMap qt_hi, qt_lo, qf_hi, qf_lo, dt_hi, dt_lo, df_hi, df_lo, o_hi, o_lo;
+    if (make_tmap_bf16_2d(&qt_hi, q_hi.p, rows_p, ld, ld, 64, 128)) return 1;
+    if (make_tmap_bf16_2d(&qt_lo, q_lo.p, rows_p, ld, ld, 64, 128)) return 1;
+    if (make_tmap_bf16_2d(&qf_hi, q_hi.p, rows_p, ld, ld, 64, kAttnKeyPad)) return 1;
+    if (make_tmap_bf16_2d(&qf_lo, q_lo.p, rows_p, ld, ld, 64, kAttnKeyPad)) return 1;
+    if (make_tmap_bf16_2d(&dt_hi, d_hi.p, rows_p, ldo, ldo, 64, 128)) return 1;
+    if (make_tmap_bf16_2d(&dt_lo, d_lo.p, rows_p, ldo, ldo, 64, 128)) return 1;
+    if (make_tmap_bf16_2d(&df_hi, d_hi.p, rows_p, ldo, ldo, 64, kAttnKeyPad)) return 1;
+    if (make_tmap_bf16_2d(&df_lo, d_lo.p, rows_p, ldo, ldo, 64, kAttnKeyPad)) return 1;
+    if (make_tmap_bf16_2d(&o_hi, g_hi.p, rows_p, ld, ld, 64, 32)) return 1;
+    if (make_tmap_bf16_2d(&o_lo, g_lo.p, rows_p, ld, ld, 64, 32)) return 1;
+    CK(configure_attention_bwd_tc_kernel());
+    AttnBwdTcMaps bm{&qt_hi, &qt_lo, &qf_hi, &qf_lo, &dt_hi, &dt_lo, &df_hi, &df_lo, &o_hi, &o_lo};
+    CK(launch_attention_bwd_tc(bm, p, stream));
+  } else {
+    CK(configure_attention_bwd_kernel());
+    CK(launch_attention_bwd(p, stream));
+  }
   CK(cudaStreamSynchronize(stream));
   std::vector<uint16_t> hh((size_t)rows * ld), hl((size_t)rows * ld);
   std::vector<float> ho((size_t)rows * ld);

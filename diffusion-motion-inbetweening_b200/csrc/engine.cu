@@ -127,6 +127,8 @@ struct cmdi_engine {
   Planes w_inT, w_outT;
   std::vector<LayerStash> stash;
   bool stash_ready = false;
+  float2* attn_stats = nullptr;          // [seq_rows_pad, H] softmax statistics handed from pass 0 to pass 1 of the attention backward
+  CUtensorMap do_f_hi{}, do_f_lo{};      // attn_p planes (dO) as 208-row operands
   Planes seed_p;               // dL/d(model output rows), frame-major [2*frame_rows_pad, D_pad]
   float* guide_grad = nullptr; // dL/dz per pass, frame-major [2*frame_rows_pad, D_pad]
   float* guide_coef = nullptr; // [T] w_r[t] * sqrt(alpha_bar_t) / 2
@@ -328,8 +330,12 @@ int ensure_stash(cmdi_engine* e) {
     return 1;
   }
   CK(configure_attention_bwd_kernel());
+  CK(configure_attention_bwd_tc_kernel());
   e->stash.resize(e->layers);
   int rc = 0;
+  rc = rc || dev_alloc(e, &e->attn_stats, (size_t)e->seq_rows_pad * e->H);
+  rc = rc || make_tmap_bf16_2d(&e->do_f_hi, e->attn_p.hi, e->seq_rows_pad, kDModel, kDModel, 64, kAttnKeyPad);
+  rc = rc || make_tmap_bf16_2d(&e->do_f_lo, e->attn_p.lo, e->seq_rows_pad, kDModel, kDModel, 64, kAttnKeyPad);
   for (auto& ls : e->stash) {
     rc = rc || alloc_planes(e, &ls.qkv, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 128);
     rc = rc || make_tmap_bf16_2d(&ls.q_hi, ls.qkv.hi, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, 128);
@@ -350,7 +356,7 @@ int ensure_stash(cmdi_engine* e) {
 // Backward pass of the (CFG-wrapped) denoiser w.r.t. its input, seeded with dL/dx0_hat of the reconstruction loss
 // (gaussian_diffusion.py:415-416).  Result: guide_grad[nseq * L, D_pad] (cond rows, then uncond rows under CFG).
 // Scratch: xseq / x1 (fp32 + planes) carry the running gradients; qkv_p / attn_p / ffh_p the per-layer ones.
-constexpr int kBackwardLaunchesPerLayer = 7;
+constexpr int kBackwardLaunchesPerLayer = 7;  // + 1 when the attention backward runs on tensor cores (two launches)
 int run_backward(cmdi_engine* e, int B, bool cfg, cudaStream_t s) {
   const int nseq = cfg ? 2 * B : B;
   const int M = nseq * e->S, MF = nseq * e->L;
@@ -391,7 +397,14 @@ int run_backward(cmdi_engine* e, int B, bool cfg, cudaStream_t s) {
     AttnBwdParams ab{};
     ab.num_seqs = nseq; ab.seq_len = e->S; ab.num_heads = e->H; ab.qkv_hi = ls.qkv.hi; ab.qkv_lo = ls.qkv.lo;
     ab.do_hi = e->attn_p.hi; ab.do_lo = e->attn_p.lo; ab.ld_do = kDModel; ab.dqkv_hi = e->qkv_p.hi; ab.dqkv_lo = e->qkv_p.lo;
-    CK(launch_attention_bwd(ab, s));
+    ab.ld_dqkv = 3 * kDModel; ab.nsplit = e->nsplit; ab.stats = e->attn_stats;
+    if (g_attn_bwd_tc) {
+      AttnBwdTcMaps bm{&ls.q_hi, &ls.q_lo, &ls.kv_hi, &ls.kv_lo, &e->attn_p.map_hi, &e->attn_p.map_lo, &e->do_f_hi, &e->do_f_lo,
+                       &e->qkv_p.st_hi, &e->qkv_p.st_lo};
+      CK(launch_attention_bwd_tc(bm, ab, s));
+    } else {
+      CK(launch_attention_bwd(ab, s));
+    }
     // QKV projection backward + the skip path: dX = dQKV Wqkv + dV1
     LinearParams bq{};
     bq.M = M; bq.N = kDModel; bq.K = 3 * kDModel; bq.nsplit = e->nsplit; bq.residual = e->x1; bq.ld_res = kDModel;
@@ -406,7 +419,9 @@ int run_backward(cmdi_engine* e, int B, bool cfg, cudaStream_t s) {
   CKI(run_linear(e, e->xseq_p, e->w_inT, fi, kBnNarrow, s));
   return 0;
 }
-int launches_per_backward(const cmdi_engine* e) { return 3 + e->layers * kBackwardLaunchesPerLayer + 1; }
+int launches_per_backward(const cmdi_engine* e) {
+  return 3 + e->layers * (kBackwardLaunchesPerLayer + (g_attn_bwd_tc ? 1 : 0)) + 1;
+}
 
 int launches_per_pass(const cmdi_engine* e) { return 1 + 1 + e->layers * (e->fuse_ln ? 5 : 7) + 1; }
 
@@ -465,6 +480,7 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   if (const char* g = getenv("CMDI_PDL")) g_use_pdl = atoi(g) != 0;
   e->bn_qkv = kBnWide;  // 256 x 192 pair tiles (CMDI_BN_QKV=192) measured no faster than 256 x 256 despite the better round count
   if (const char* g = getenv("CMDI_BN_QKV")) e->bn_qkv = atoi(g);
+  if (const char* g = getenv("CMDI_ATTN_BWD")) g_attn_bwd_tc = strcmp(g, "simt") != 0;
   if (const char* g = getenv("CMDI_ATTN")) g_attn_persistent = strcmp(g, "oneshot") != 0;
   if (const char* g = getenv("CMDI_FUSE_LN")) e->fuse_ln = atoi(g) != 0;
   e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount; e->nsplit = cfg->precision;

@@ -242,9 +242,21 @@ struct AttnBwdParams {
   int ld_do;
   __nv_bfloat16* dqkv_hi;        // out: dQ|dK|dV planes [rows, 3*H*128]
   __nv_bfloat16* dqkv_lo;
+  // tensor-core kernel only
+  int ld_dqkv;                   // 3*H*128
+  int nsplit;                    // 1 or 3
+  float2* stats;                 // [rows, H]: (max*c + log2(sum), delta) per query row, written by pass 0, read by pass 1
 };
 cudaError_t configure_attention_bwd_kernel();
-cudaError_t launch_attention_bwd(const AttnBwdParams& p, cudaStream_t stream);
+cudaError_t launch_attention_bwd(const AttnBwdParams& p, cudaStream_t stream);  // fp32 CUDA cores (backward.cu)
+// tcgen05 version (attention_bwd_tc.cu).  Maps over the bf16 planes, box {64, rows}: *_t = 128-row tiles, *_f = 208-row
+// operands; out_* = the dqkv planes as TMA-store targets, box {64, 32}.
+struct AttnBwdTcMaps {
+  const CUtensorMap *qkv_t_hi, *qkv_t_lo, *qkv_f_hi, *qkv_f_lo, *do_t_hi, *do_t_lo, *do_f_hi, *do_f_lo, *out_hi, *out_lo;
+};
+extern bool g_attn_bwd_tc;
+cudaError_t configure_attention_bwd_tc_kernel();
+cudaError_t launch_attention_bwd_tc(const AttnBwdTcMaps& m, const AttnBwdParams& p, cudaStream_t stream);
 cudaError_t launch_transpose_split(const float* w, int R, int C, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_out,
                                    cudaStream_t stream);
 

@@ -158,7 +158,8 @@ def test_layernorm_backward_matches_autograd():
     assert err < 2e-5, err  # fp32 kernel vs fp64 autograd on identical fp32 inputs (|dV| up to ~4)
 
 
-@pytest.mark.parametrize("nseq,S,H", [(1, 197, 1), (3, 197, 4), (2, 50, 4), (2, 5, 2)])
+@pytest.mark.parametrize("nseq,S,H", [(1, 197, 1), (3, 197, 4), (2, 50, 4), (2, 5, 2), (2, 1, 4), (2, 128, 2), (2, 129, 2),
+                                      (1, 207, 4), (64, 197, 4)])
 def test_attention_backward_matches_autograd(nseq, S, H):
     g = torch.Generator(device="cuda").manual_seed(S)
     qkv = torch.randn(nseq * S, 3 * H * 128, device="cuda", generator=g)
@@ -169,9 +170,25 @@ def test_attention_backward_matches_autograd(nseq, S, H):
     got = torch.full_like(qkv, float("nan"))
     C.capi.check(_lib().cmdi_test_attention_bwd(_p(qkv), _p(dO), _p(got), nseq, S, H, None))
     torch.cuda.synchronize()
-    # inputs are rounded to bf16 hi+lo (2^-17) on the way in, fp32 arithmetic inside
+    # tcgen05 kernel: every product with the bf16 hi/lo split (attention_bwd_tc.cu)
     assert torch.allclose(got.double(), ref, rtol=1e-3, atol=1e-4)
     assert (got.double() - ref).abs().max() < 1e-4
+
+
+def test_attention_backward_cuda_core_kernel_agrees(monkeypatch):
+    """the fp32 CUDA-core kernel (CMDI_ATTN_BWD=simt) stays as the independent implementation of the same math"""
+    monkeypatch.setenv("CMDI_TEST_ATTN_BWD_SIMT", "1")
+    nseq, S, H = 2, 197, 4
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = torch.randn(nseq * S, 3 * H * 128, device="cuda", generator=g)
+    dO = torch.randn(nseq * S, H * 128, device="cuda", generator=g)
+    simt = torch.full_like(qkv, float("nan"))
+    C.capi.check(_lib().cmdi_test_attention_bwd(_p(qkv), _p(dO), _p(simt), nseq, S, H, None))
+    monkeypatch.delenv("CMDI_TEST_ATTN_BWD_SIMT")
+    tc = torch.full_like(qkv, float("nan"))
+    C.capi.check(_lib().cmdi_test_attention_bwd(_p(qkv), _p(dO), _p(tc), nseq, S, H, None))
+    torch.cuda.synchronize()
+    assert (simt - tc).abs().max() < 1e-4
 
 
 def test_counter_based_normal_generator():
