@@ -293,7 +293,7 @@ def run_engine(args):
     split = 3 if precision == C.capi.PRECISION_BF16X3 else 1
     traffic, traffic_src = None, None
     try:  # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture (per launch, like `achieved`)
-        with open(os.path.join(ROOT, "profiles", "r01c_dominant_kernel_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")) as f:
             tr = json.load(f)
         if tr.get("kernel") == dom:
             traffic, traffic_src = tr["dram_bytes_read"] + tr["dram_bytes_write"], tr["source"]
