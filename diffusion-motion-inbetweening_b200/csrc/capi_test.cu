@@ -78,6 +78,14 @@ extern "C" int cmdi_test_linear(const float* A, const float* W, const float* bia
   LinearParams p{};
   p.M = M; p.N = N; p.K = K; p.nsplit = precision;
   p.bias = bias; p.residual = residual; p.ld_res = N;
+  DevBuf r_hi, r_lo;
+  if (residual && getenv("CMDI_TEST_RES_PLANES")) {
+    // the same residual handed over as bf16 hi/lo planes (what the engine does between encoder sublayers)
+    CK(r_hi.alloc((size_t)M * N * 2));
+    CK(r_lo.alloc((size_t)M * N * 2));
+    CK(launch_split_planes(residual, M, N, N, r_hi.as<__nv_bfloat16>(), r_lo.as<__nv_bfloat16>(), N, stream));
+    p.residual = nullptr; p.res_hi = r_hi.as<__nv_bfloat16>(); p.res_lo = r_lo.as<__nv_bfloat16>(); p.ld_res_bf = N;
+  }
   p.act = act; p.rowmap = ROWMAP_IDENTITY;
   p.out_f32 = C; p.ld_f32 = N;
   p.nsplit_out = precision;

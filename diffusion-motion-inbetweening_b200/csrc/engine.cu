@@ -86,6 +86,7 @@ struct cmdi_engine {
   int bn_qkv = kBnWide;
   int debug = 0, bn_wide = kBnWide, bn_narrow = kBnNarrow;  // CMDI_DEBUG / CMDI_BN_WIDE / CMDI_BN_NARROW (bring-up knobs)
   bool fuse_ln = false;   // CMDI_FUSE_LN=1: out-proj+norm1 and linear2+norm2 as one kernel each (correct, but 2-10% slower at B=64: its 3-pass epilogue is exposed with 50 tiles on 74 clusters; kept for larger batches / later tuning)
+  bool plane_residual = false;  // CMDI_RES=planes: residual stream from the bf16 hi/lo planes, LayerNorm skips its fp32 copy (+1.7 % steps/s, but the CFG-amplified error grows from 4.2e-5 to 7.1e-5 against the 1e-4 gate: off)
   bool tma_store = true;  // CMDI_EPI=stg selects the coalesced-STG epilogue everywhere
   bool use_pair = true;  // CTA-pair (cta_group::2) linear kernels; CMDI_GEMM=single selects the 1-CTA kernels
   int D = 263, D_pad = 264, L = 196, S = 197, ff = 1024, H = 4, layers = 8, maxB = 0;
@@ -241,11 +242,14 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
   for (int r_ = 0; r_ < reps; ++r_) CK(launch_token_rows(tk, s));
   CKI(mark());
 
+  // bf16x3, unfused LayerNorm: the residual stream lives in the hi/lo planes only (x = hi + lo to 2^-17) -- LayerNorm
+  // and the frame embedding skip their fp32 copy, the next sublayer's epilogue adds the planes back
+  const bool plane_res = e->plane_residual && e->nsplit == 3 && !e->fuse_ln;
   LinearParams p{};
   // frame embedding + positional encoding (mdm.py:271, :279-280)
   p.M = B * e->L; p.N = kDModel; p.K = e->D; p.nsplit = e->nsplit; p.bias = e->b_in; p.pos_enc = e->pe;
   p.rowmap = ROWMAP_FRAMES_TO_SEQ; p.frames = e->L; p.dup_row_offset = dup ? B * e->S : 0;
-  p.out_f32 = e->xseq; p.ld_f32 = kDModel; p.out_hi = e->xseq_p.hi; p.out_lo = e->xseq_p.lo; p.ld_bf = kDModel;
+  p.out_f32 = plane_res ? nullptr : e->xseq; p.ld_f32 = kDModel; p.out_hi = e->xseq_p.hi; p.out_lo = e->xseq_p.lo; p.ld_bf = kDModel;
   p.nsplit_out = e->nsplit;
   for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->x_state_p, e->w_in, p, kBnNarrow, s));
   CKI(mark());
@@ -282,11 +286,12 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
     } else {
       LinearParams o{};
       o.M = M; o.N = kDModel; o.K = kDModel; o.nsplit = e->nsplit; o.bias = w.bo; o.residual = e->xseq; o.ld_res = kDModel;
+      if (plane_res) { o.residual = nullptr; o.res_hi = e->xseq_p.hi; o.res_lo = e->xseq_p.lo; o.ld_res_bf = kDModel; }
       o.out_f32 = v1_out; o.ld_f32 = kDModel; o.nsplit_out = e->nsplit;
       for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->attn_p, w.wo, o, kBnNarrow, s, nullptr, ls ? nullptr : &e->vsum_st));
       CKI(mark());
       for (int r_ = 0; r_ < reps; ++r_)
-        CK(launch_layernorm512(v1_out, w.g1, w.be1, 1e-5f, M, e->x1, e->x1_p.hi, e->nsplit == 3 ? e->x1_p.lo : nullptr, s));
+        CK(launch_layernorm512(v1_out, w.g1, w.be1, 1e-5f, M, plane_res ? nullptr : e->x1, e->x1_p.hi, e->nsplit == 3 ? e->x1_p.lo : nullptr, s));
       CKI(mark());
     }
     // FFN
@@ -307,11 +312,12 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
     } else {
       LinearParams f2{};
       f2.M = M; f2.N = kDModel; f2.K = e->ff; f2.nsplit = e->nsplit; f2.bias = w.b2; f2.residual = e->x1; f2.ld_res = kDModel;
+      if (plane_res) { f2.residual = nullptr; f2.res_hi = e->x1_p.hi; f2.res_lo = e->x1_p.lo; f2.ld_res_bf = kDModel; }
       f2.out_f32 = v2_out; f2.ld_f32 = kDModel; f2.nsplit_out = e->nsplit;
       for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->ffh_p, w.w2, f2, kBnNarrow, s, nullptr, ls ? nullptr : &e->vsum_st));
       CKI(mark());
       for (int r_ = 0; r_ < reps; ++r_)
-        CK(launch_layernorm512(v2_out, w.g2, w.be2, 1e-5f, M, e->xseq, e->xseq_p.hi, e->nsplit == 3 ? e->xseq_p.lo : nullptr, s));
+        CK(launch_layernorm512(v2_out, w.g2, w.be2, 1e-5f, M, plane_res ? nullptr : e->xseq, e->xseq_p.hi, e->nsplit == 3 ? e->xseq_p.lo : nullptr, s));
       CKI(mark());
     }
   }
@@ -325,8 +331,8 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
 }
 int ensure_stash(cmdi_engine* e) {
   if (e->stash_ready) return 0;
-  if (e->S > 197) {
-    set_last_error("reconstruction guidance supports nframes <= 196 (attention backward tile)");
+  if (e->S > 197 && !g_attn_bwd_tc) {
+    set_last_error("the CUDA-core attention backward supports nframes <= 196");
     return 1;
   }
   CK(configure_attention_bwd_kernel());
@@ -480,6 +486,7 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   if (const char* g = getenv("CMDI_PDL")) g_use_pdl = atoi(g) != 0;
   e->bn_qkv = kBnWide;  // 256 x 192 pair tiles (CMDI_BN_QKV=192) measured no faster than 256 x 256 despite the better round count
   if (const char* g = getenv("CMDI_BN_QKV")) e->bn_qkv = atoi(g);
+  if (const char* g = getenv("CMDI_RES")) e->plane_residual = strcmp(g, "planes") == 0;
   if (const char* g = getenv("CMDI_ATTN_BWD")) g_attn_bwd_tc = strcmp(g, "simt") != 0;
   if (const char* g = getenv("CMDI_ATTN")) g_attn_persistent = strcmp(g, "oneshot") != 0;
   if (const char* g = getenv("CMDI_FUSE_LN")) e->fuse_ln = atoi(g) != 0;

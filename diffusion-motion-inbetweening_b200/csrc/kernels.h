@@ -34,6 +34,9 @@ struct LinearParams {
   const float* bias;      // [N] or null
   const float* residual;  // fp32 [rows, ld_res], indexed by OUTPUT row; or null
   int ld_res;
+  const __nv_bfloat16* res_hi;  // the same residual as bf16 hi/lo planes [rows, ld_res_bf] (x = hi + lo), or null:
+  const __nv_bfloat16* res_lo;  // lets LayerNorm skip its fp32 output (the planes are what the next GEMM reads anyway)
+  int ld_res_bf;
   const float* pos_enc;  // fp32 [L+1, N] table added per output sequence position (ROWMAP_FRAMES_TO_SEQ); or null
   int act;               // 0 none, 1 exact erf GELU
   int f32_pre;           // 1: out_f32 receives the value BEFORE the activation (stash for the GELU backward)

@@ -65,6 +65,15 @@ def test_linear_epilogues(act, res, bn):
     assert torch.allclose(out, ref, **GATE)
 
 
+@pytest.mark.parametrize("bn", [-256, -128, 128])
+def test_linear_residual_from_bf16_planes(monkeypatch, bn):
+    """the residual stream between encoder sublayers is handed over as bf16 hi/lo planes (x = hi + lo to 2^-17)"""
+    monkeypatch.setenv("CMDI_TEST_RES_PLANES", "1")
+    out, ref = run_linear(777, 512, 512, 3, bn, act=0, res=True)
+    assert torch.allclose(out, ref, **GATE)
+    assert (out - ref).abs().max() < 1e-4
+
+
 def test_linear_plain_bf16_is_bf16_accurate():
     out, ref = run_linear(512, 512, 512, 1, 128)
     err = (out - ref).abs().max().item()
