@@ -23,7 +23,17 @@ import sys
 import threading
 import time
 
-os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner / debug lines do not belong on stdout
+
+# Rank 0 prints exactly ONE JSON line on stdout.  Libraries (NCCL's version banner, torch warnings) write to fd 1
+# whenever they like, so fd 1 is pointed at stderr for the life of the process and the JSON line goes to the saved fd.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 import torch  # noqa: E402
 
@@ -184,7 +194,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_engine(args):
@@ -323,7 +333,7 @@ def run_engine(args):
                        "l2": "per-step working set (weights 70 MB as bf16 hi+lo, activations ~0.4 GB) exceeds the 126 MB L2; no explicit flush",
                        "cuda_graph": f"one captured {len(prof) + 1}-kernel step graph, replayed per step, step index on the device"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
