@@ -320,9 +320,11 @@ def run_engine(args):
                         "issues 3 MMAs per product, so the tensor pipe does `mma_terms_per_product` x that work"}
 
     # ---- CPU baseline on this box's host cores: a bounded sample of the same workload ----
-    done, dt, threads = cpu_reference_steps(max_steps=12, budget_s=25.0)
-    cpu = {"value": done / dt, "unit": UNIT, "cores": threads, "kind": "port",
-           "sample": f"{done} consecutive DDPM steps of the same B=64 loop on the host CPU (fp32 PyTorch restatement of the reference)"}
+    cpu = None  # timed at N=1 only (the other ranks' processes would compete for the same host cores)
+    if world == 1:
+        done, dt, threads = cpu_reference_steps(max_steps=12, budget_s=25.0)
+        cpu = {"value": done / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{done} consecutive DDPM steps of the same B=64 loop on the host CPU (fp32 PyTorch restatement of the reference)"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
