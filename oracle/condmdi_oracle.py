@@ -527,3 +527,8 @@ def postprocess_inputs(B: int = 3, D: int = 263, L: int = 196) -> Dict[str, torc
     dataset statistics used and the REFERENCE's outputs)."""
     g = torch.Generator().manual_seed(4321)
     return dict(sample=torch.randn(B, D, 1, L, generator=g), ragged=torch.randn(2, 1, 57, D, generator=g))
+
+
+def long_loop_tape(B: int = 2, D: int = 263, L: int = 196, steps: int = 1000) -> torch.Tensor:
+    """(1 + steps, B, D, 1, L) seeded noise of the full-length loop fixture (tests/golden/long_loop.npz); 412 MB."""
+    return torch.randn(1 + steps, B, D, 1, L, generator=torch.Generator().manual_seed(2024))

@@ -216,6 +216,32 @@ def golden_postprocess():
     np.savez_compressed(os.path.join(GOLDEN, "postprocess.npz"), **out)
 
 
+def golden_long_loop():
+    """The whole 1000-step ancestral loop (configs[1] at B=2) run by the reference on the CPU: pins error growth over
+    the full length of the chain, not just a few steps."""
+    print("full-length DDPM loop, 1000 steps, B=2 (takes a few minutes)")
+    sd = O.random_state_dict(seed=7, text=False)
+    m = ref_model_with(sd, text=False)
+    d = RH.build_reference_diffusion("")
+    tape = O.long_loop_tape()
+    near_end = None
+    with torch.no_grad(), RH.noise_tape(tape):
+        for k, o_ in enumerate(d.p_sample_loop_progressive(m, (2, D, 1, L), clip_denoised=False, model_kwargs={"y": {}},
+                                                           device="cpu", progress=False)):
+            if k == 994:
+                near_end = o_["sample"].clone()   # x_t entering the step with t = 4
+            sample = o_["sample"]
+    # the oracle restatement reproduces the last five steps from the reference's own state (cheap CPU check)
+    c = O.Conditioning()
+    x = near_end
+    with torch.no_grad():
+        for t in range(4, -1, -1):
+            x = O.p_sample(sd, O.make_tables(""), x, torch.full((2,), t), c, tape[1 + 999 - t])["sample"]
+    close(sample, x, 2e-5, "last 5 of 1000 steps")
+    np.savez_compressed(os.path.join(GOLDEN, "long_loop.npz"), sample=sample.numpy(), x_at_t4=near_end.numpy(),
+                        tape_checksum=np.array([float(tape.double().sum()), float(tape[500].double().abs().sum())]))
+
+
 def main():
     if not RH.available():
         raise SystemExit("the reference tree is required to (re)generate golden vectors")
@@ -225,6 +251,7 @@ def main():
     golden_masks()
     golden_model_and_sampler()
     golden_postprocess()
+    golden_long_loop()
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)) // 1024, "KiB")
 

@@ -107,6 +107,17 @@ def test_p_sample_loop_three_steps_vs_reference_golden(plain, gi, gold):
     assert torch.equal(res[True]["sample"], res[False]["sample"])  # graph replay == plain launches, bit for bit
 
 
+def test_full_1000_step_ddpm_loop_vs_reference_golden(plain, golden_dir):
+    """configs[1] at B=2, the whole chain: 1000 engine steps against the reference's own CPU run of the same loop on the
+    same noise (tests/golden/long_loop.npz) -- error growth over the full length, through the public API and the graph."""
+    g = np.load(os.path.join(golden_dir, "long_loop.npz"))
+    m, _ = plain
+    diff = C.create_gaussian_diffusion()
+    diff.noise_tape = O.long_loop_tape().to(DEV)
+    out = diff.p_sample_loop(m, (B, D, 1, L), clip_denoised=False, model_kwargs={"y": {}})
+    assert close(out, g["sample"], **GATE)
+
+
 def test_ddim50_full_loop_vs_reference_golden(plain, gi, gold):
     m, sd = plain
     d50 = C.create_gaussian_diffusion(timestep_respacing="ddim50")

@@ -126,3 +126,17 @@ def test_recover_from_ric_matches_reference(golden_dir, tag, abs_3d):
     rag = O.recover_from_ric(inp["ragged"], 22, abs_3d)
     assert rag.shape == (2, 1, 57, 22, 3)
     assert torch.allclose(rag, torch.from_numpy(g[f"{tag}.ragged"]), rtol=1e-6, atol=1e-6)
+
+
+def test_full_length_loop_fixture_last_steps(golden_dir):
+    """tests/golden/long_loop.npz = the reference's own 1000-step DDPM loop (B=2).  The CPU suite replays its last
+    five steps from the reference's state at t=4 (the whole chain takes minutes on a CPU; the GPU suite runs all of it)."""
+    g = np.load(os.path.join(golden_dir, "long_loop.npz"))
+    tape = O.long_loop_tape()
+    assert np.allclose([float(tape.double().sum()), float(tape[500].double().abs().sum())], g["tape_checksum"], rtol=1e-12)
+    sd, tab, c = O.random_state_dict(seed=7, text=False), O.make_tables(""), O.Conditioning()
+    x = torch.from_numpy(g["x_at_t4"])
+    with torch.no_grad():
+        for t in range(4, -1, -1):
+            x = O.p_sample(sd, tab, x, torch.full((2,), t), c, tape[1 + 999 - t])["sample"]
+    assert torch.allclose(x, torch.from_numpy(g["sample"]), rtol=1e-5, atol=2e-5)
