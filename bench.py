@@ -316,8 +316,11 @@ def run_engine(args):
                 "mma_terms_per_product": split, "tensor_pipe_frac_incl_split": split * achieved / peaks["bf16_tflops"],
                 "whole_step_algorithmic_tflops": flops_per_pass(B) * args.steps / (ms * 1e-3) / 1e12,
                 "per_kernel_ms_per_step": {k: round(v[0], 4) for k, v in by_kind.items()},
+                "between_kernels_ms_per_step": round(ms / args.steps - step_ms, 4),
                 "note": "achieved = algorithmic FLOPs (2MNK, fp32-equivalent product) / event-timed launch; the bf16x3 split "
-                        "issues 3 MMAs per product, so the tensor pipe does `mma_terms_per_product` x that work"}
+                        "issues 3 MMAs per product, so the tensor pipe does `mma_terms_per_product` x that work; "
+                        "between_kernels = graph-replayed step time minus the sum of the per-kernel times (the step kernel, "
+                        "kernel tails / ramps at the 60 kernel boundaries, graph launch)"}
 
     # ---- CPU baseline on this box's host cores: a bounded sample of the same workload ----
     cpu = None  # timed at N=1 only (the other ranks' processes would compete for the same host cores)
