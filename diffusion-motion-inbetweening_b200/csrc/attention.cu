@@ -58,7 +58,7 @@ __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
 // logits of this thread's key range -> registers, row max, exchange, probabilities -> TMEM, row sum
 template <int CHUNK0, int NCHUNKS>
 __device__ __forceinline__ float softmax_half(uint32_t trow, int S, bool split, float c_scale, float (*red_max)[128], int half,
-                                              int row) {
+                                              int row, bool trunc) {
   float s[NCHUNKS * 16];
   {
     // all TMEM reads in flight at once, one wait
@@ -91,7 +91,7 @@ __device__ __forceinline__ float softmax_half(uint32_t trow, int S, bool split, 
       const float p0 = fast_exp2(fmaf(s[c * 16 + j * 2], c_scale, -mc));
       const float p1 = fast_exp2(fmaf(s[c * 16 + j * 2 + 1], c_scale, -mc));
       sum += p0 + p1;
-      split_bf16x2(p0, p1, ph[j], pl[j]);
+      if (trunc) split_bf16x2_trunc(p0, p1, ph[j], pl[j]); else split_bf16x2(p0, p1, ph[j], pl[j]);
     }
     tmem_st8(trow + kColPHi + (CHUNK0 + c) * 8, ph);
     if (split) tmem_st8(trow + kColPLo + (CHUNK0 + c) * 8, pl);
@@ -247,9 +247,9 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_cons
     tc_fence_after();
     float sum;
     if (half == 0) {
-      sum = softmax_half<0, kChunks0>(trow, S, split, c_scale, bars->red_max, 0, row);
+      sum = softmax_half<0, kChunks0>(trow, S, split, c_scale, bars->red_max, 0, row, p.trunc_split != 0);
     } else {
-      sum = softmax_half<kChunks0, kChunks1>(trow, S, split, c_scale, bars->red_max, 1, row);
+      sum = softmax_half<kChunks0, kChunks1>(trow, S, split, c_scale, bars->red_max, 1, row, p.trunc_split != 0);
     }
     bars->red_sum[half][row] = sum;
     tmem_st_wait();
@@ -535,9 +535,9 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap map_q_hi, const 
       tc_fence_after();
       float sum;
       if (half == 0) {
-        sum = softmax_half<0, kChunks0>(trow, S, split, c_scale, bars->red_max, 0, row);
+        sum = softmax_half<0, kChunks0>(trow, S, split, c_scale, bars->red_max, 0, row, p.trunc_split != 0);
       } else {
-        sum = softmax_half<kChunks0, kChunks1>(trow, S, split, c_scale, bars->red_max, 1, row);
+        sum = softmax_half<kChunks0, kChunks1>(trow, S, split, c_scale, bars->red_max, 1, row, p.trunc_split != 0);
       }
       bars->red_sum[half][row] = sum;
       tmem_st_wait();
@@ -558,8 +558,13 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap map_q_hi, const 
       uint32_t hw[32], lw[32];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        split_bf16x2(__uint_as_float(v0[2 * j]) * inv, __uint_as_float(v0[2 * j + 1]) * inv, hw[j], lw[j]);
-        split_bf16x2(__uint_as_float(v1[2 * j]) * inv, __uint_as_float(v1[2 * j + 1]) * inv, hw[16 + j], lw[16 + j]);
+        if (p.trunc_split) {
+          split_bf16x2_trunc(__uint_as_float(v0[2 * j]) * inv, __uint_as_float(v0[2 * j + 1]) * inv, hw[j], lw[j]);
+          split_bf16x2_trunc(__uint_as_float(v1[2 * j]) * inv, __uint_as_float(v1[2 * j + 1]) * inv, hw[16 + j], lw[16 + j]);
+        } else {
+          split_bf16x2(__uint_as_float(v0[2 * j]) * inv, __uint_as_float(v0[2 * j + 1]) * inv, hw[j], lw[j]);
+          split_bf16x2(__uint_as_float(v1[2 * j]) * inv, __uint_as_float(v1[2 * j + 1]) * inv, hw[16 + j], lw[16 + j]);
+        }
       }
       const int group_row0 = qtile * kQTile + lane_group * 32;  // first query of this warp's 32 rows
       if (group_row0 + 32 <= S) {

@@ -168,6 +168,7 @@ extern "C" int cmdi_test_attention(const float* qkv, float* O, int num_seqs, int
   AttnParams p{};
   p.num_seqs = num_seqs; p.seq_len = S; p.num_heads = H; p.nsplit = precision; p.nsplit_out = 3;
   p.out_hi = o_hi.as<__nv_bfloat16>(); p.out_lo = o_lo.as<__nv_bfloat16>(); p.ld_out = ldo;
+  if (const char* g = getenv("CMDI_ATTN_SPLIT")) p.trunc_split = strcmp(g, "trunc") == 0;
   DevBuf adbg;
   const int nctas = ((S + 127) / 128) * H * num_seqs;
   if (getenv("CMDI_TEST_DBG")) {

@@ -86,6 +86,7 @@ struct cmdi_engine {
   int bn_qkv = kBnWide;
   int debug = 0, bn_wide = kBnWide, bn_narrow = kBnNarrow;  // CMDI_DEBUG / CMDI_BN_WIDE / CMDI_BN_NARROW (bring-up knobs)
   bool fuse_ln = false;   // CMDI_FUSE_LN=1: out-proj+norm1 and linear2+norm2 as one kernel each (correct, but 2-10% slower at B=64: its 3-pass epilogue is exposed with 50 tiles on 74 clusters; kept for larger batches / later tuning)
+  int attn_trunc_split = 0;  // CMDI_ATTN_SPLIT=trunc
   bool plane_residual = false;  // CMDI_RES=planes: residual stream from the bf16 hi/lo planes, LayerNorm skips its fp32 copy (+1.7 % steps/s, but the CFG-amplified error grows from 4.2e-5 to 7.1e-5 against the 1e-4 gate: off)
   bool tma_store = true;  // CMDI_EPI=stg selects the coalesced-STG epilogue everywhere
   bool use_pair = true;  // CTA-pair (cta_group::2) linear kernels; CMDI_GEMM=single selects the 1-CTA kernels
@@ -270,7 +271,7 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
     // attention core
     AttnParams a{};
     a.num_seqs = nseq; a.seq_len = e->S; a.num_heads = e->H; a.nsplit = e->nsplit; a.nsplit_out = e->nsplit;
-    a.out_hi = e->attn_p.hi; a.out_lo = e->attn_p.lo; a.ld_out = kDModel;
+    a.out_hi = e->attn_p.hi; a.out_lo = e->attn_p.lo; a.ld_out = kDModel; a.trunc_split = e->attn_trunc_split;
     for (int r_ = 0; r_ < reps; ++r_) CK(launch_attention(ls ? ls->q_hi : e->q_map_hi, ls ? ls->q_lo : e->q_map_lo, ls ? ls->kv_hi : e->kv_map_hi,
                                                          ls ? ls->kv_lo : e->kv_map_lo, e->attn_p.st_hi, e->attn_p.st_lo, a, s));
     CKI(mark());
@@ -486,6 +487,7 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   if (const char* g = getenv("CMDI_PDL")) g_use_pdl = atoi(g) != 0;
   e->bn_qkv = kBnWide;  // 256 x 192 pair tiles (CMDI_BN_QKV=192) measured no faster than 256 x 256 despite the better round count
   if (const char* g = getenv("CMDI_BN_QKV")) e->bn_qkv = atoi(g);
+  if (const char* g = getenv("CMDI_ATTN_SPLIT")) e->attn_trunc_split = strcmp(g, "trunc") == 0;
   if (const char* g = getenv("CMDI_RES")) e->plane_residual = strcmp(g, "planes") == 0;
   if (const char* g = getenv("CMDI_ATTN_BWD")) g_attn_bwd_tc = strcmp(g, "simt") != 0;
   if (const char* g = getenv("CMDI_ATTN")) g_attn_persistent = strcmp(g, "oneshot") != 0;

@@ -97,6 +97,7 @@ struct AttnParams {
   __nv_bfloat16* out_lo;
   int ld_out;
   long long* dbg_cycles;  // bring-up only: [num_ctas][16] cycle counters or null
+  int trunc_split;        // 1: hi plane of P and O by truncation (split_bf16x2_trunc): half the conversions, error 2^-16 instead of 2^-17
 };
 // qkv maps: bf16 [rows, 3*H*128] row-major planes (hi, lo); box {64, 128} for Q, {64, 208} for K and V.
 // o maps: the output planes [rows, H*128] as TMA-store targets, box {64, 32}.
@@ -277,7 +278,7 @@ void set_last_error(const char* fmt, ...);
 
 // Launch helper: with `pdl` the kernel is allowed to overlap its prologue with the tail of the previous kernel in
 // the stream (programmatic dependent launch; every such kernel calls griddep_wait() before touching global memory).
-extern bool g_use_pdl;  // CMDI_PDL=0 turns it off
+extern bool g_use_pdl;  // CMDI_PDL=1 turns programmatic dependent launch on (off by default: slower in graph replay)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                  Args&&... args) {
