@@ -971,7 +971,9 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
   for (int k = 0; k < nsteps; ++k) {
     // utils/editing_util.py:325-333: guidance is active while t >= stop_recguidance_at (t is uniform over the batch)
     const bool guided = a->recon_guidance && (t0 - k) >= a->stop_recguidance_at;
-    if (a->use_graph) {
+    // calls of one or two steps (the *_progressive generators issue one native call per step, each with its own t0)
+    // are launched directly: capturing and instantiating a graph costs more than it saves there
+    if (a->use_graph && nsteps >= 3) {
       cudaGraphExec_t& ex = guided ? exec_guided : exec_plain;
       if (!ex) CKI(get_exec(guided, &ex));
       CK(cudaGraphLaunch(ex, s));
