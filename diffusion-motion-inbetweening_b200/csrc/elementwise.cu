@@ -261,63 +261,87 @@ __global__ void __launch_bounds__(256) diffusion_step_kernel(const StepParams p)
   const float text_scale = p.cfg ? p.text_scale[b] : 0.f;
   const bool do_impute = p.impute && (t >= p.stop_imputation_at);
 
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int l = l0 + ty + i * 8, c = c0 + tx;
-    if (l >= p.L || c >= p.D_pad) continue;
-    const size_t idx = ((size_t)b * p.L + l) * p.D_pad + c;
-    float xn = 0.f, x0 = 0.f;
-    if (c < p.D) {
-      // model output (+ classifier-free guidance: out_uncond + scale * (out - out_uncond), cfg_sampler.py:35)
-      float out = p.model_out[idx];
-      if (p.cfg) {
-        const float u = p.model_out[idx + (size_t)p.B * p.L * p.D_pad];
-        out = __fadd_rn(u, __fmul_rn(text_scale, __fsub_rn(out, u)));
-      }
+  // one thread = 4 consecutive features of one frame (16-byte accesses; D_pad is a multiple of 8)
+  {
+    const int tid = ty * 32 + tx;
+    const int ll = tid >> 3, cq = (tid & 7) * 4;
+    const int l = l0 + ll, c = c0 + cq;
+    if (l < p.L && c < p.D_pad) {
+      const size_t idx = ((size_t)b * p.L + l) * p.D_pad + c;
+      const size_t uoff = (size_t)p.B * p.L * p.D_pad;  // uncond half of the batch-doubled pass
+      const float4 mo4 = *reinterpret_cast<const float4*>(p.model_out + idx);
+      const float4 mu4 = p.cfg ? *reinterpret_cast<const float4*>(p.model_out + idx + uoff) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 xt4 = *reinterpret_cast<const float4*>(p.x_t + idx);
+      const bool need_obs = p.guided || do_impute;
+      const float4 ob4 = need_obs ? *reinterpret_cast<const float4*>(p.x_obs + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const uchar4 mk4 = need_obs ? *reinterpret_cast<const uchar4*>(p.obs_mask + idx) : make_uchar4(0, 0, 0, 0);
+      float4 gg4 = make_float4(0.f, 0.f, 0.f, 0.f), gu4 = gg4;
       if (p.guided) {
-        // reconstruction guidance (:416-425): cond_grad = grad * ~M ; tilde = hat - (w_r sqrt(abar) / 2) cond_grad ;
-        // output = tilde * ~M + (imputing ? x_obs : hat) * M
-        const float m = p.obs_mask[idx] ? 1.0f : 0.0f;
-        float g = p.guide_grad[idx];
-        if (p.cfg) g = __fadd_rn(g, p.guide_grad[idx + (size_t)p.B * p.L * p.D_pad]);
-        g = __fmul_rn(g, 1.0f - m);
-        const float tilde = __fsub_rn(out, __fmul_rn(p.guide_coef[t], g));
-        out = __fadd_rn(__fmul_rn(tilde, 1.0f - m), __fmul_rn(do_impute ? p.x_obs[idx] : out, m));
-      } else if (do_impute) {
-        // imputation: (hat_x * ~M) + (x_obs * M)   (gaussian_diffusion.py:435)
-        const float m = p.obs_mask[idx] ? 1.0f : 0.0f;
-        out = __fadd_rn(__fmul_rn(out, 1.0f - m), __fmul_rn(p.x_obs[idx], m));
+        gg4 = *reinterpret_cast<const float4*>(p.guide_grad + idx);
+        if (p.cfg) gu4 = *reinterpret_cast<const float4*>(p.guide_grad + idx + uoff);
       }
-      x0 = out;  // START_X, no clipping (:513-515)
-      const float xt = p.x_t[idx];
-      const float noise = s_noise[tx][ty + i * 8];
-      if (p.sampler == 2) {
-        xn = 0.f;
-      } else if (p.sampler == 0) {
-        // mean = coef1*x0 + coef2*x_t (:338-342); sample = mean + nonzero*exp(0.5*logvar)*noise (:710-711)
-        const float mean = __fadd_rn(__fmul_rn(coef1, x0), __fmul_rn(coef2, xt));
-        const float sd = expf(__fmul_rn(0.5f, logvar));
-        xn = __fadd_rn(mean, __fmul_rn(__fmul_rn(nonzero, sd), noise));
-      } else {
-        // ddim_sample_with_grad (:1397-1412)
-        const float r1 = p.tab.sqrt_recip_acp[t], r2 = p.tab.sqrt_recipm1_acp[t];
-        const float ab = p.tab.acp[t], abp = p.tab.acp_prev[t];
-        const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(r1, xt), x0), r2);
-        const float sigma = __fmul_rn(__fmul_rn(p.eta, sqrtf(__fdiv_rn(1.0f - abp, 1.0f - ab))),
-                                      sqrtf(__fsub_rn(1.0f, __fdiv_rn(ab, abp))));
-        const float mean_pred = __fadd_rn(__fmul_rn(x0, sqrtf(abp)),
-                                          __fmul_rn(sqrtf(__fsub_rn(__fsub_rn(1.0f, abp), __fmul_rn(sigma, sigma))), eps));
-        xn = __fadd_rn(mean_pred, __fmul_rn(__fmul_rn(nonzero, sigma), noise));
+      const float mo[4] = {mo4.x, mo4.y, mo4.z, mo4.w}, mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w};
+      const float xtv[4] = {xt4.x, xt4.y, xt4.z, xt4.w}, ob[4] = {ob4.x, ob4.y, ob4.z, ob4.w};
+      const unsigned char mk[4] = {mk4.x, mk4.y, mk4.z, mk4.w};
+      const float gg[4] = {gg4.x, gg4.y, gg4.z, gg4.w}, gu[4] = {gu4.x, gu4.y, gu4.z, gu4.w};
+      const float guide_c = p.guided ? p.guide_coef[t] : 0.f;
+      float xn4[4], x04[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float xn = 0.f, x0 = 0.f;
+        if (c + j < p.D) {
+          // model output (+ classifier-free guidance: out_uncond + scale * (out - out_uncond), cfg_sampler.py:35)
+          float out = mo[j];
+          if (p.cfg) out = __fadd_rn(mu[j], __fmul_rn(text_scale, __fsub_rn(out, mu[j])));
+          if (p.guided) {
+            // reconstruction guidance (:416-425): cond_grad = grad * ~M ; tilde = hat - (w_r sqrt(abar) / 2) cond_grad ;
+            // output = tilde * ~M + (imputing ? x_obs : hat) * M
+            const float m = mk[j] ? 1.0f : 0.0f;
+            float g = gg[j];
+            if (p.cfg) g = __fadd_rn(g, gu[j]);
+            g = __fmul_rn(g, 1.0f - m);
+            const float tilde = __fsub_rn(out, __fmul_rn(guide_c, g));
+            out = __fadd_rn(__fmul_rn(tilde, 1.0f - m), __fmul_rn(do_impute ? ob[j] : out, m));
+          } else if (do_impute) {
+            // imputation: (hat_x * ~M) + (x_obs * M)   (gaussian_diffusion.py:435)
+            const float m = mk[j] ? 1.0f : 0.0f;
+            out = __fadd_rn(__fmul_rn(out, 1.0f - m), __fmul_rn(ob[j], m));
+          }
+          x0 = out;  // START_X, no clipping (:513-515)
+          const float xt = xtv[j];
+          const float noise = s_noise[cq + j][ll];
+          if (p.sampler == 2) {
+            xn = 0.f;
+          } else if (p.sampler == 0) {
+            // mean = coef1*x0 + coef2*x_t (:338-342); sample = mean + nonzero*exp(0.5*logvar)*noise (:710-711)
+            const float mean = __fadd_rn(__fmul_rn(coef1, x0), __fmul_rn(coef2, xt));
+            const float sd = expf(__fmul_rn(0.5f, logvar));
+            xn = __fadd_rn(mean, __fmul_rn(__fmul_rn(nonzero, sd), noise));
+          } else {
+            // ddim_sample_with_grad (:1397-1412)
+            const float r1 = p.tab.sqrt_recip_acp[t], r2 = p.tab.sqrt_recipm1_acp[t];
+            const float ab = p.tab.acp[t], abp = p.tab.acp_prev[t];
+            const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(r1, xt), x0), r2);
+            const float sigma = __fmul_rn(__fmul_rn(p.eta, sqrtf(__fdiv_rn(1.0f - abp, 1.0f - ab))),
+                                          sqrtf(__fsub_rn(1.0f, __fdiv_rn(ab, abp))));
+            const float mean_pred = __fadd_rn(__fmul_rn(x0, sqrtf(abp)),
+                                              __fmul_rn(sqrtf(__fsub_rn(__fsub_rn(1.0f, abp), __fmul_rn(sigma, sigma))), eps));
+            xn = __fadd_rn(mean_pred, __fmul_rn(__fmul_rn(nonzero, sigma), noise));
+          }
+        }
+        xn4[j] = xn;
+        x04[j] = x0;
       }
+      if (p.x_next) {
+        *reinterpret_cast<float4*>(p.x_next + idx) = make_float4(xn4[0], xn4[1], xn4[2], xn4[3]);
+        uint32_t h01, l01, h23, l23;
+        split_bf16x2(xn4[0], xn4[1], h01, l01);
+        split_bf16x2(xn4[2], xn4[3], h23, l23);
+        *reinterpret_cast<uint2*>(p.x_next_hi + idx) = make_uint2(h01, h23);
+        if (p.x_next_lo) *reinterpret_cast<uint2*>(p.x_next_lo + idx) = make_uint2(l01, l23);
+      }
+      if (p.pred_xstart) *reinterpret_cast<float4*>(p.pred_xstart + idx) = make_float4(x04[0], x04[1], x04[2], x04[3]);
     }
-    if (p.x_next) {
-      p.x_next[idx] = xn;
-      __nv_bfloat16 h, lo;
-      split_bf16(xn, h, lo);
-      p.x_next_hi[idx] = h;
-      if (p.x_next_lo) p.x_next_lo[idx] = lo;
-    }
-    if (p.pred_xstart) p.pred_xstart[idx] = x0;
   }
 
   // ---- advance the device-side step counter once every block has read it ----

@@ -73,7 +73,7 @@ struct GraphKey {
   int B, cfg, sampler, impute, stop_at, tape_mode, has_cond;
   float eta;
   const void* tape;
-  int t0, uncond, guided;
+  int t0, uncond, guided, group;
   bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
 };
 
@@ -86,6 +86,8 @@ struct cmdi_engine {
   int bn_qkv = kBnWide;
   int debug = 0, bn_wide = kBnWide, bn_narrow = kBnNarrow;  // CMDI_DEBUG / CMDI_BN_WIDE / CMDI_BN_NARROW (bring-up knobs)
   bool fuse_ln = false;   // CMDI_FUSE_LN=1: out-proj+norm1 and linear2+norm2 as one kernel each (correct, but 2-10% slower at B=64: its 3-pass epilogue is exposed with 50 tiles on 74 clusters; kept for larger batches / later tuning)
+  int steps_per_graph = 1;  // CMDI_GRAPH_STEPS: consecutive steps captured into one graph (10 and 50 measured: no gain over 1)
+  bool no_graph = false;    // CMDI_NO_GRAPH=1: plain stream launches even when the caller asks for graph replay
   int attn_trunc_split = 0;  // CMDI_ATTN_SPLIT=trunc
   bool plane_residual = false;  // CMDI_RES=planes: residual stream from the bf16 hi/lo planes, LayerNorm skips its fp32 copy (+1.7 % steps/s, but the CFG-amplified error grows from 4.2e-5 to 7.1e-5 against the 1e-4 gate: off)
   bool tma_store = true;  // CMDI_EPI=stg selects the coalesced-STG epilogue everywhere
@@ -487,6 +489,8 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   if (const char* g = getenv("CMDI_PDL")) g_use_pdl = atoi(g) != 0;
   e->bn_qkv = kBnWide;  // 256 x 192 pair tiles (CMDI_BN_QKV=192) measured no faster than 256 x 256 despite the better round count
   if (const char* g = getenv("CMDI_BN_QKV")) e->bn_qkv = atoi(g);
+  if (const char* g = getenv("CMDI_NO_GRAPH")) e->no_graph = atoi(g) != 0;
+  if (const char* g = getenv("CMDI_GRAPH_STEPS")) e->steps_per_graph = atoi(g) > 0 ? atoi(g) : 1;
   if (const char* g = getenv("CMDI_ATTN_SPLIT")) e->attn_trunc_split = strcmp(g, "trunc") == 0;
   if (const char* g = getenv("CMDI_RES")) e->plane_residual = strcmp(g, "planes") == 0;
   if (const char* g = getenv("CMDI_ATTN_BWD")) g_attn_bwd_tc = strcmp(g, "simt") != 0;
@@ -932,13 +936,13 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
     return 0;
   };
 
-  auto get_exec = [&](bool guided, cudaGraphExec_t* out_exec) -> int {
+  auto get_exec = [&](bool guided, int group, cudaGraphExec_t* out_exec) -> int {
     GraphKey key{};
     memset(&key, 0, sizeof(key));
     key.B = B; key.cfg = a->cfg != 0; key.sampler = a->sampler; key.impute = a->imputate != 0;
     key.stop_at = a->stop_imputation_at; key.tape_mode = tape != nullptr; key.has_cond = has_cond; key.eta = a->eta;
     key.tape = tape; key.t0 = t0; key.uncond = a->uncond != 0;
-    key.guided = guided;
+    key.guided = guided; key.group = group;
     auto it = e->graphs.find(key);
     if (it != e->graphs.end()) {
       *out_exec = it->second;
@@ -949,7 +953,8 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
     CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-    const int erc = enqueue_step(cs, guided);
+    int erc = 0;
+    for (int g = 0; g < group && !erc; ++g) erc = enqueue_step(cs, guided);
     cudaError_t ce = cudaStreamEndCapture(cs, &graph);
     cudaStreamDestroy(cs);
     if (erc) return 1;
@@ -957,31 +962,43 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
     cudaGraphExec_t ex = nullptr;
     CK(cudaGraphInstantiate(&ex, graph, 0));
     cudaGraphDestroy(graph);
-    if (e->graphs.size() > 16) {  // bounded cache
-      for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
-      e->graphs.clear();
-    }
     e->graphs[key] = ex;
     *out_exec = ex;
     return 0;
   };
-  cudaGraphExec_t exec_plain = nullptr, exec_guided = nullptr;
+  if (e->graphs.size() > 16) {  // bounded cache; cleared before this call takes any handle out of it
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+    e->graphs.clear();
+  }
+  // graphs of `group` consecutive steps (one launch replays that many steps: the per-launch cost of a graph is paid
+  // once per group); single-step graphs serve the remainder and the steps whose pred_xstart is dumped
+  const int group = e->steps_per_graph > 1 ? e->steps_per_graph : 1;
+  cudaGraphExec_t exec1[2] = {nullptr, nullptr}, execg[2] = {nullptr, nullptr};  // [guided]
 
   int dump_i = 0;
-  for (int k = 0; k < nsteps; ++k) {
+  auto guided_at = [&](int k) { return a->recon_guidance && (t0 - k) >= a->stop_recguidance_at; };
+  for (int k = 0; k < nsteps;) {
     // utils/editing_util.py:325-333: guidance is active while t >= stop_recguidance_at (t is uniform over the batch)
-    const bool guided = a->recon_guidance && (t0 - k) >= a->stop_recguidance_at;
+    const bool guided = guided_at(k);
+    int run = 1;
     // calls of one or two steps (the *_progressive generators issue one native call per step, each with its own t0)
     // are launched directly: capturing and instantiating a graph costs more than it saves there
-    if (a->use_graph && nsteps >= 3) {
-      cudaGraphExec_t& ex = guided ? exec_guided : exec_plain;
-      if (!ex) CKI(get_exec(guided, &ex));
-      CK(cudaGraphLaunch(ex, s));
+    if (a->use_graph && !e->no_graph && nsteps >= 3) {
+      const bool dump_in_group = a->dump_xstart && dump_i < a->n_dump && a->dump_steps[dump_i] < k + group;
+      if (group > 1 && k + group <= nsteps && !dump_in_group && guided_at(k + group - 1) == guided) {
+        if (!execg[guided]) CKI(get_exec(guided, group, &execg[guided]));
+        CK(cudaGraphLaunch(execg[guided], s));
+        run = group;
+      } else {
+        if (!exec1[guided]) CKI(get_exec(guided, 1, &exec1[guided]));
+        CK(cudaGraphLaunch(exec1[guided], s));
+      }
     } else {
       CKI(enqueue_step(s, guided));
     }
-    e->launches += launches_per_pass(e) + 1 + (guided ? launches_per_backward(e) : 0);
-    if (a->dump_xstart && dump_i < a->n_dump && a->dump_steps[dump_i] == k) {
+    e->launches += (long long)run * (launches_per_pass(e) + 1 + (guided ? launches_per_backward(e) : 0));
+    k += run;
+    if (a->dump_xstart && dump_i < a->n_dump && a->dump_steps[dump_i] == k - 1) {
       if (host) {
         CK(launch_frames_to_ref(e->pred_x0, B, e->D, e->L, e->D_pad, e->ref_b, s));
         CK(cudaMemcpyAsync(a->dump_xstart + (size_t)dump_i * n, e->ref_b, n * 4, cudaMemcpyDeviceToHost, s));
