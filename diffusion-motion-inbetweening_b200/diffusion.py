@@ -383,13 +383,19 @@ _warned_policy = False
 _policy_ok = {}
 
 
-def aten_launch_policy(numel: int, device) -> tuple:
-    """(threads, philox offset increment) of ATen's CUDA `normal_` kernel for `numel` elements on `device`
-    (aten/src/ATen/native/cuda/DistributionTemplates.h: calc_execution_policy, block 256, unroll 4)."""
-    prop = torch.cuda.get_device_properties(device)
-    blocks = min(prop.multi_processor_count * (prop.max_threads_per_multi_processor // 256), (numel + 255) // 256)
+def aten_policy(numel: int, num_sms: int, max_threads_per_sm: int) -> tuple:
+    """(threads, philox offset increment) of ATen's CUDA `normal_` kernel for `numel` elements
+    (aten/src/ATen/native/cuda/DistributionTemplates.h: calc_execution_policy, block 256, unroll 4): the grid is
+    min(SMs * resident blocks per SM, ceil(numel / 256)) blocks, every thread makes ceil(numel / (threads * 4)) calls
+    of curand_normal4 and each call advances the generator offset by 4."""
+    blocks = min(num_sms * (max_threads_per_sm // 256), (numel + 255) // 256)
     threads = 256 * blocks
     return threads, ((numel - 1) // (threads * 4) + 1) * 4
+
+
+def aten_launch_policy(numel: int, device) -> tuple:
+    prop = torch.cuda.get_device_properties(device)
+    return aten_policy(numel, prop.multi_processor_count, prop.max_threads_per_multi_processor)
 
 
 def _cuda_rng_state(device) -> tuple:

@@ -164,3 +164,21 @@ def test_q_sample_matches_oracle_formula():
     tab = O.make_tables("")
     ref = O.extract(tab.sqrt_alphas_cumprod, t, x0.shape) * x0 + O.extract(tab.sqrt_one_minus_alphas_cumprod, t, x0.shape) * nz
     assert torch.equal(d.q_sample(x0, t, nz), ref)
+
+
+def test_aten_launch_policy_arithmetic():
+    """host side of CMDI_RNG_TORCH: ATen's grid / philox-offset bookkeeping for a B200 (148 SMs x 2048 threads)."""
+    from condmdi_b200.diffusion import aten_policy
+    assert aten_policy(64 * 263 * 196, 148, 2048) == (256 * 1184, 12)   # 3 curand_normal4 calls per thread
+    assert aten_policy(4 * 263 * 196, 148, 2048) == (256 * 806, 4)      # fewer blocks than the SMs could hold
+    assert aten_policy(1000, 148, 2048) == (1024, 4)
+    assert aten_policy(256 * 1184 * 4, 148, 2048) == (256 * 1184, 4)
+    assert aten_policy(256 * 1184 * 4 + 1, 148, 2048) == (256 * 1184, 8)
+
+
+def test_post_processing_has_no_cpu_path():
+    import condmdi_b200 as C
+    with pytest.raises(RuntimeError):
+        C.recover_from_ric(torch.zeros(1, 4, 263), 22)
+    with pytest.raises(RuntimeError):
+        C.sample_to_joints(torch.zeros(1, 263, 1, 4), torch.zeros(263), torch.ones(263))
