@@ -8,9 +8,9 @@
 // 256 x 512 tile (cta_group::2, two N = 256 MMAs per k-step into the full 512 TMEM columns), so each CTA holds 128
 // COMPLETE rows and the epilogue can normalise them in place:
 //
-//   pass 1  TMEM -> +bias +residual -> written back to TMEM, row sums            (2 warps per row: 256 columns each)
-//   pass 2  centred sum of squares from TMEM                                    (two-pass variance, fp32)
-//   pass 3  normalise, scale/shift, fp32 + bf16 hi/lo planes -> TMA stores
+//   pass 1  TMEM -> +bias +residual -> written back to TMEM; shifted sum and sum of squares of each thread's 256
+//           columns, the two threads of a row combine (mean, M2) by Chan's formula
+//   pass 2  normalise, scale/shift, fp32 + bf16 hi/lo planes -> TMA stores
 //
 // Protocol identical to gemm2.cu (leader-owned full / tmem_empty barriers, multicast commits), single accumulator.
 #include "common.cuh"
@@ -190,8 +190,9 @@ linear2_ln_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
       mbar_wait(&bars->tmem_full, acc_phase);
       tc_fence_after();
 
-      // ---- pass 1: v = acc + bias + residual -> back into TMEM; row sum ----
-      float sum = 0.f;
+      // ---- pass 1: v = acc + bias + residual -> back into TMEM; shifted sums of this thread's 256 columns
+      //      (shift = the first value, so the single-pass variance does not cancel) ----
+      float s1 = 0.f, s2 = 0.f, shift = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         if (lane == 0) tma_store_wait_read();
@@ -219,38 +220,31 @@ linear2_ln_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
           const float x1 = __uint_as_float(vv[1]) + b1 + __uint_as_float(rr[1]);
           const float x2 = __uint_as_float(vv[2]) + b2 + __uint_as_float(rr[2]);
           const float x3 = __uint_as_float(vv[3]) + b3 + __uint_as_float(rr[3]);
-          sum += (x0 + x1) + (x2 + x3);
+          if (c == 0 && g == 0) shift = x0;
+          const float d0 = x0 - shift, d1 = x1 - shift, d2 = x2 - shift, d3 = x3 - shift;
+          s1 += (d0 + d1) + (d2 + d3);
+          s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
           vv[0] = __float_as_uint(x0); vv[1] = __float_as_uint(x1); vv[2] = __float_as_uint(x2); vv[3] = __float_as_uint(x3);
         }
         tmem_st32(trow + c * 64, v0);
         tmem_st32(trow + c * 64 + 32, v1);
       }
       tmem_st_wait();
-      bars->red[half][row] = sum;
+      // the two threads of a row combine (count, mean, M2) of their halves (Chan et al.): 256 columns each
+      // (one 1 KB exchange array, used twice: the smem budget leaves no room for a second one next to two stages)
+      bars->red[half][row] = shift + s1 * (1.0f / 256.0f);
       tc_fence_before();
       epi_barrier();
       tc_fence_after();
-      const float mean = (bars->red[0][row] + bars->red[1][row]) * (1.0f / kN);
-      epi_barrier();  // red[] is reused below
-
-      // ---- pass 2: centred sum of squares ----
-      float sq = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        uint32_t v[32];
-        tmem_ld32(trow + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float d = __uint_as_float(v[j]) - mean;
-          sq = fmaf(d, d, sq);
-        }
-      }
-      bars->red[half][row] = sq;
+      const float m0 = bars->red[0][row], m1 = bars->red[1][row];
+      const float mean = 0.5f * (m0 + m1);
       epi_barrier();
-      const float rstd = rsqrtf((bars->red[0][row] + bars->red[1][row]) * (1.0f / kN) + p.eps);
+      bars->red[half][row] = s2 - s1 * s1 * (1.0f / 256.0f);
+      epi_barrier();
+      const float m2 = bars->red[0][row] + bars->red[1][row] + (m0 - m1) * (m0 - m1) * 128.0f;
+      const float rstd = rsqrtf(m2 * (1.0f / kN) + p.eps);
 
-      // ---- pass 3: normalise, affine, store fp32 + bf16 planes ----
+      // ---- pass 2: normalise, affine, store fp32 + bf16 planes ----
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v0[32], v1[32];
