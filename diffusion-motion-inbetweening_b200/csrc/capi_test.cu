@@ -78,6 +78,19 @@ extern "C" int cmdi_test_linear(const float* A, const float* W, const float* bia
   LinearParams p{};
   p.M = M; p.N = N; p.K = K; p.nsplit = precision;
   p.bias = bias; p.residual = residual; p.ld_res = N;
+  DevBuf ln_g, ln_b, ln_s;
+  if (residual && N == 512 && getenv("CMDI_TEST_RES_LN")) {
+    // the residual is LayerNorm(`residual`) (gamma = 1.5, beta = -0.25), re-derived in the epilogue from the
+    // statistics the LayerNorm kernel publishes
+    std::vector<float> hg(512, 1.5f), hb(512, -0.25f);
+    CK(ln_g.alloc(512 * 4)); CK(ln_b.alloc(512 * 4)); CK(ln_s.alloc((size_t)M * sizeof(float2)));
+    CK(cudaMemcpyAsync(ln_g.p, hg.data(), 512 * 4, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(ln_b.p, hb.data(), 512 * 4, cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    CK(launch_layernorm512(residual, ln_g.as<float>(), ln_b.as<float>(), 1e-5f, M, nullptr, nullptr, nullptr, stream, ln_s.as<float2>()));
+    p.residual = nullptr; p.ln_src = residual; p.ld_ln = N; p.ln_stats = ln_s.as<float2>();
+    p.ln_gamma = ln_g.as<float>(); p.ln_beta = ln_b.as<float>();
+  }
   DevBuf r_hi, r_lo;
   if (residual && getenv("CMDI_TEST_RES_PLANES")) {
     // the same residual handed over as bf16 hi/lo planes (what the engine does between encoder sublayers)

@@ -50,6 +50,12 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi_word
   lo_word = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// y = (x - mean) * rstd * gamma + beta with a fixed operation order: the LayerNorm kernel and the epilogues that
+// re-derive LayerNorm's output as a residual (from its fp32 input and the row statistics) must agree bit for bit.
+__device__ __forceinline__ float ln_apply(float x, float mean, float rstd, float g, float b) {
+  return __fmaf_rn(__fmul_rn(__fsub_rn(x, mean), rstd), g, b);
+}
+
 // Same split with the hi half taken by truncation (one PRMT instead of a conversion): v = hi + lo still holds to
 // 2^-16 |v| (hi is exact in bf16, lo = RN(v - hi) with |v - hi| < 2^-7 |v|).  Halves the work on the conversion pipe
 // where the values are produced at MUFU rate anyway (softmax probabilities, attention outputs).

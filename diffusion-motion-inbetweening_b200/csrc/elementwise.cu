@@ -32,7 +32,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restrict__ v, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float eps, int rows,
                                                            float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
-                                                           __nv_bfloat16* __restrict__ out_lo) {
+                                                           __nv_bfloat16* __restrict__ out_lo, float2* __restrict__ stats_out) {
   griddep_launch_dependents();
   griddep_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -53,16 +53,17 @@ __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restri
     q += (a * a + b * b) + (c * c + d * d);
   }
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / 512.0f) + eps);
+  if (stats_out && lane == 0) stats_out[row] = make_float2(mean, rstd);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int col = (i * 32 + lane) * 4;
     const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
     const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + col));
     float4 y;
-    y.x = (x[i].x - mean) * rstd * g.x + bb.x;
-    y.y = (x[i].y - mean) * rstd * g.y + bb.y;
-    y.z = (x[i].z - mean) * rstd * g.z + bb.z;
-    y.w = (x[i].w - mean) * rstd * g.w + bb.w;
+    y.x = ln_apply(x[i].x, mean, rstd, g.x, bb.x);
+    y.y = ln_apply(x[i].y, mean, rstd, g.y, bb.y);
+    y.z = ln_apply(x[i].z, mean, rstd, g.z, bb.z);
+    y.w = ln_apply(x[i].w, mean, rstd, g.w, bb.w);
     if (out_f32) reinterpret_cast<float4*>(out_f32 + (size_t)row * 512)[i * 32 + lane] = y;
     if (out_hi) {
       __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
@@ -573,8 +574,9 @@ inline int grid_for(size_t n, int block) {
 }  // namespace
 
 cudaError_t launch_layernorm512(const float* v, const float* gamma, const float* beta, float eps, int rows, float* out_f32,
-                                __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream) {
-  return launch_kernel(layernorm512_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, v, gamma, beta, eps, rows, out_f32, out_hi, out_lo);
+                                __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream, float2* stats_out) {
+  return launch_kernel(layernorm512_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, v, gamma, beta, eps, rows, out_f32, out_hi, out_lo,
+                       stats_out);
 }
 
 cudaError_t launch_small_linear(const float* in, const float* W, const float* bias, float* out, int rows, int N, int K,

@@ -89,6 +89,8 @@ struct cmdi_engine {
   int steps_per_graph = 1;  // CMDI_GRAPH_STEPS: consecutive steps captured into one graph (10 and 50 measured: no gain over 1)
   bool no_graph = false;    // CMDI_NO_GRAPH=1: plain stream launches even when the caller asks for graph replay
   int attn_trunc_split = 0;  // CMDI_ATTN_SPLIT=trunc
+  bool ln_residual = true;   // CMDI_RES=f32: LayerNorm also writes its fp32 output and the next epilogue reads that back
+  float2 *ln_stats1 = nullptr, *ln_stats2 = nullptr;  // (mean, rstd) per token row published by norm1 / norm2
   bool plane_residual = false;  // CMDI_RES=planes: residual stream from the bf16 hi/lo planes, LayerNorm skips its fp32 copy (+1.7 % steps/s, but the CFG-amplified error grows from 4.2e-5 to 7.1e-5 against the 1e-4 gate: off)
   bool tma_store = true;  // CMDI_EPI=stg selects the coalesced-STG epilogue everywhere
   bool use_pair = true;  // CTA-pair (cta_group::2) linear kernels; CMDI_GEMM=single selects the 1-CTA kernels
@@ -248,6 +250,9 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
   // bf16x3, unfused LayerNorm: the residual stream lives in the hi/lo planes only (x = hi + lo to 2^-17) -- LayerNorm
   // and the frame embedding skip their fp32 copy, the next sublayer's epilogue adds the planes back
   const bool plane_res = e->plane_residual && e->nsplit == 3 && !e->fuse_ln;
+  // default: LayerNorm writes only the bf16 planes and its row statistics; the sublayer that needs its fp32 output as
+  // the residual re-derives it in the epilogue from LayerNorm's input (bit-identical, 26 MB less traffic per LayerNorm)
+  const bool ln_res = e->ln_residual && !plane_res && !e->fuse_ln;
   LinearParams p{};
   // frame embedding + positional encoding (mdm.py:271, :279-280)
   p.M = B * e->L; p.N = kDModel; p.K = e->D; p.nsplit = e->nsplit; p.bias = e->b_in; p.pos_enc = e->pe;
@@ -290,11 +295,17 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
       LinearParams o{};
       o.M = M; o.N = kDModel; o.K = kDModel; o.nsplit = e->nsplit; o.bias = w.bo; o.residual = e->xseq; o.ld_res = kDModel;
       if (plane_res) { o.residual = nullptr; o.res_hi = e->xseq_p.hi; o.res_lo = e->xseq_p.lo; o.ld_res_bf = kDModel; }
+      if (ln_res && l > 0) {
+        // residual = norm2 of the previous layer, from its input (in place when that is the shared vsum buffer)
+        o.residual = nullptr; o.ln_src = stash ? (*stash)[l - 1].v2 : e->vsum; o.ld_ln = kDModel; o.ln_stats = e->ln_stats2;
+        o.ln_gamma = e->lw[l - 1].g2; o.ln_beta = e->lw[l - 1].be2;
+      }
       o.out_f32 = v1_out; o.ld_f32 = kDModel; o.nsplit_out = e->nsplit;
       for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->attn_p, w.wo, o, kBnNarrow, s, nullptr, ls ? nullptr : &e->vsum_st));
       CKI(mark());
       for (int r_ = 0; r_ < reps; ++r_)
-        CK(launch_layernorm512(v1_out, w.g1, w.be1, 1e-5f, M, plane_res ? nullptr : e->x1, e->x1_p.hi, e->nsplit == 3 ? e->x1_p.lo : nullptr, s));
+        CK(launch_layernorm512(v1_out, w.g1, w.be1, 1e-5f, M, (plane_res || ln_res) ? nullptr : e->x1, e->x1_p.hi,
+                               e->nsplit == 3 ? e->x1_p.lo : nullptr, s, ln_res ? e->ln_stats1 : nullptr));
       CKI(mark());
     }
     // FFN
@@ -316,11 +327,15 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
       LinearParams f2{};
       f2.M = M; f2.N = kDModel; f2.K = e->ff; f2.nsplit = e->nsplit; f2.bias = w.b2; f2.residual = e->x1; f2.ld_res = kDModel;
       if (plane_res) { f2.residual = nullptr; f2.res_hi = e->x1_p.hi; f2.res_lo = e->x1_p.lo; f2.ld_res_bf = kDModel; }
+      if (ln_res) {
+        f2.residual = nullptr; f2.ln_src = v1_out; f2.ld_ln = kDModel; f2.ln_stats = e->ln_stats1; f2.ln_gamma = w.g1; f2.ln_beta = w.be1;
+      }
       f2.out_f32 = v2_out; f2.ld_f32 = kDModel; f2.nsplit_out = e->nsplit;
       for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->ffh_p, w.w2, f2, kBnNarrow, s, nullptr, ls ? nullptr : &e->vsum_st));
       CKI(mark());
       for (int r_ = 0; r_ < reps; ++r_)
-        CK(launch_layernorm512(v2_out, w.g2, w.be2, 1e-5f, M, plane_res ? nullptr : e->xseq, e->xseq_p.hi, e->nsplit == 3 ? e->xseq_p.lo : nullptr, s));
+        CK(launch_layernorm512(v2_out, w.g2, w.be2, 1e-5f, M, (plane_res || ln_res) ? nullptr : e->xseq, e->xseq_p.hi,
+                               e->nsplit == 3 ? e->xseq_p.lo : nullptr, s, ln_res ? e->ln_stats2 : nullptr));
       CKI(mark());
     }
   }
@@ -492,7 +507,10 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   if (const char* g = getenv("CMDI_NO_GRAPH")) e->no_graph = atoi(g) != 0;
   if (const char* g = getenv("CMDI_GRAPH_STEPS")) e->steps_per_graph = atoi(g) > 0 ? atoi(g) : 1;
   if (const char* g = getenv("CMDI_ATTN_SPLIT")) e->attn_trunc_split = strcmp(g, "trunc") == 0;
-  if (const char* g = getenv("CMDI_RES")) e->plane_residual = strcmp(g, "planes") == 0;
+  if (const char* g = getenv("CMDI_RES")) {
+    e->plane_residual = strcmp(g, "planes") == 0;
+    e->ln_residual = strcmp(g, "ln") == 0;
+  }
   if (const char* g = getenv("CMDI_ATTN_BWD")) g_attn_bwd_tc = strcmp(g, "simt") != 0;
   if (const char* g = getenv("CMDI_ATTN")) g_attn_persistent = strcmp(g, "oneshot") != 0;
   if (const char* g = getenv("CMDI_FUSE_LN")) e->fuse_ln = atoi(g) != 0;
@@ -564,6 +582,8 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   A(dev_alloc(e, &e->text_scale, e->maxB));
   A(dev_alloc(e, &e->step_ctr, 2));
   A(dev_alloc(e, &e->rng, 1));
+  A(dev_alloc(e, &e->ln_stats1, (size_t)e->seq_rows_pad));
+  A(dev_alloc(e, &e->ln_stats2, (size_t)e->seq_rows_pad));
   A(dev_alloc(e, &e->ref_a, (size_t)e->maxB * e->D * e->L));
   A(dev_alloc(e, &e->ref_b, (size_t)e->maxB * e->D * e->L));
   A(dev_alloc(e, &e->ref_mask, (size_t)e->maxB * e->D * e->L));

@@ -176,6 +176,19 @@ __device__ __forceinline__ void epilogue_tile(const LinearParams& p, const EpiSt
     if (p.bias && lane * 4 < part_cols && nb < p.N) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb));
   }
 
+  // residual re-derived from LayerNorm's input: gamma / beta of this warp's columns like the bias, and the
+  // (mean, rstd) of the row this thread owns in the blocks load_block_coalesced hands out (row = warp_row0 + lane)
+  float4 lng4 = make_float4(0.f, 0.f, 0.f, 0.f), lnb4 = lng4;
+  float2 ln_st = make_float2(0.f, 0.f);
+  if (p.ln_src) {
+    const int nb = n_blk * BLOCK_N + col_start + lane * 4;
+    if (lane * 4 < part_cols && nb < p.N) {
+      lng4 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + nb));
+      lnb4 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + nb));
+    }
+    if (warp_row0 + lane < p.M) ln_st = p.ln_stats[warp_row0 + lane];
+  }
+
 #pragma unroll 1
   for (int c64 = 0; c64 < part_cols / 64; ++c64) {
     const int col_in_tile = col_start + c64 * 64;
@@ -231,6 +244,22 @@ __device__ __forceinline__ void epilogue_tile(const LinearParams& p, const EpiSt
                              (long long)p.ld_res * 4, (p.N - n0 - h * 32) / 4);
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[h * 32 + j] += __uint_as_float(r[j]);
+      }
+    }
+    if (p.ln_src) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[32];
+        load_block_coalesced(stage, lane, r, reinterpret_cast<const char*>(p.ln_src + n0 + h * 32), rows,
+                             (long long)p.ld_ln * 4, (p.N - n0 - h * 32) / 4);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int src = c64 * 16 + h * 8 + g;  // lane holding gamma / beta of columns [n0 + h*32 + 4g, +4)
+          f[h * 32 + g * 4 + 0] += ln_apply(__uint_as_float(r[g * 4 + 0]), ln_st.x, ln_st.y, __shfl_sync(0xffffffffu, lng4.x, src), __shfl_sync(0xffffffffu, lnb4.x, src));
+          f[h * 32 + g * 4 + 1] += ln_apply(__uint_as_float(r[g * 4 + 1]), ln_st.x, ln_st.y, __shfl_sync(0xffffffffu, lng4.y, src), __shfl_sync(0xffffffffu, lnb4.y, src));
+          f[h * 32 + g * 4 + 2] += ln_apply(__uint_as_float(r[g * 4 + 2]), ln_st.x, ln_st.y, __shfl_sync(0xffffffffu, lng4.z, src), __shfl_sync(0xffffffffu, lnb4.z, src));
+          f[h * 32 + g * 4 + 3] += ln_apply(__uint_as_float(r[g * 4 + 3]), ln_st.x, ln_st.y, __shfl_sync(0xffffffffu, lng4.w, src), __shfl_sync(0xffffffffu, lnb4.w, src));
+        }
       }
     }
     if (p.res_hi) {

@@ -34,6 +34,14 @@ struct LinearParams {
   const float* bias;      // [N] or null
   const float* residual;  // fp32 [rows, ld_res], indexed by OUTPUT row; or null
   int ld_res;
+  // residual = LayerNorm(ln_src) re-derived in the epilogue from LayerNorm's fp32 INPUT [rows, ld_ln], the per-row
+  // (mean, rstd) it published and its gamma / beta: bit-identical to the fp32 tensor LayerNorm would have written,
+  // which it then does not have to write.  ln_src may alias out_f32 (each block is read before it is stored).
+  const float* ln_src;
+  int ld_ln;
+  const float2* ln_stats;
+  const float* ln_gamma;
+  const float* ln_beta;
   const __nv_bfloat16* res_hi;  // the same residual as bf16 hi/lo planes [rows, ld_res_bf] (x = hi + lo), or null:
   const __nv_bfloat16* res_lo;  // lets LayerNorm skip its fp32 output (the planes are what the next GEMM reads anyway)
   int ld_res_bf;
@@ -112,8 +120,9 @@ extern bool g_attn_persistent;  // persistent (one CTA per SM, prefetching) vs o
 // elementwise / row kernels      (elementwise.cu)
 // ----------------------------------------------------------------------------------------------
 // y = LayerNorm(v) * gamma + beta over rows of 512; writes fp32 and bf16 planes.
+// (stats_out: optional [rows] (mean, rstd) for epilogues that re-derive the output, see LinearParams::ln_src)
 cudaError_t launch_layernorm512(const float* v, const float* gamma, const float* beta, float eps, int rows, float* out_f32,
-                                __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream);
+                                __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream, float2* stats_out = nullptr);
 
 // fp32 CUDA-core linear for the tiny per-loop tables: out[r, n] = act(in[r,:] . W[n,:] + b[n])
 // act: 0 none, 2 SiLU

@@ -74,6 +74,27 @@ def test_linear_residual_from_bf16_planes(monkeypatch, bn):
     assert (out - ref).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize("bn", [-256, -128, 128])
+def test_linear_residual_rederived_from_layernorm_input(monkeypatch, bn):
+    """default residual path between encoder sublayers: LayerNorm publishes (mean, rstd) per row and writes only the
+    bf16 planes; the next epilogue re-derives LayerNorm's fp32 output from its input"""
+    monkeypatch.setenv("CMDI_TEST_RES_LN", "1")
+    M, N, K = 777, 512, 512
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    v = torch.randn(M, N, device="cuda", generator=g) * 2 + 0.3
+    out = torch.full((M, N), float("nan"), device="cuda")
+    C.capi.check(_lib().cmdi_test_linear(_p(A), _p(W), _p(b), _p(v), _p(out), M, N, K, 0, 3, bn, None))
+    torch.cuda.synchronize()
+    ln = torch.nn.functional.layer_norm(v.double(), (N,), torch.full((N,), 1.5, device="cuda", dtype=torch.float64),
+                                        torch.full((N,), -0.25, device="cuda", dtype=torch.float64), 1e-5)
+    ref = A.double() @ W.double().t() + b.double() + ln
+    assert torch.allclose(out.double(), ref, **GATE)
+    assert (out.double() - ref).abs().max() < 1e-4
+
+
 def test_linear_plain_bf16_is_bf16_accurate():
     out, ref = run_linear(512, 512, 512, 1, 128)
     err = (out - ref).abs().max().item()
