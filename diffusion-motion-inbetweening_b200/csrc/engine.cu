@@ -501,7 +501,10 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   if (const char* g = getenv("CMDI_GEMM")) e->use_pair = strcmp(g, "single") != 0;
   if (const char* g = getenv("CMDI_DEBUG")) e->debug = atoi(g);
   if (const char* g = getenv("CMDI_EPI")) e->tma_store = strcmp(g, "stg") != 0;
-  if (const char* g = getenv("CMDI_PDL")) g_use_pdl = atoi(g) != 0;
+  if (const char* g = getenv("CMDI_PDL")) {
+    g_pdl_light = strcmp(g, "ln") == 0;
+    g_use_pdl = !g_pdl_light && atoi(g) != 0;
+  }
   e->bn_qkv = kBnWide;  // 256 x 192 pair tiles (CMDI_BN_QKV=192) measured no faster than 256 x 256 despite the better round count
   if (const char* g = getenv("CMDI_BN_QKV")) e->bn_qkv = atoi(g);
   if (const char* g = getenv("CMDI_NO_GRAPH")) e->no_graph = atoi(g) != 0;

@@ -287,7 +287,24 @@ void set_last_error(const char* fmt, ...);
 
 // Launch helper: with `pdl` the kernel is allowed to overlap its prologue with the tail of the previous kernel in
 // the stream (programmatic dependent launch; every such kernel calls griddep_wait() before touching global memory).
-extern bool g_use_pdl;  // CMDI_PDL=1 turns programmatic dependent launch on (off by default: slower in graph replay)
+extern bool g_use_pdl;     // CMDI_PDL=1 turns programmatic dependent launch on (off by default: slower in graph replay)
+extern bool g_pdl_light;   // CMDI_PDL=ln: only the kernels without shared memory / TMEM (LayerNorm), which can become resident
+                           // next to a running GEMM, are launched as programmatic dependents
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_ex(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                    Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                  Args&&... args) {
