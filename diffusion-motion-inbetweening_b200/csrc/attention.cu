@@ -426,6 +426,15 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap map_q_hi, const 
         mbar_wait(&bars->s_done, ph);      // Q_i and K_i consumed
         if (split) load_v(w, true);
         if (wn < num_items) load_k(wn);
+        if (wn < num_items && p.prefetch_q) {
+          // Q_{i+1} can only land once V_lo_i has left the Q region; pull it into L2 meanwhile
+          int seq, head, qtile;
+          decode(wn, seq, head, qtile);
+          for (int j = 0; j < 2; ++j) {
+            tma_prefetch_2d(&map_q_hi, head * kHeadDim + j * 64, seq * S + qtile * kQTile);
+            if (split) tma_prefetch_2d(&map_q_lo, head * kHeadDim + j * 64, seq * S + qtile * kQTile);
+          }
+        }
         mbar_wait(&bars->o_done, ph);      // V_lo_i and V_hi_i consumed
         if (wn < num_items) load_q(wn);
         mbar_wait(&bars->stage_free, ph);  // the epilogue of item i no longer reads its staging tiles (V_hi region)

@@ -294,6 +294,13 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap qkv_t_hi, const __gr
         }
       }
       load_c(0);
+      // the operands of the later phases can only land once their shared-memory regions drain; pull them into L2 now
+      for (int j = 0; j < 2; ++j) {
+        tma_prefetch_2d(a2_hi, a2_col + j * 64, row0 + tile * kTile);
+        if (split) tma_prefetch_2d(a2_lo, a2_col + j * 64, row0 + tile * kTile);
+      }
+      tma_prefetch_2d(b2_hi, b2_col + 64, row0);
+      if (split) tma_prefetch_2d(b2_lo, b2_col + 64, row0);
       mbar_wait(&bars->x_done, 0);   // the X MMAs no longer read R_A
       mbar_arrive_expect_tx(&bars->a2_full, planes * 2 * kTBlk);
       for (int j = 0; j < 2; ++j) {

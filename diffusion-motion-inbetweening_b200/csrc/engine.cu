@@ -88,6 +88,7 @@ struct cmdi_engine {
   bool fuse_ln = false;   // CMDI_FUSE_LN=1: out-proj+norm1 and linear2+norm2 as one kernel each (correct, but 2-10% slower at B=64: its 3-pass epilogue is exposed with 50 tiles on 74 clusters; kept for larger batches / later tuning)
   int steps_per_graph = 1;  // CMDI_GRAPH_STEPS: consecutive steps captured into one graph (10 and 50 measured: no gain over 1)
   bool no_graph = false;    // CMDI_NO_GRAPH=1: plain stream launches even when the caller asks for graph replay
+  int attn_prefetch_q = 1;   // CMDI_ATTN_PREFETCH=0
   int attn_trunc_split = 0;  // CMDI_ATTN_SPLIT=trunc
   bool ln_residual = true;   // CMDI_RES=f32: LayerNorm also writes its fp32 output and the next epilogue reads that back
   float2 *ln_stats1 = nullptr, *ln_stats2 = nullptr;  // (mean, rstd) per token row published by norm1 / norm2
@@ -278,7 +279,7 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
     // attention core
     AttnParams a{};
     a.num_seqs = nseq; a.seq_len = e->S; a.num_heads = e->H; a.nsplit = e->nsplit; a.nsplit_out = e->nsplit;
-    a.out_hi = e->attn_p.hi; a.out_lo = e->attn_p.lo; a.ld_out = kDModel; a.trunc_split = e->attn_trunc_split;
+    a.out_hi = e->attn_p.hi; a.out_lo = e->attn_p.lo; a.ld_out = kDModel; a.trunc_split = e->attn_trunc_split; a.prefetch_q = e->attn_prefetch_q;
     for (int r_ = 0; r_ < reps; ++r_) CK(launch_attention(ls ? ls->q_hi : e->q_map_hi, ls ? ls->q_lo : e->q_map_lo, ls ? ls->kv_hi : e->kv_map_hi,
                                                          ls ? ls->kv_lo : e->kv_map_lo, e->attn_p.st_hi, e->attn_p.st_lo, a, s));
     CKI(mark());
@@ -509,6 +510,7 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   if (const char* g = getenv("CMDI_BN_QKV")) e->bn_qkv = atoi(g);
   if (const char* g = getenv("CMDI_NO_GRAPH")) e->no_graph = atoi(g) != 0;
   if (const char* g = getenv("CMDI_GRAPH_STEPS")) e->steps_per_graph = atoi(g) > 0 ? atoi(g) : 1;
+  if (const char* g = getenv("CMDI_ATTN_PREFETCH")) e->attn_prefetch_q = atoi(g) != 0;
   if (const char* g = getenv("CMDI_ATTN_SPLIT")) e->attn_trunc_split = strcmp(g, "trunc") == 0;
   if (const char* g = getenv("CMDI_RES")) {
     e->plane_residual = strcmp(g, "planes") == 0;

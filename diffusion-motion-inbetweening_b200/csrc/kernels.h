@@ -105,6 +105,7 @@ struct AttnParams {
   __nv_bfloat16* out_lo;
   int ld_out;
   long long* dbg_cycles;  // bring-up only: [num_ctas][16] cycle counters or null
+  int prefetch_q;         // persistent kernel: L2-prefetch the next item's Q tile while its smem region is still occupied
   int trunc_split;        // 1: hi plane of P and O by truncation (split_bf16x2_trunc): half the conversions, error 2^-16 instead of 2^-17
 };
 // qkv maps: bf16 [rows, 3*H*128] row-major planes (hi, lo); box {64, 128} for Q, {64, 208} for K and V.
