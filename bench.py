@@ -336,6 +336,7 @@ def run_engine(args):
                 "traffic_unit": "bytes of DRAM read + written per launch", "traffic_source": traffic_src,
                 "peak_source": peaks["source"], "launch_ms": dom_ms, "share_of_step": by_kind[dom][0] / step_ms,
                 "mma_terms_per_product": split, "tensor_pipe_frac_incl_split": split * achieved / peaks["bf16_tflops"],
+                "frac_ceiling": 1.0 / split,  # fp32-parity mode spends `split` MMAs per algorithmic product
                 "whole_step_algorithmic_tflops": flops_per_pass(B) * args.steps / (ms * 1e-3) / 1e12,
                 "per_kernel_ms_per_step": {k: round(v[0], 4) for k, v in by_kind.items()},
                 "between_kernels_ms_per_step": round(ms / args.steps - step_ms, 4),
