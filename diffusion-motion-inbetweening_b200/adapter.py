@@ -40,6 +40,8 @@ def install(ref_diffusion, fallback_to_reference: bool = False):
         def make(name=name, original=original):
             def loop(self, *args, **kwargs):
                 try:
+                    # (the *_progressive loops validate their configuration when CALLED and return the step
+                    # generator, so an unsupported configuration surfaces inside this try block too)
                     return getattr(fast, name)(*args, **kwargs)
                 except NotImplementedError:
                     if fallback_to_reference:

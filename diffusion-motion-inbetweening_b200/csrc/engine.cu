@@ -635,8 +635,13 @@ extern "C" int cmdi_load_weights(cmdi_engine* e, const cmdi_tensor_desc* tensors
   }
   CK(cudaSetDevice(e->device));
   cudaStream_t s = 0;
+  // staging for host-resident weight matrices: the largest one of this configuration
   float* scratch = nullptr;
-  CK(cudaMalloc(&scratch, (size_t)3 * kDModel * 1024 * 4));
+  size_t scratch_elems = (size_t)3 * kDModel * kDModel;
+  if ((size_t)e->ff * kDModel > scratch_elems) scratch_elems = (size_t)e->ff * kDModel;
+  if ((size_t)kDModel * e->D_pad > scratch_elems) scratch_elems = (size_t)kDModel * e->D_pad;
+  CK(cudaMalloc(&scratch, scratch_elems * 4));
+  struct ScratchGuard { float* p; ~ScratchGuard() { cudaFree(p); } } scratch_guard{scratch};
   std::map<std::string, const cmdi_tensor_desc*> by_name;
   for (int i = 0; i < n; ++i) by_name[tensors[i].name] = &tensors[i];
   std::string missing;
@@ -691,7 +696,6 @@ extern "C" int cmdi_load_weights(cmdi_engine* e, const cmdi_tensor_desc* tensors
 #undef LOAD_F32
 #undef LOAD_PL
   cudaError_t se = cudaStreamSynchronize(s);
-  cudaFree(scratch);
   if (!missing.empty()) {
     set_last_error("state dict is missing: %s", missing.c_str());
     return 1;
@@ -822,7 +826,7 @@ extern "C" int cmdi_model_forward(cmdi_engine* e, const cmdi_forward_args* a, fl
   if (a->cfg) CK(cudaMemcpyAsync(e->text_scale, a->text_scale, (size_t)B * 4, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
   CK(launch_set_int(e->step_ctr, a->timestep, s));
   const bool has_cond = a->cond_emb != nullptr;
-  const int n_cond = a->cfg ? B : (a->uncond ? 0 : B);
+  const int n_cond = a->uncond ? 0 : B;  // y['uncond'] under the CFG wrapper makes BOTH passes unconditional (cfg_sampler.py:28-33)
   CKI(run_denoiser(e, B, a->cfg != 0, n_cond, has_cond, /*tmap*/ nullptr, s));
   // combine (cfg) into pred_x0 via the step kernel's pass-through mode, then back to the reference layout
   StepParams sp{};
@@ -945,7 +949,7 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
   }
   const bool has_cond = a->cond_emb != nullptr;
   auto enqueue_step = [&](cudaStream_t st, bool guided) -> int {
-    CKI(run_denoiser(e, B, a->cfg != 0, (a->uncond && !a->cfg) ? 0 : B, has_cond, e->d_tmap, st, nullptr, 1,
+    CKI(run_denoiser(e, B, a->cfg != 0, a->uncond ? 0 : B, has_cond, e->d_tmap, st, nullptr, 1,
                      guided ? &e->stash : nullptr));
     if (guided) CKI(run_backward(e, B, a->cfg != 0, st));
     StepParams sp{};

@@ -122,6 +122,7 @@ class GaussianDiffusion:
         # reference loop would advance it); "engine" = the engine's own counter-based generator keyed by the global
         # sample index (sharding-independent; used by distributed.sharded_sample)
         self.rng = "torch"
+        self.engine_seed = None  # rng="engine": explicit Philox key (sharded_sample broadcasts rank 0's); None = draw one
 
     # ------------------------------------------------------------------------------------------
     def q_sample(self, x_start, t, noise=None):
@@ -181,10 +182,13 @@ class GaussianDiffusion:
             text_scale = y["text_scale"].to(device=device, dtype=torch.float32).reshape(-1)
         # ---- keyframe imputation (gaussian_diffusion.py:427-442, editing_util.py:336-346) ----
         imputate, stop_at, obs, mask, y_mask = False, 0, None, None, None
+        guided_cfg = bool(y.get("reconstruction_guidance", False))
         if "imputate" in y.keys() and y["imputate"]:
             assert "stop_imputation_at" in y.keys()
             assert "inpainting_mask" in y.keys() and "inpainted_motion" in y.keys()
-            dist = y["replacement_distribution"]
+            # the reconstruction-guidance branch (:405-425) imputes whenever requires_imputation() holds and never reads
+            # replacement_distribution; only the un-guided branch (:427-442) dispatches on it
+            dist = "conditional" if guided_cfg else y["replacement_distribution"]
             if dist == "conditional":
                 imputate, stop_at = True, int(y["stop_imputation_at"])
                 obs = y["inpainted_motion"].to(device=device, dtype=torch.float32)
@@ -213,10 +217,15 @@ class GaussianDiffusion:
             coef = (w_r * sab / 2).float().cpu().numpy()
         # ---- noise ----
         tape = self.noise_tape  # tape[0]: the initial randn(*shape) draw; tape[1 + k]: the k-th randn_like draw
+        engine_rng = tape is None and self.rng != "torch"
         if noise is not None:
             x_T = noise.to(device=device, dtype=torch.float32)
         elif tape is not None:
             x_T = tape[0]
+        elif engine_rng:
+            # the engine draws x_T itself, keyed by (seed, sample_offset + b): rank r of a sharded run starts its
+            # sample i from the x_T a single-GPU run gives global sample r*B/G + i (distributed.sharded_sample)
+            x_T = None
         else:
             x_T = torch.randn(*shape, device=device)  # the reference's first draw (:1248)
         if tape is not None:
@@ -224,15 +233,19 @@ class GaussianDiffusion:
         seed, rng_args = 0, {}
         if tape is None:
             n_draws = self.num_timesteps - skip_timesteps  # one randn_like per loop iteration (:696, :1407)
-            rng_args = _torch_stream_args(device, int(np.prod(shape)), n_draws) if self.rng == "torch" else None
+            rng_args = _torch_stream_args(device, int(np.prod(shape)), n_draws, lazy=progressive) if self.rng == "torch" else None
             if rng_args is None:
-                # per-step noise comes from the engine's counter-based generator, keyed by a draw from torch's
-                # global generator so `fixseed` still makes runs reproducible
-                seed, rng_args = int(torch.randint(0, 2 ** 62, (1,)).item()), {}
+                if x_T is not None and noise is None:
+                    x_T = None  # torch-compatible stream unavailable in this build: fall through to the engine generator
+                # per-step noise comes from the engine's counter-based generator, keyed by `engine_seed` (set by
+                # sharded_sample: identical on all ranks) or by a draw from torch's global CPU generator, so `fixseed`
+                # still makes runs reproducible
+                seed = self.engine_seed if self.engine_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+                rng_args = {}
             else:
                 seed = rng_args.pop("seed")
         if skip_timesteps and init_image is None:
-            init_image = torch.zeros_like(x_T)
+            init_image = torch.zeros(tuple(shape), device=device, dtype=torch.float32)
         if init_image is not None:
             init_image = init_image.to(device=device, dtype=torch.float32)
         common = dict(batch=B, sampler=sampler, eta=eta, cond_emb=cond_emb, uncond=uncond, cfg=is_cfg, text_scale=text_scale,
@@ -257,6 +270,10 @@ class GaussianDiffusion:
             res = eng.sample(skip_timesteps=skip_timesteps + k, num_steps=1, resume=(k > 0), init_image=init_image if k == 0 else None,
                              x_T=state, noise_tape=None if tape is None else tape[k:], want_pred_xstart=True, **common)
             state = res["sample"]
+            if common.get("rng_mode", capi.RNG_ENGINE) == capi.RNG_TORCH:
+                # torch's generator moves one randn_like at a time, as the reference's loop moves it: a caller that
+                # breaks out of the generator early leaves it where the reference would
+                _advance_torch_generator(eng.device, inc)
             yield {"sample": res["sample"], "pred_xstart": res["pred_xstart"]}
 
     # ------------------------------------------------------------------------------------------
@@ -273,8 +290,9 @@ class GaussianDiffusion:
     def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                                   model_kwargs=None, device=None, progress=False, skip_timesteps=0, init_image=None,
                                   randomize_class=False, cond_fn_with_grad=False, const_noise=False):
-        """gaussian_diffusion.py:1217-1297."""
-        yield from self._run(capi.SAMPLER_DDPM, model, shape, noise, cond_fn, model_kwargs, device, skip_timesteps,
+        """gaussian_diffusion.py:1217-1297.  Returns the step generator; the configuration is validated at the call (the
+        reference, a generator function, defers the same checks to the first next())."""
+        return self._run(capi.SAMPLER_DDPM, model, shape, noise, cond_fn, model_kwargs, device, skip_timesteps,
                              init_image, randomize_class, None, const_noise, 0.0, progressive=True)
 
     def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
@@ -293,7 +311,7 @@ class GaussianDiffusion:
                                      model_kwargs=None, device=None, progress=False, eta=0.0, skip_timesteps=0,
                                      init_image=None, randomize_class=False, cond_fn_with_grad=False):
         """gaussian_diffusion.py:1514-1587."""
-        yield from self._run(capi.SAMPLER_DDIM, model, shape, noise, cond_fn, model_kwargs, device, skip_timesteps,
+        return self._run(capi.SAMPLER_DDIM, model, shape, noise, cond_fn, model_kwargs, device, skip_timesteps,
                              init_image, randomize_class, None, False, eta, progressive=True)
 
 
@@ -406,7 +424,13 @@ def _cuda_rng_state(device) -> tuple:
     return int.from_bytes(raw[:8], "little"), int.from_bytes(raw[8:], "little")
 
 
-def _torch_stream_args(device, numel: int, n_draws: int):
+def _advance_torch_generator(device, n_offsets: int) -> None:
+    seed, off = _cuda_rng_state(device)
+    new_state = torch.tensor(list(seed.to_bytes(8, "little") + (off + n_offsets).to_bytes(8, "little")), dtype=torch.uint8)
+    torch.cuda.set_rng_state(new_state, device)
+
+
+def _torch_stream_args(device, numel: int, n_draws: int, lazy: bool = False):
     """Engine arguments that continue torch's CUDA generator stream for `n_draws` randn_like draws of `numel`
     elements, and advance torch's generator past them.  None (with one warning) if this torch build's launch policy
     is not the one `aten_launch_policy` models -- verified by drawing one element block and watching the offset."""
@@ -428,8 +452,8 @@ def _torch_stream_args(device, numel: int, n_draws: int):
             warnings.warn("torch-compatible noise stream unavailable for this torch build; using the engine generator")
             _warned_policy = True
         return None
-    new_state = torch.tensor(list(seed.to_bytes(8, "little") + (off + n_draws * inc).to_bytes(8, "little")), dtype=torch.uint8)
-    torch.cuda.set_rng_state(new_state, device)
+    if not lazy:  # the fused loop consumes all its draws inside one native call; the generators advance per yielded step
+        _advance_torch_generator(device, n_draws * inc)
     return dict(seed=seed, rng_mode=capi.RNG_TORCH, aten_offset=off, aten_increment=inc, aten_threads=threads)
 
 

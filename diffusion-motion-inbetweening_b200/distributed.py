@@ -47,8 +47,19 @@ def sharded_sample(diffusion, model, shape, model_kwargs: Optional[dict] = None,
     prev_offset = getattr(diffusion, "sample_offset", 0)
     prev_tape = getattr(diffusion, "noise_tape", None)
     prev_rng = getattr(diffusion, "rng", "engine")
+    prev_seed = getattr(diffusion, "engine_seed", None)
     diffusion.sample_offset = lo
     diffusion.rng = "engine"  # keyed by global sample index: the result does not depend on the number of ranks
+    if prev_seed is None:
+        # one Philox key for the whole job: rank 0 draws it from torch's global CPU generator (so `fixseed` still
+        # decides it) and every rank uses that one; x_T and the per-step noise of global sample g are then functions
+        # of (key, g) only
+        key = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64)
+        if world > 1:
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            key = key.to(dev)
+            dist.broadcast(key, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        diffusion.engine_seed = int(key.item())
     if prev_tape is not None:
         diffusion.noise_tape = prev_tape[:, lo:hi].contiguous()
     try:
@@ -57,6 +68,7 @@ def sharded_sample(diffusion, model, shape, model_kwargs: Optional[dict] = None,
     finally:
         diffusion.sample_offset = prev_offset
         diffusion.rng = prev_rng
+        diffusion.engine_seed = prev_seed
         diffusion.noise_tape = prev_tape
     if world == 1 or not gather:
         return local

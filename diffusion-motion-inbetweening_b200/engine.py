@@ -148,7 +148,12 @@ class Engine:
         pred = torch.empty(shape, dtype=torch.float32, device=dev, pin_memory=host_buffers) if want_pred_xstart else None
         dump, dump_arr, n_dump = None, None, 0
         if dump_steps is not None:
-            steps_sorted = sorted(int(s) for s in dump_steps)
+            # one entry per loop iteration that matches, like the reference's `if i in dump_steps` (:1208-1213):
+            # duplicates collapse and iterations the loop never reaches are dropped
+            n_iter = self.num_timesteps - int(skip_timesteps)
+            if num_steps:
+                n_iter = min(n_iter, int(num_steps))
+            steps_sorted = sorted({int(s) for s in dump_steps if 0 <= int(s) < n_iter})
             n_dump = len(steps_sorted)
             dump_arr = (ctypes.c_int32 * max(n_dump, 1))(*steps_sorted)
             dump = torch.empty((max(n_dump, 1),) + shape, dtype=torch.float32, device=dev, pin_memory=host_buffers)

@@ -242,16 +242,100 @@ def golden_long_loop():
                         tape_checksum=np.array([float(tape.double().sum()), float(tape[500].double().abs().sum())]))
 
 
+def golden_chains():
+    """Long chains at the regimes the short fixtures do not reach: a whole DDIM-100 loop (configs[4]),
+    and the LAST 50 steps (t = 49 .. 0, where sqrt(alpha_bar_t) ~ 1 and the guidance coefficient is at its largest) of
+    configs[2] (CFG 2.5 + keyframe imputation) and configs[3] (CFG + imputation + reconstruction guidance w = 20)."""
+    ref = RH.import_reference()
+    out = {}
+    gi = O.golden_inputs()
+    x, cond, x_obs, tape, scale, lengths, y_mask, kf_mask = (gi[k] for k in (
+        "x", "cond", "x_obs", "tape", "text_scale", "lengths", "y_mask", "kf_mask"))
+    sd = O.random_state_dict(seed=7, text=False)
+    m = ref_model_with(sd, text=False)
+    sdt = O.random_state_dict(seed=7, text=True)
+    mt = ref_model_with(sdt, text=True)
+    mt._synthetic_text_emb = cond
+    cfgm = ref.cfg_sampler.ClassifierFreeSampleModel(mt)
+
+    print("ddim_sample_loop ddim100, all 100 steps, tape cycled")
+    d100 = RH.build_reference_diffusion("ddim100")
+    tape100 = tape[torch.arange(101) % 8]
+    with RH.noise_tape(tape100):
+        r = d100.ddim_sample_loop(m, (B, D, 1, L), model_kwargs={"y": {}}, device="cpu", clip_denoised=False)
+    o = O.sample_loop(sd, O.make_tables("ddim100"), (B, D, 1, L), O.Conditioning(), tape100, "ddim")
+    close(r, o, 2e-4, "ddim100 final sample")
+    out["ddim100.sample"] = r.numpy()
+
+    diff = RH.build_reference_diffusion("")
+    tab = O.make_tables("")
+    tape51 = tape[torch.arange(51) % 8]
+    ykw = {"text": ["a", "b"], "text_scale": scale, "mask": y_mask, "lengths": lengths, "imputate": 1,
+           "stop_imputation_at": 1, "replacement_distribution": "conditional", "inpainted_motion": x_obs,
+           "inpainting_mask": kf_mask}
+    print("p_sample_loop, CFG + imputation, last 50 steps (t = 49..0)")
+    with RH.noise_tape(tape51):
+        r3 = diff.p_sample_loop(cfgm, (B, D, 1, L), model_kwargs={"y": ykw}, device="cpu", clip_denoised=False,
+                                skip_timesteps=950, init_image=x_obs)
+    c = O.Conditioning(cond_emb=cond, cfg=True, text_scale=scale, y_mask=y_mask, imputate=True, stop_imputation_at=1,
+                       inpainted_motion=x_obs, inpainting_mask=kf_mask)
+    o3 = O.sample_loop(sdt, tab, (B, D, 1, L), c, tape51, "ddpm", skip_timesteps=950, init_image=x_obs)
+    close(r3, o3, 2e-4, "cfg + imputation, 50-step tail")
+    out["cfg_impute50.sample"] = r3.numpy()
+
+    print("p_sample_loop, CFG + imputation + reconstruction guidance (w=20), last 50 steps (t = 49..0)")
+    ykw2 = dict(ykw)
+    ykw2.update(reconstruction_guidance=True, reconstruction_weight=20.0, gradient_schedule=None, diffusion_steps=1000,
+                stop_recguidance_at=0)
+    r4 = []
+    with RH.noise_tape(tape51):
+        for o_ in diff.p_sample_loop_progressive(cfgm, (B, D, 1, L), model_kwargs={"y": ykw2}, device="cpu",
+                                                 clip_denoised=False, skip_timesteps=950, init_image=x_obs):
+            r4.append(o_["sample"].clone())
+    assert len(r4) == 50
+
+    def guided_oracle(dtype):
+        sd_ = {k: v.to(dtype) for k, v in sdt.items()}
+        c2 = O.Conditioning(cond_emb=cond.to(dtype), cfg=True, text_scale=scale.to(dtype), y_mask=y_mask, imputate=True,
+                            stop_imputation_at=1, inpainted_motion=x_obs.to(dtype), inpainting_mask=kf_mask,
+                            reconstruction_guidance=True, reconstruction_weight=20.0)
+        return O.sample_loop(sd_, tab, (B, D, 1, L), c2, tape51.to(dtype), "ddpm", skip_timesteps=950,
+                             init_image=x_obs.to(dtype), return_all=True)
+
+    o4 = guided_oracle(torch.float32)
+    o4d = guided_oracle(torch.float64)   # the same restatement evaluated in float64: the chain's ground truth
+    # Down to t = 10 the guided chain is contracting and fp32 implementations agree to ~1e-6.  Below t ~ 8 the map
+    # x_t -> x0_tilde = x0_hat - 10 * grad is EXPANDING (coef1 -> 1, sqrt(alpha_bar) -> 1): rounding differences grow by
+    # ~2.5x per step, and two fp32 evaluations of the same formulas (the reference and this restatement) end 2e-3 apart,
+    # each ~3e-3 from the float64 chain.  No implementation can hold rtol 1e-3 / atol 1e-4 on the END of this chain, the
+    # reference against itself included; the fixtures therefore pin (a) the state after t = 10 at the gate, (b) single
+    # steps restarted from the reference's own states inside the expanding regime at the gate, and (c) the end state
+    # relative to the float64 chain, next to the reference's own distance from it.
+    close(r4[39], o4[39]["sample"], 5e-5, "cfg + imputation + guidance, after t = 10 (40 steps)")
+    for k in (39, 44, 47, 49):
+        e_ref = (r4[k].double() - o4d[k]["sample"]).abs().max().item()
+        e_orc = (o4[k]["sample"].double() - o4d[k]["sample"]).abs().max().item()
+        print(f"  after step k={k} (t={49 - k}): |ref32 - f64| = {e_ref:.3e}   |oracle32 - f64| = {e_orc:.3e}")
+    gap = (r4[49] - r3).abs().max().item()
+    print(f"  guided vs unguided final samples differ by max {gap:.3e}")
+    assert gap > 1e-2  # the guided chain must differ visibly from the unguided one, or it would not exercise guidance
+    for k in (39, 44, 45, 47, 48, 49):
+        out[f"recon50.sample_k{k}"] = r4[k].numpy()
+    out["recon50.f64_final"] = o4d[49]["sample"].numpy()
+    out["recon50.ref_err_vs_f64"] = np.array([(r4[49].double() - o4d[49]["sample"]).abs().max().item(),
+                                              (r4[49].double() - o4d[49]["sample"]).abs().mean().item()])
+    np.savez_compressed(os.path.join(GOLDEN, "chains.npz"), **out)
+
+
 def main():
     if not RH.available():
         raise SystemExit("the reference tree is required to (re)generate golden vectors")
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
-    golden_schedules()
-    golden_masks()
-    golden_model_and_sampler()
-    golden_postprocess()
-    golden_long_loop()
+    parts = {"schedules": golden_schedules, "masks": golden_masks, "sampler": golden_model_and_sampler,
+             "postprocess": golden_postprocess, "long_loop": golden_long_loop, "chains": golden_chains}
+    for name in (sys.argv[1:] or list(parts)):  # `python -m oracle.make_golden chains` regenerates one fixture file
+        parts[name]()
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)) // 1024, "KiB")
 

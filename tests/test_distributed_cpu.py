@@ -18,6 +18,7 @@ class StandInDiffusion:
 
     def p_sample_loop(self, model, shape, noise=None, model_kwargs=None, **kw):
         B = shape[0]
+        self.seen_seed = getattr(self, "engine_seed", None)
         y = model_kwargs["y"]
         assert len(y["text"]) == B and y["text_scale"].shape[0] == B and y["mask"].shape[0] == B
         assert y["imputate"] == 1  # non-batched entries pass through
@@ -53,6 +54,13 @@ def _worker(rank, world, port, B):
         assert out.shape == (B,) + shape
         assert torch.allclose(out, _expected(B, shape, text, scale, noise, tape), atol=1e-5)
         assert d.sample_offset == 0 and d.noise_tape is tape  # restored
+        # every rank ran with the SAME engine noise key (rank 0's draw), although the ranks' own generators differ
+        torch.manual_seed(100 + rank)
+        sharded_sample(d, None, (B,) + shape, model_kwargs=kw, noise=noise)
+        seeds = [None] * world
+        dist.all_gather_object(seeds, d.seen_seed)
+        assert seeds[0] is not None and all(s_ == seeds[0] for s_ in seeds), seeds
+        assert getattr(d, "engine_seed", None) is None  # restored
         with pytest.raises(ValueError):
             sharded_sample(d, None, (B + 1,) + shape, model_kwargs=kw)
     finally:

@@ -140,3 +140,39 @@ def test_full_length_loop_fixture_last_steps(golden_dir):
         for t in range(4, -1, -1):
             x = O.p_sample(sd, tab, x, torch.full((2,), t), c, tape[1 + 999 - t])["sample"]
     assert torch.allclose(x, torch.from_numpy(g["sample"]), rtol=1e-5, atol=2e-5)
+
+
+def test_stock_torch_standin_equals_oracle_on_cpu():
+    """tests/standin.py (stock nn.TransformerEncoder under the reference's keys; used by the GPU drop-in test where
+    /root/reference is absent) computes what the oracle computes from the same state dict."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from standin import ClassifierFreeSampleModel as StockCFG
+    from standin import StockMDM
+    torch.manual_seed(11)
+    stock = StockMDM(text=True, layers=2).eval()
+    gi = O.golden_inputs()
+    stock.text_emb = gi["cond"]
+    sd = {k: v.detach() for k, v in stock.state_dict().items()}
+    assert set(sd.keys()) == set(O.random_state_dict(seed=0, text=True, layers=2).keys())
+    t = torch.tensor([300, 300])
+    with torch.no_grad():
+        got = StockCFG(stock)(gi["x"], t, y={"text": ["a", "b"], "text_scale": gi["text_scale"]})
+    want = O.cfg_forward(sd, gi["x"], t, gi["cond"], gi["text_scale"])
+    assert torch.allclose(got, want, rtol=1e-4, atol=2e-5), (got - want).abs().max()
+
+
+def test_oracle_long_chains_vs_reference_golden(golden_dir):
+    """tests/golden/chains.npz (reference outputs): whole DDIM-100 loop and the t = 49..0 tail of CFG + imputation."""
+    g = np.load(os.path.join(golden_dir, "chains.npz"))
+    gi = O.golden_inputs()
+    tape = gi["tape"]
+    sd = O.random_state_dict(seed=7, text=False)
+    got = O.sample_loop(sd, O.make_tables("ddim100"), (B, D, 1, L), O.Conditioning(), tape[torch.arange(101) % 8], "ddim")
+    assert torch.allclose(got, torch.from_numpy(g["ddim100.sample"]), rtol=1e-4, atol=2e-5)
+    sdt = O.random_state_dict(seed=7, text=True)
+    c = O.Conditioning(cond_emb=gi["cond"], cfg=True, text_scale=gi["text_scale"], y_mask=gi["y_mask"], imputate=True,
+                       stop_imputation_at=1, inpainted_motion=gi["x_obs"], inpainting_mask=gi["kf_mask"])
+    got = O.sample_loop(sdt, O.make_tables(""), (B, D, 1, L), c, tape[torch.arange(51) % 8], "ddpm", skip_timesteps=950,
+                        init_image=gi["x_obs"])
+    assert torch.allclose(got, torch.from_numpy(g["cfg_impute50.sample"]), rtol=1e-4, atol=5e-5)
