@@ -448,6 +448,33 @@ __global__ void set_int_kernel(int* p, int v) {
   p[1] = 0;  // block-arrival counter used by diffusion_step_kernel
 }
 
+// LayerNorm folded into the linear layer that consumes it: Wf[n,k] = W[n,k] * gamma[k] (fp32, split into planes by
+// the caller), c[n] = sum_k Wf[n,k], d[n] = sum_k W[n,k] * beta[k] + bias[n].  One warp per output row, fp64 sums.
+__global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ W, int N, int K, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const float* __restrict__ bias,
+                                                      float* __restrict__ Wf, float* __restrict__ c, float* __restrict__ d) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  double cs = 0.0, ds = 0.0;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[(size_t)n * K + k];
+    const float wf = w * gamma[k];
+    Wf[(size_t)n * K + k] = wf;
+    cs += (double)wf;
+    ds += (double)w * (double)beta[k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cs += __shfl_xor_sync(0xffffffffu, cs, o);
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+  }
+  if (lane == 0) {
+    c[n] = (float)cs;
+    d[n] = (float)(ds + (bias ? (double)bias[n] : 0.0));
+  }
+}
+
 __global__ void split_planes_kernel(const float* __restrict__ in, int rows, int cols, int ld_in, __nv_bfloat16* __restrict__ hi,
                                     __nv_bfloat16* __restrict__ lo, int ld_out) {
   const size_t total = (size_t)rows * ld_out;
@@ -650,6 +677,12 @@ cudaError_t launch_recover_from_ric(const float* data, long long sb, long long s
 
 cudaError_t launch_set_int(int* p, int v, cudaStream_t stream) {
   set_int_kernel<<<1, 1, 0, stream>>>(p, v);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fold_ln(const float* W, int N, int K, const float* gamma, const float* beta, const float* bias, float* Wf,
+                           float* c, float* d, cudaStream_t stream) {
+  fold_ln_kernel<<<(N + 7) / 8, 256, 0, stream>>>(W, N, K, gamma, beta, bias, Wf, c, d);
   return cudaGetLastError();
 }
 

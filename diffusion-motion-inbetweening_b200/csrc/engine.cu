@@ -12,6 +12,7 @@
 // every step of a loop with no host work in between (reference: one Python iteration + ~150 PyTorch ops
 // + several H2D table copies per step, gaussian_diffusion.py:1270-1297, :2225, respace.py:129).
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -51,6 +52,7 @@ struct Planes {  // a bf16 hi/lo operand: [rows, ld] row-major, with TMA maps fo
   CUtensorMap map_hi{}, map_lo{};
   CUtensorMap pair_hi{}, pair_lo{};  // same planes, box height halved: W operand of the CTA-pair kernel
   CUtensorMap st_hi{}, st_lo{};      // same planes as a TMA-store target: box {64, 32}
+  CUtensorMap st32_hi{}, st32_lo{};  // ... box {32, 32}, 64-byte swizzle (32-column slices of the chained epilogue)
   CUtensorMap ln_hi{}, ln_lo{};      // W operand of the fused linear+LayerNorm kernel: box {64, 128}
 };
 
@@ -67,6 +69,17 @@ struct LayerStash {  // forward values the backward pass of one layer needs
   Planes qkv;
   CUtensorMap q_hi{}, q_lo{}, kv_hi{}, kv_lo{};
   float *v1 = nullptr, *v2 = nullptr, *pre = nullptr;
+};
+
+struct FoldedW {  // a linear layer with the LayerNorm in front of it folded in (LinearParams::fold_stats)
+  Planes w;            // W * gamma
+  float* c = nullptr;  // [N] sum_k W[n,k] gamma[k]
+  float* d = nullptr;  // [N] sum_k W[n,k] beta[k] + b[n]
+};
+struct ChainTables {  // per number of sequences: the phase lists of the chained launches, one list per encoder layer
+  ChainPhaseDesc* dev = nullptr;  // [layers][kMaxChainPhases]
+  std::vector<int> total_tiles;   // per layer
+  int num_phases = 4;
 };
 
 struct GraphKey {
@@ -139,6 +152,19 @@ struct cmdi_engine {
   Planes seed_p;               // dL/d(model output rows), frame-major [2*frame_rows_pad, D_pad]
   float* guide_grad = nullptr; // dL/dz per pass, frame-major [2*frame_rows_pad, D_pad]
   float* guide_coef = nullptr; // [T] w_r[t] * sqrt(alpha_bar_t) / 2
+  // forward path with LayerNorm folded into the consuming linear layers and the linear layers of a layer chained into one
+  // persistent launch (gemm_chain.cu).  CMDI_CHAIN=0 selects the round-1 path (one launch per layer + LayerNorm kernels),
+  // which guided steps (they stash LayerNorm inputs for the backward pass) always use.
+  bool use_chain = true;
+  int chain_publish_now = 1;  // CMDI_CHAIN_PUBLISH=deferred: counter bumps deferred to the warp's next tile
+  std::vector<FoldedW> f_qkv, f_w1;
+  FoldedW f_out;
+  std::vector<CUtensorMap> wo_chain, w2_chain;  // [layer][hi, lo]: wo / w2 planes with the chain's W box
+  float2 *stats1 = nullptr, *stats2 = nullptr;  // [seq_rows_pad][16] partial row statistics of v1 / v2 (32-column slices)
+  int* chain_ctr = nullptr;                     // [layers][3][max_m_pairs] dependency counters, zeroed every pass
+  int max_m_pairs = 0;
+  long long* chain_dbg = nullptr;               // CMDI_CHAIN_DBG=1: cycle counters of layer 1's chain during cmdi_profile_pass
+  std::map<int, ChainTables> chain_tables;
   std::map<GraphKey, cudaGraphExec_t> graphs;
   int64_t launches = 0;
 };
@@ -166,6 +192,8 @@ int alloc_planes(cmdi_engine* e, Planes* pl, int rows, int cols, int ld, int box
   CKI(make_tmap_bf16_2d(&pl->pair_lo, pl->lo, rows, cols, ld, 64, box_rows / 2));
   CKI(make_tmap_bf16_2d(&pl->st_hi, pl->hi, rows, cols, ld, 64, 32));
   CKI(make_tmap_bf16_2d(&pl->st_lo, pl->lo, rows, cols, ld, 64, 32));
+  CKI(make_tmap_bf16_2d(&pl->st32_hi, pl->hi, rows, cols, ld, 32, 32));
+  CKI(make_tmap_bf16_2d(&pl->st32_lo, pl->lo, rows, cols, ld, 32, 32));
   CKI(make_tmap_bf16_2d(&pl->ln_hi, pl->hi, rows, cols, ld, 64, 128));
   CKI(make_tmap_bf16_2d(&pl->ln_lo, pl->lo, rows, cols, ld, 64, 128));
   return 0;
@@ -225,10 +253,16 @@ int run_linear(cmdi_engine* e, const Planes& a, const Planes& w, const LinearPar
   return 0;
 }
 
+bool chain_eligible(const cmdi_engine* e);
+int prepare_chain(cmdi_engine* e, int nseq);
+int run_denoiser_chain(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond, const int* tmap_dev, cudaStream_t s,
+                       std::vector<cudaEvent_t>* evs, int reps);
+
 // One denoiser pass over `nseq` sequences whose frame features are in x_state planes (first B sequences;
 // with dup the frame embedding is written for sequences [0,B) and [B,2B)).
 int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond, const int* tmap_dev, cudaStream_t s,
                  std::vector<cudaEvent_t>* evs = nullptr, int reps = 1, std::vector<LayerStash>* stash = nullptr) {
+  if (!stash && chain_eligible(e)) return run_denoiser_chain(e, B, dup, n_cond_seqs, has_cond, tmap_dev, s, evs, reps);
   auto mark = [&]() -> int {
     if (!evs) return 0;
     cudaEvent_t ev;
@@ -348,6 +382,163 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
   CKI(mark());
   return 0;
 }
+bool chain_eligible(const cmdi_engine* e) {
+  return e->use_chain && e->use_pair && e->tma_store && !e->fuse_ln && !e->plane_residual && e->debug == 0 && e->layers >= 1;
+}
+
+// Phase lists for `nseq` sequences: layer l = [out-proj_l, FFN1_l, FFN2_l, QKV_{l+1} | output head].
+int get_chain_tables(cmdi_engine* e, int nseq, const ChainTables** out) {
+  auto it = e->chain_tables.find(nseq);
+  if (it != e->chain_tables.end()) {
+    *out = &it->second;
+    return 0;
+  }
+  const int M = nseq * e->S;
+  const int m_pairs = (M + 255) / 256;
+  std::vector<ChainPhaseDesc> host((size_t)e->layers * kMaxChainPhases);
+  ChainTables ct;
+  ct.total_tiles.assign(e->layers, 0);
+  auto base = [&](ChainPhaseDesc& d, const Planes& a, const CUtensorMap& w_hi, const CUtensorMap& w_lo, int N, int K, int bn) {
+    memset(&d, 0, sizeof(d));
+    d.a_hi = a.map_hi; d.a_lo = a.map_lo; d.w_hi = w_hi; d.w_lo = w_lo;
+    d.o_hi = a.map_hi; d.o_lo = a.map_hi; d.o_f32 = a.map_hi;  // placeholders unless set below
+    ChainPhaseInfo& pi = d.info;
+    pi.p.M = M; pi.p.N = N; pi.p.K = K; pi.p.nsplit = e->nsplit; pi.p.nsplit_out = e->nsplit; pi.p.rowmap = ROWMAP_IDENTITY;
+    pi.p.tma_store = 1;
+    pi.block_n = bn; pi.num_m_pairs = m_pairs; pi.num_n_blocks = (N + bn - 1) / bn; pi.num_k_blocks = (K + 63) / 64;
+  };
+  for (int l = 0; l < e->layers; ++l) {
+    const LayerW& w = e->lw[l];
+    ChainPhaseDesc* ph = &host[(size_t)l * kMaxChainPhases];
+    int* ctr = e->chain_ctr + (size_t)l * 3 * e->max_m_pairs;
+    // out-proj + residual -> v1 (fp32 + planes + partial statistics)
+    base(ph[0], e->attn_p, e->wo_chain[2 * l], e->wo_chain[2 * l + 1], kDModel, kDModel, kBnWide);
+    {
+      LinearParams& p = ph[0].info.p;
+      p.bias = w.bo;
+      if (l == 0) { p.residual = e->xseq; p.ld_res = kDModel; }
+      else {
+        p.ln_src = e->vsum; p.ld_ln = kDModel; p.ln_partials = e->stats2; p.ln_gamma = e->lw[l - 1].g2; p.ln_beta = e->lw[l - 1].be2;
+      }
+      p.out_f32 = e->x1; p.ld_f32 = kDModel; p.out_hi = e->x1_p.hi; p.out_lo = e->x1_p.lo; p.ld_bf = kDModel; p.stats_out = e->stats1;
+      ph[0].o_hi = e->x1_p.st32_hi; ph[0].o_lo = e->x1_p.st32_lo; ph[0].o_f32 = e->x1_st;
+      ph[0].info.done_ctr = ctr;
+    }
+    // FFN1 (norm1 folded) + GELU -> hidden planes
+    base(ph[1], e->x1_p, e->f_w1[l].w.pair_hi, e->f_w1[l].w.pair_lo, e->ff, kDModel, kBnWide);
+    {
+      LinearParams& p = ph[1].info.p;
+      p.bias = e->f_w1[l].d; p.fold_c = e->f_w1[l].c; p.fold_stats = e->stats1; p.act = 1;
+      p.out_hi = e->ffh_p.hi; p.out_lo = e->ffh_p.lo; p.ld_bf = e->ff;
+      ph[1].o_hi = e->ffh_p.st32_hi; ph[1].o_lo = e->ffh_p.st32_lo;
+      ph[1].info.wait_ctr = ctr; ph[1].info.wait_target = ph[0].info.num_n_blocks * 2;
+      ph[1].info.done_ctr = ctr + e->max_m_pairs;
+    }
+    // FFN2 + residual LN1(v1) -> v2 (fp32 + planes + partial statistics)
+    base(ph[2], e->ffh_p, e->w2_chain[2 * l], e->w2_chain[2 * l + 1], kDModel, e->ff, kBnWide);
+    {
+      LinearParams& p = ph[2].info.p;
+      p.bias = w.b2; p.ln_src = e->x1; p.ld_ln = kDModel; p.ln_partials = e->stats1; p.ln_gamma = w.g1; p.ln_beta = w.be1;
+      p.out_f32 = e->vsum; p.ld_f32 = kDModel; p.out_hi = e->xseq_p.hi; p.out_lo = e->xseq_p.lo; p.ld_bf = kDModel; p.stats_out = e->stats2;
+      ph[2].o_hi = e->xseq_p.st32_hi; ph[2].o_lo = e->xseq_p.st32_lo; ph[2].o_f32 = e->vsum_st;
+      ph[2].info.wait_ctr = ctr + e->max_m_pairs; ph[2].info.wait_target = ph[1].info.num_n_blocks * 2;
+      ph[2].info.done_ctr = ctr + 2 * e->max_m_pairs;
+    }
+    if (l + 1 < e->layers) {
+      // next layer's QKV projection (norm2 folded)
+      const FoldedW& fq = e->f_qkv[l + 1];
+      base(ph[3], e->xseq_p, fq.w.pair_hi, fq.w.pair_lo, 3 * kDModel, kDModel, kBnWide);
+      LinearParams& p = ph[3].info.p;
+      p.bias = fq.d; p.fold_c = fq.c; p.fold_stats = e->stats2;
+      p.out_hi = e->qkv_p.hi; p.out_lo = e->qkv_p.lo; p.ld_bf = 3 * kDModel;
+      ph[3].o_hi = e->qkv_p.st32_hi; ph[3].o_lo = e->qkv_p.st32_lo;
+    } else {
+      // output head on tokens 1.. (norm2 of the last layer folded), frame-major fp32 rows
+      base(ph[3], e->xseq_p, e->f_out.w.pair_hi, e->f_out.w.pair_lo, e->D_pad, kDModel, kBnWide);
+      LinearParams& p = ph[3].info.p;
+      p.bias = e->f_out.d; p.fold_c = e->f_out.c; p.fold_stats = e->stats2;
+      p.rowmap = ROWMAP_SEQ_TO_FRAMES; p.frames = e->L; p.out_f32 = e->model_out; p.ld_f32 = e->D_pad; p.tma_store = 0;
+    }
+    ph[3].info.wait_ctr = ctr + 2 * e->max_m_pairs; ph[3].info.wait_target = ph[2].info.num_n_blocks * 2;
+    int tiles = 0;
+    for (int i = 0; i < kMaxChainPhases; ++i) {
+      ph[i].info.publish_now = e->chain_publish_now;
+      ph[i].info.tile_begin = tiles;
+      tiles += ph[i].info.num_m_pairs * ph[i].info.num_n_blocks;
+      ph[i].info.tile_end = tiles;
+    }
+    ct.total_tiles[l] = tiles;
+  }
+  CKI(dev_alloc(e, &ct.dev, host.size()));
+  CK(cudaMemcpy(ct.dev, host.data(), host.size() * sizeof(ChainPhaseDesc), cudaMemcpyHostToDevice));
+  auto ins = e->chain_tables.emplace(nseq, std::move(ct));
+  *out = &ins.first->second;
+  return 0;
+}
+
+// Build (outside any stream capture: it allocates) the phase lists a pass over `nseq` sequences will use.
+int prepare_chain(cmdi_engine* e, int nseq) {
+  if (!chain_eligible(e)) return 0;
+  const ChainTables* ct = nullptr;
+  return get_chain_tables(e, nseq, &ct);
+}
+
+// The denoiser pass with LayerNorm folded into the consuming linear layers and each encoder layer's linear layers
+// chained into one launch: token rows, frame embedding, QKV_0, then per layer {attention, chain}: 3 + 2 * layers launches.
+int run_denoiser_chain(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond, const int* tmap_dev, cudaStream_t s,
+                       std::vector<cudaEvent_t>* evs, int reps) {
+  auto mark = [&]() -> int {
+    if (!evs) return 0;
+    cudaEvent_t ev;
+    CK(cudaEventCreate(&ev));
+    CK(cudaEventRecord(ev, s));
+    evs->push_back(ev);
+    return 0;
+  };
+  const int nseq = dup ? 2 * B : B;
+  const int M = nseq * e->S;
+  const ChainTables* ct = nullptr;
+  CKI(get_chain_tables(e, nseq, &ct));
+  // the dependency counters of all chained launches of this pass start from zero (one memset node per step)
+  CK(cudaMemsetAsync(e->chain_ctr, 0, (size_t)e->layers * 3 * e->max_m_pairs * sizeof(int), s));
+  CKI(mark());
+  TokenParams tk{};
+  tk.temb_table = e->temb_table; tk.step_ptr = e->step_ctr; tk.timestep_map = tmap_dev;
+  tk.cond_proj = has_cond ? e->cond_proj : nullptr; tk.uncond_proj = has_cond ? e->et_b : nullptr;
+  tk.pe0 = e->pe; tk.num_seqs = nseq; tk.n_cond_seqs = n_cond_seqs; tk.seq_len = e->S;
+  tk.x_f32 = e->xseq; tk.x_hi = e->xseq_p.hi; tk.x_lo = e->xseq_p.lo;
+  for (int r_ = 0; r_ < reps; ++r_) CK(launch_token_rows(tk, s));
+  CKI(mark());
+  LinearParams p{};
+  p.M = B * e->L; p.N = kDModel; p.K = e->D; p.nsplit = e->nsplit; p.bias = e->b_in; p.pos_enc = e->pe;
+  p.rowmap = ROWMAP_FRAMES_TO_SEQ; p.frames = e->L; p.dup_row_offset = dup ? B * e->S : 0;
+  p.out_f32 = e->xseq; p.ld_f32 = kDModel; p.out_hi = e->xseq_p.hi; p.out_lo = e->xseq_p.lo; p.ld_bf = kDModel;
+  p.nsplit_out = e->nsplit;
+  for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->x_state_p, e->w_in, p, kBnNarrow, s));
+  CKI(mark());
+  LinearParams q{};
+  q.M = M; q.N = 3 * kDModel; q.K = kDModel; q.nsplit = e->nsplit; q.bias = e->lw[0].bqkv;
+  q.out_hi = e->qkv_p.hi; q.out_lo = e->qkv_p.lo; q.ld_bf = 3 * kDModel; q.nsplit_out = e->nsplit;
+  for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->xseq_p, e->lw[0].wqkv, q, e->bn_qkv, s, &e->qkv_p));
+  CKI(mark());
+  AttnParams a{};
+  a.num_seqs = nseq; a.seq_len = e->S; a.num_heads = e->H; a.nsplit = e->nsplit; a.nsplit_out = e->nsplit;
+  a.out_hi = e->attn_p.hi; a.out_lo = e->attn_p.lo; a.ld_out = kDModel; a.trunc_split = e->attn_trunc_split; a.prefetch_q = e->attn_prefetch_q;
+  for (int l = 0; l < e->layers; ++l) {
+    for (int r_ = 0; r_ < reps; ++r_)
+      CK(launch_attention(e->q_map_hi, e->q_map_lo, e->kv_map_hi, e->kv_map_lo, e->attn_p.st_hi, e->attn_p.st_lo, a, s));
+    CKI(mark());
+    for (int r_ = 0; r_ < reps; ++r_) {
+      if (reps > 1)  // profiling repeats one launch back to back: its counters start from zero each time
+        CK(cudaMemsetAsync(e->chain_ctr + (size_t)l * 3 * e->max_m_pairs, 0, (size_t)3 * e->max_m_pairs * sizeof(int), s));
+      CK(launch_linear_chain(ct->dev + (size_t)l * kMaxChainPhases, kMaxChainPhases, ct->total_tiles[l], e->num_sms, s,
+                             (evs && l == 1) ? e->chain_dbg : nullptr));
+    }
+    CKI(mark());
+  }
+  return 0;
+}
+
 int ensure_stash(cmdi_engine* e) {
   if (e->stash_ready) return 0;
   if (e->S > 197 && !g_attn_bwd_tc) {
@@ -448,7 +639,10 @@ int launches_per_backward(const cmdi_engine* e) {
   return 3 + e->layers * (kBackwardLaunchesPerLayer + (g_attn_bwd_tc ? 1 : 0)) + 1;
 }
 
-int launches_per_pass(const cmdi_engine* e) { return 1 + 1 + e->layers * (e->fuse_ln ? 5 : 7) + 1; }
+int launches_per_pass(const cmdi_engine* e, bool guided = false) {
+  if (!guided && chain_eligible(e)) return 3 + 2 * e->layers;
+  return 1 + 1 + e->layers * ((e->fuse_ln && !guided) ? 5 : 7) + 1;
+}
 
 int check_ready(cmdi_engine* e, int B, bool need_schedule) {
   if (!e->weights_loaded) {
@@ -498,6 +692,7 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   CK(configure_linear2_kernels());
   CK(configure_linear_ln_kernel());
   CK(configure_attention_kernel());
+  CK(configure_linear_chain_kernel());
   cmdi_engine* e = new cmdi_engine();
   if (const char* g = getenv("CMDI_GEMM")) e->use_pair = strcmp(g, "single") != 0;
   if (const char* g = getenv("CMDI_DEBUG")) e->debug = atoi(g);
@@ -519,7 +714,11 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   if (const char* g = getenv("CMDI_ATTN_BWD")) g_attn_bwd_tc = strcmp(g, "simt") != 0;
   if (const char* g = getenv("CMDI_ATTN")) g_attn_persistent = strcmp(g, "oneshot") != 0;
   if (const char* g = getenv("CMDI_FUSE_LN")) e->fuse_ln = atoi(g) != 0;
+  if (const char* g = getenv("CMDI_CHAIN")) e->use_chain = atoi(g) != 0;
+  if (const char* g = getenv("CMDI_CHAIN_PUBLISH")) e->chain_publish_now = strcmp(g, "deferred") != 0;
   e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount; e->nsplit = cfg->precision;
+  // the chained launches spin on counters other CTA pairs bump: every pair must be resident at once
+  if (e->use_chain && linear_chain_max_clusters(e->num_sms) < e->num_sms / 2) e->use_chain = false;
   e->D = cfg->njoints; e->D_pad = round_up(cfg->njoints, 8); e->L = cfg->nframes; e->S = cfg->nframes + 1;
   e->ff = cfg->ff_size; e->H = cfg->num_heads; e->layers = cfg->num_layers; e->maxB = cfg->max_batch;
   e->max_seqs = 2 * e->maxB;
@@ -587,6 +786,33 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   A(dev_alloc(e, &e->text_scale, e->maxB));
   A(dev_alloc(e, &e->step_ctr, 2));
   A(dev_alloc(e, &e->rng, 1));
+  // chained forward path: folded weights, partial row statistics, dependency counters
+  e->f_qkv.resize(e->layers);
+  e->f_w1.resize(e->layers);
+  for (int l = 0; l < e->layers; ++l) {
+    if (l > 0) {
+      A(alloc_planes(e, &e->f_qkv[l].w, 3 * kDModel, kDModel, kDModel, kBnWide));
+      A(dev_alloc(e, &e->f_qkv[l].c, 3 * kDModel)); A(dev_alloc(e, &e->f_qkv[l].d, 3 * kDModel));
+    }
+    A(alloc_planes(e, &e->f_w1[l].w, e->ff, kDModel, kDModel, kBnWide));
+    A(dev_alloc(e, &e->f_w1[l].c, e->ff)); A(dev_alloc(e, &e->f_w1[l].d, e->ff));
+  }
+  A(alloc_planes(e, &e->f_out.w, round_up(e->D_pad, 256), kDModel, kDModel, kBnWide));
+  A(dev_alloc(e, &e->f_out.c, round_up(e->D_pad, 256))); A(dev_alloc(e, &e->f_out.d, round_up(e->D_pad, 256)));
+  e->wo_chain.resize(2 * e->layers);
+  e->w2_chain.resize(2 * e->layers);
+  for (int l = 0; l < e->layers && !rc; ++l) {
+    const LayerW& w = e->lw[l];
+    A(make_tmap_bf16_2d(&e->wo_chain[2 * l], w.wo.hi, kDModel, kDModel, kDModel, 64, kBnWide / 2));
+    A(make_tmap_bf16_2d(&e->wo_chain[2 * l + 1], w.wo.lo, kDModel, kDModel, kDModel, 64, kBnWide / 2));
+    A(make_tmap_bf16_2d(&e->w2_chain[2 * l], w.w2.hi, kDModel, e->ff, e->ff, 64, kBnWide / 2));
+    A(make_tmap_bf16_2d(&e->w2_chain[2 * l + 1], w.w2.lo, kDModel, e->ff, e->ff, 64, kBnWide / 2));
+  }
+  A(dev_alloc(e, &e->stats1, (size_t)e->seq_rows_pad * 16));
+  A(dev_alloc(e, &e->stats2, (size_t)e->seq_rows_pad * 16));
+  e->max_m_pairs = (e->seq_rows_pad + 255) / 256;
+  A(dev_alloc(e, &e->chain_ctr, (size_t)e->layers * 3 * e->max_m_pairs));
+  if (getenv("CMDI_CHAIN_DBG")) A(dev_alloc(e, &e->chain_dbg, (size_t)e->num_sms * kMaxChainPhases * 16));
   A(dev_alloc(e, &e->ln_stats1, (size_t)e->seq_rows_pad));
   A(dev_alloc(e, &e->ln_stats2, (size_t)e->seq_rows_pad));
   A(dev_alloc(e, &e->ref_a, (size_t)e->maxB * e->D * e->L));
@@ -695,6 +921,33 @@ extern "C" int cmdi_load_weights(cmdi_engine* e, const cmdi_tensor_desc* tensors
   }
 #undef LOAD_F32
 #undef LOAD_PL
+  // ---- LayerNorm folded into the layers that consume it (chained forward path): W * gamma planes, c, d ----
+  if (missing.empty() && !rc) {
+    float* folded = nullptr;
+    CK(cudaMalloc(&folded, scratch_elems * 4));
+    ScratchGuard folded_guard{folded};
+    auto fold = [&](FoldedW& fw, const std::string& key, int rows, int cols, const float* gamma, const float* beta,
+                    const float* bias_dev) -> int {
+      const cmdi_tensor_desc* t = by_name[key];
+      const float* src = t->data;
+      if (t->on_host) {
+        CK(cudaMemcpyAsync(scratch, t->data, (size_t)rows * cols * 4, cudaMemcpyHostToDevice, s));
+        src = scratch;
+      }
+      CK(launch_fold_ln(src, rows, cols, gamma, beta, bias_dev, folded, fw.c, fw.d, s));
+      CK(launch_split_planes(folded, rows, cols, cols, fw.w.hi, fw.w.lo, fw.w.ld, s));
+      return 0;
+    };
+    for (int l = 0; l < e->layers && !rc; ++l) {
+      const std::string p = "seqTransEncoder.layers." + std::to_string(l) + ".";
+      if (l > 0)
+        rc = rc || fold(e->f_qkv[l], p + "self_attn.in_proj_weight", 3 * kDModel, kDModel, e->lw[l - 1].g2, e->lw[l - 1].be2, e->lw[l].bqkv);
+      rc = rc || fold(e->f_w1[l], p + "linear1.weight", e->ff, kDModel, e->lw[l].g1, e->lw[l].be1, e->lw[l].b1);
+    }
+    rc = rc || fold(e->f_out, "output_process.poseFinal.weight", e->D, kDModel, e->lw[e->layers - 1].g2, e->lw[e->layers - 1].be2, e->b_out);
+    cudaError_t fe = cudaStreamSynchronize(s);
+    if (!rc) CK(fe);
+  }
   cudaError_t se = cudaStreamSynchronize(s);
   if (!missing.empty()) {
     set_last_error("state dict is missing: %s", missing.c_str());
@@ -818,6 +1071,7 @@ extern "C" int cmdi_model_forward(cmdi_engine* e, const cmdi_forward_args* a, fl
   const bool host = a->host_buffers != 0;
   const size_t n = (size_t)B * e->D * e->L;
   CKI(ensure_temb(e, s));
+  CKI(prepare_chain(e, a->cfg ? 2 * B : B));
   int rc = 0;
   const float* x = (const float*)stage_in(a->x, e->ref_a, n * 4, host, s, &rc);
   if (rc) return 1;
@@ -883,6 +1137,7 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
   const int t0 = e->T - 1 - a->skip_timesteps;
   const int nsteps = (a->num_steps > 0 && a->num_steps < t0 + 1) ? a->num_steps : t0 + 1;
   CKI(ensure_temb(e, s));
+  CKI(prepare_chain(e, a->cfg ? 2 * B : B));
   int rc = 0;
 
   // ---- x_T (gaussian_diffusion.py:1245-1248) ----
@@ -1025,7 +1280,7 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
     } else {
       CKI(enqueue_step(s, guided));
     }
-    e->launches += (long long)run * (launches_per_pass(e) + 1 + (guided ? launches_per_backward(e) : 0));
+    e->launches += (long long)run * (launches_per_pass(e, guided) + 1 + (guided ? launches_per_backward(e) : 0));
     k += run;
     if (a->dump_xstart && dump_i < a->n_dump && a->dump_steps[dump_i] == k - 1) {
       if (host) {
@@ -1129,6 +1384,7 @@ extern "C" int cmdi_profile_pass(cmdi_engine* e, int batch, int cfg, int repeats
     return 1;
   }
   if (repeats < 1) repeats = 1;
+  CKI(prepare_chain(e, cfg ? 2 * batch : batch));
   const int rc = run_denoiser(e, batch, cfg != 0, batch, has_cond, nullptr, s, &evs, repeats);
   cudaError_t se = cudaStreamSynchronize(s);
   int n = (int)evs.size() - 1;
@@ -1142,6 +1398,24 @@ extern "C" int cmdi_profile_pass(cmdi_engine* e, int batch, int cfg, int repeats
   for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
   if (rc) return 1;
   CK(se);
+  if (e->chain_dbg) {
+    std::vector<long long> h((size_t)e->num_sms * kMaxChainPhases * 16);
+    CK(cudaMemcpy(h.data(), e->chain_dbg, h.size() * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemset(e->chain_dbg, 0, h.size() * 8));
+    const char* names[16] = {"tiles", "tma_dep_wait", "tma_slot_wait", "mma_operand_wait", "mma_acc_wait", "epi0_acc_wait", "epi0_slices", "epi0_publish",
+                             "s_rowstats", "s_stage_free", "s_loads+acc", "s_fold_bias_res", "s_stats_act", "s_f32_store", "s_plane_store", "-"};
+    for (int ph = 0; ph < kMaxChainPhases; ++ph) {
+      double tiles = 0, acc[16] = {0};
+      for (int b = 0; b < e->num_sms; ++b) {
+        tiles += (double)h[((size_t)b * kMaxChainPhases + ph) * 16];
+        for (int k = 1; k < 16; ++k) acc[k] += (double)h[((size_t)b * kMaxChainPhases + ph) * 16 + k];
+      }
+      // tiles are counted by both CTAs' TMA threads; the MMA counters exist on leaders only
+      fprintf(stderr, "chain dbg phase %d: %.0f tile visits (%d repeats);  cycles per tile:", ph, tiles, repeats);
+      for (int k = 1; k < 15; ++k) fprintf(stderr, " %s=%.0f", names[k], acc[k] / (tiles > 0 ? tiles : 1) * ((k == 3 || k == 4) ? 2.0 : 1.0));
+      fprintf(stderr, "\n");
+    }
+  }
   e->launches += (int64_t)launches_per_pass(e) * repeats;
   return 0;
 }

@@ -203,7 +203,7 @@ linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       long long c1 = clock64();
       tc_fence_after();
-      epilogue_tile<BLOCK_N>(p, epi_maps, tmem_base, acc, m_blk, n_blk, lane_group, col_part, lane, epi_stage_addr);
+      epilogue_tile<BLOCK_N>(p, epi_maps, tmem_base, (uint32_t)(acc * BLOCK_N), m_blk, n_blk, lane_group, col_part, lane, epi_stage_addr);
       long long c2 = clock64();
       tc_fence_before();
       __syncwarp();

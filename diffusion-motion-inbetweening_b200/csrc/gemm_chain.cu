@@ -1,0 +1,555 @@
+// Several linear layers of an encoder layer in ONE persistent launch of CTA pairs (tcgen05.mma.cta_group::2).
+//
+// Why.  Launched one by one (gemm2.cu), every linear layer pays (a) its own tile quantisation -- QKV is 300 pair
+// tiles on 74 clusters = 4.05 rounds, i.e. 5; the N = 512 layers 2.7 rounds, i.e. 3 -- and (b) a kernel boundary
+// whose cost is the tail imbalance of the last round + the prologue + the first TMA round trip, because every one of
+// these kernels owns all shared memory and all 512 TMEM columns of its SM and a successor cannot become resident
+// early.  Here the tiles of out-proj, FFN1, FFN2 and the NEXT layer's QKV projection (or the output head) form one
+// list of 700 tiles (256 x 256 each) walked by the 74 clusters in order; the smem rings, the TMEM double buffer and the
+// warp roles simply keep running across phase boundaries.
+//
+// Dependencies.  Phase p + 1 reads, as its A operand, rows that phase p writes.  Tiles are ordered row-pair-major
+// inside a phase; when a CTA's half of a tile is in memory it bumps a per-(phase, row-pair) counter, and the TMA
+// producer of a consuming tile spins on that counter (acquire) before it issues the first load of the tile.
+// All clusters are co-resident (grid = 2 x 74 <= SM count, checked at start-up with the occupancy API) and walk
+// their tiles in increasing global index, and a tile only ever waits for tiles of LOWER index: no deadlock.
+//
+//   epilogue warp:     TMA stores -> cp.async.bulk.wait_group 0 -> mbarrier.arrive(publish[tile & 3])     (release.cta;
+//                      the other lanes' plain stores are ordered before lane 0's arrive by __syncwarp)
+//   publisher warp:    mbarrier wait(publish[..]) (acquire.cta) -> fence.proxy.async -> __threadfence -> atomicAdd(counter)
+//   consumer TMA lane: ld.acquire.gpu(counter) >= target -> fence.proxy.async -> cp.async.bulk.tensor loads
+//   consumer epilogue: ordered after the TMA lane's acquire through full[] -> MMA -> tmem_full[]; its reads of
+//                      activations written in this launch use ld.global.cg
+//
+// Epilogue.  Measured on the first version of this kernel (8 epilogue warps, 64-column chunks): the epilogue, not the
+// tensor pipe, set the pace -- 13k .. 44k cycles per tile against a 12.3k-cycle K = 512 mainloop -- because two warps
+// per scheduler cannot hide the global-load, TMA-store-readout and fence latencies of a long serial per-chunk
+// program.  Now: TWELVE epilogue warps (three per TMEM lane group; 128 registers each), the accumulator tile is cut
+// into eight 32-column slices handed round-robin to the three warps of a lane group (so the next tile's slices start
+// while the previous tile's are still being written), a slice is one fp32 TMA store + one store of both bf16 planes
+// through 64-byte-swizzled boxes, per-column constants come from broadcast loads instead of shuffles, and the
+// release fence / counter bump lives in a warp of its own.  Shared memory: A ring 3 x 32 KB, W ring 2 x 32 KB
+// (separate barriers), 12 x 4 KB staging tiles.
+#include "common.cuh"
+#include "gemm_epilogue.cuh"
+#include "kernels.h"
+
+namespace cmdi {
+
+namespace {
+
+constexpr int kBlockM = 128;  // per CTA; 256 per pair
+constexpr int kBlockN = 256;
+constexpr int kBlockK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kNumEpiWarps = 12;
+constexpr int kFirstEpiWarp = 3;
+constexpr int kNumThreads = (kFirstEpiWarp + kNumEpiWarps) * 32;
+constexpr int kStagesA = 3, kStagesW = 2;
+constexpr int kPlaneBytes = kBlockM * kBlockK * 2;   // one bf16 plane of a 128-row x 64-column operand block = 16 KB
+constexpr int kOperandBytes = 2 * kPlaneBytes;       // hi + lo
+constexpr int kSlices = kBlockN / 32;                // 32-column slices per tile
+constexpr int kAccStride = 256;                      // TMEM columns per accumulator buffer
+constexpr uint32_t kTmemCols = 512;
+constexpr int kPublishBars = 4;
+
+struct __align__(8) ChainBarriers {
+  uint64_t full_a[kStagesA], empty_a[kStagesA];
+  uint64_t full_w[kStagesW], empty_w[kStagesW];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t publish[kPublishBars];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+constexpr int kSmemBytes = 1024 + (kStagesA + kStagesW) * kOperandBytes + kNumEpiWarps * kEpiStageBytes + (int)sizeof(ChainBarriers) +
+                           kMaxChainPhases * (int)sizeof(ChainPhaseInfo);
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// Bounded like mbar_wait: a protocol bug must trap, not hang the GPU.
+__device__ __forceinline__ void wait_counter(const int* ctr, int target) {
+  if (ld_acquire_gpu(ctr) >= target) return;
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(ctr) < target) {
+    __nanosleep(32);
+    if (clock64() - t0 > 4000000000LL) {
+      printf("cmdi: chain dependency timeout block=%d counter=%p value=%d target=%d\n", blockIdx.x, ctr, ld_acquire_gpu(ctr), target);
+      __trap();
+    }
+  }
+}
+
+// (mean, rstd) of a 512-wide row from the 16 partial statistics (mean_j, M2_j) of its 32-column slices
+// (Chan et al. parallel combination with equal counts; fp32 throughout)
+__device__ __forceinline__ float2 combine_row_stats(const float2* partials_row) {
+  float m[16], q = 0.f, s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 a = ld_global_cg_v4(partials_row + 2 * i);
+    m[2 * i] = __uint_as_float(a.x);
+    m[2 * i + 1] = __uint_as_float(a.z);
+    q += __uint_as_float(a.y) + __uint_as_float(a.w);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += m[i];
+  const float mean = s * (1.0f / 16.0f);
+  float dev = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float d = m[i] - mean;
+    dev = fmaf(d, d, dev);
+  }
+  const float var = (q + 32.0f * dev) * (1.0f / 512.0f);
+  return make_float2(mean, rsqrtf(var + 1e-5f));  // nn.LayerNorm default eps, as nn.TransformerEncoderLayer uses it
+}
+
+// hi and lo planes of a 32-row x 32-column block (thread `lane` holds row `lane` as 16 bf16x2 words per plane) through
+// the warp's staging tile as two {64 B x 32 rows} boxes with the 64-byte swizzle (16-byte chunk c of row r sits at
+// chunk c ^ ((r >> 1) & 3): conflict-free for a row-per-lane writer), one bulk tensor store each.
+__device__ __forceinline__ void store_planes_tma(uint32_t stage, int lane, const uint32_t (&hw)[16], const uint32_t (&lw)[16],
+                                                 const CUtensorMap* map_hi, const CUtensorMap* map_lo, bool with_lo, int col, int row) {
+  if (lane == 0) tma_store_wait_read();
+  __syncwarp();
+  const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    st_shared_v4(stage + lane * 64 + ((c ^ sw) << 4), hw[c * 4], hw[c * 4 + 1], hw[c * 4 + 2], hw[c * 4 + 3]);
+    if (with_lo) st_shared_v4(stage + 2048 + lane * 64 + ((c ^ sw) << 4), lw[c * 4], lw[c * 4 + 1], lw[c * 4 + 2], lw[c * 4 + 3]);
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(map_hi, stage, col, row);
+    if (with_lo) tma_store_2d(map_lo, stage + 2048, col, row);
+    tma_store_commit();
+  }
+}
+
+struct RowStats {   // per-tile cache of the row statistics this thread needs (its row of the tile)
+  float2 fold, ln;
+};
+
+// One 32-column slice of a 128-row accumulator: TMEM -> registers -> [folded LayerNorm] -> bias -> [residual] ->
+// [partial statistics] -> [GELU] -> fp32 rows and/or bf16 hi/lo planes.
+__device__ __forceinline__ void epilogue_slice(const LinearParams& p, const ChainPhaseDesc& pd, uint32_t tmem_acc, int m_blk, int n_blk,
+                                               int slice, int lane_group, int lane, uint32_t stage, RowStats& rs, bool new_tile, long long* dbg) {
+  long long t0 = clock64(), t1;
+#define CMDI_T(i) do { if (dbg) { t1 = clock64(); dbg[i] += t1 - t0; t0 = t1; } } while (0)
+  const int warp_row0 = m_blk * kBlockM + lane_group * 32;
+  const int row = warp_row0 + lane;
+  if (new_tile) {
+    if (p.fold_stats) rs.fold = combine_row_stats(p.fold_stats + (size_t)row * 16);
+    if (p.ln_partials) rs.ln = combine_row_stats(p.ln_partials + (size_t)row * 16);
+  }
+  const int n0 = n_blk * kBlockN + slice * 32;
+  if (n0 >= p.N) return;  // warp-uniform: columns beyond the layer's width (output head)
+  const float* res_src = p.residual ? p.residual : p.ln_src;
+  // the staging tile is about to be rewritten (residual fetch or stores): the bulk store issued from it has been read out
+  CMDI_T(8);   // row statistics
+  if (lane == 0) tma_store_wait_read();
+  __syncwarp();
+  CMDI_T(9);   // staging free
+  uint4 rv[8];
+  if (res_src) {
+    // fp32 residual block, 32 rows x 128 B, fetched coalesced (4 complete row segments per instruction)
+    const long long ld = p.residual ? p.ld_res : p.ld_ln;
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      rv[it] = ld_global_cg_v4(res_src + (long long)(warp_row0 + it * 4 + (lane >> 3)) * ld + n0 + (lane & 7) * 4);
+  }
+  uint32_t v[32];
+  tmem_ld32(tmem_acc + slice * 32, v);
+  tmem_ld_wait();
+  CMDI_T(10);  // residual loads issued + accumulator read
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (p.fold_stats) {
+    // acc = v (W.gamma)^T  ->  rstd * (acc - mean * c[n]);  the bias added next carries W beta + b
+    const float nm = -rs.fold.x;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.fold_c + n0) + g);
+      f[g * 4 + 0] = __fmaf_rn(nm, c4.x, f[g * 4 + 0]) * rs.fold.y;
+      f[g * 4 + 1] = __fmaf_rn(nm, c4.y, f[g * 4 + 1]) * rs.fold.y;
+      f[g * 4 + 2] = __fmaf_rn(nm, c4.z, f[g * 4 + 2]) * rs.fold.y;
+      f[g * 4 + 3] = __fmaf_rn(nm, c4.w, f[g * 4 + 3]) * rs.fold.y;
+    }
+  }
+  if (p.bias) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + g);
+      f[g * 4 + 0] += b4.x; f[g * 4 + 1] += b4.y; f[g * 4 + 2] += b4.z; f[g * 4 + 3] += b4.w;
+    }
+  }
+  if (res_src) {
+    // transpose through the staging tile: every thread gets its own row
+    const int c = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3);
+      st_shared_v4(stage + rr * 128 + ((c ^ (rr & 7)) << 4), rv[it].x, rv[it].y, rv[it].z, rv[it].w);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const uint4 u = ld_shared_v4(stage + lane * 128 + ((g ^ (lane & 7)) << 4));
+      if (p.ln_src) {
+        // residual = LayerNorm(ln_src) re-derived from its fp32 input, the row statistics and gamma / beta
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + n0) + g);
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + n0) + g);
+        f[g * 4 + 0] += ln_apply(__uint_as_float(u.x), rs.ln.x, rs.ln.y, g4.x, b4.x);
+        f[g * 4 + 1] += ln_apply(__uint_as_float(u.y), rs.ln.x, rs.ln.y, g4.y, b4.y);
+        f[g * 4 + 2] += ln_apply(__uint_as_float(u.z), rs.ln.x, rs.ln.y, g4.z, b4.z);
+        f[g * 4 + 3] += ln_apply(__uint_as_float(u.w), rs.ln.x, rs.ln.y, g4.w, b4.w);
+      } else {
+        f[g * 4 + 0] += __uint_as_float(u.x); f[g * 4 + 1] += __uint_as_float(u.y);
+        f[g * 4 + 2] += __uint_as_float(u.z); f[g * 4 + 3] += __uint_as_float(u.w);
+      }
+    }
+  }
+  CMDI_T(11);  // fold + bias + residual
+  if (p.stats_out) {
+    // partial LayerNorm statistics of this thread's 32 output values (two-pass in registers)
+    float sm = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) sm += (f[j] + f[j + 1]) + (f[j + 2] + f[j + 3]);
+    const float mean32 = sm * (1.0f / 32.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float a = f[j] - mean32;
+      q = fmaf(a, a, q);
+    }
+    p.stats_out[(size_t)row * 16 + (n0 >> 5)] = make_float2(mean32, q);
+  }
+  if (p.act == 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+  }
+  CMDI_T(12);  // statistics + activation
+  if (p.out_f32) {
+    uint32_t w[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(f[j]);
+    if (p.tma_store) {
+      store_block_tma(stage, lane, w, &pd.o_f32, n0, warp_row0);
+    } else {
+      // row-mapped fp32 output (output head: sequence rows -> frame rows, token row dropped): masked coalesced stores
+      RowSlots rows;
+      rows.ok = 0;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        int pos_unused;
+        long long r;
+        if (map_row(p, warp_row0 + it * 4 + (lane >> 3), r, pos_unused)) rows.ok |= 1u << it;
+        rows.row[it] = (int)r;
+      }
+      store_block_coalesced(stage, lane, w, reinterpret_cast<char*>(p.out_f32 + n0), rows, (long long)p.ld_f32 * 4, (p.N - n0) / 4, 1, 0);
+    }
+  }
+  CMDI_T(13);  // fp32 store
+  if (p.out_hi) {
+    uint32_t hw[16], lw[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) split_bf16x2(f[2 * j], f[2 * j + 1], hw[j], lw[j]);
+    store_planes_tma(stage, lane, hw, lw, &pd.o_hi, &pd.o_lo, p.nsplit_out == 3, n0, warp_row0);
+  }
+  CMDI_T(14);  // plane stores
+#undef CMDI_T
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+linear_chain_kernel(const ChainPhaseDesc* __restrict__ phases, const int num_phases, const int total_tiles, long long* dbg) {
+  // dbg (bring-up, CMDI_CHAIN_DBG=1): [gridDim.x][kMaxChainPhases][8] cycle counters per CTA and phase:
+  //   0 tiles  1 tma: dependency wait  2 tma: slot wait  3 mma: operand wait  4 mma: accumulator wait
+  //   5 epilogue warp 0: accumulator wait  6 its slice work  7 its publish wait
+  long long* dbg_me = dbg ? dbg + (size_t)blockIdx.x * kMaxChainPhases * 16 : nullptr;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring_a = smem;
+  uint8_t* ring_w = ring_a + kStagesA * kOperandBytes;
+  uint8_t* epi_stage = ring_w + kStagesW * kOperandBytes;  // kNumEpiWarps x 4 KB store-staging tiles
+  ChainBarriers* bars = reinterpret_cast<ChainBarriers*>(epi_stage + kNumEpiWarps * kEpiStageBytes);
+  ChainPhaseInfo* info = reinterpret_cast<ChainPhaseInfo*>(bars + 1);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int my_tiles = (total_tiles - cluster_id + num_clusters - 1) / num_clusters;
+
+  // phase descriptors (all but the tensor maps) into shared memory: every role reads them per tile
+  for (int i = threadIdx.x; i < num_phases * (int)(sizeof(ChainPhaseInfo) / 4); i += kNumThreads) {
+    const int ph = i / (int)(sizeof(ChainPhaseInfo) / 4), w = i % (int)(sizeof(ChainPhaseInfo) / 4);
+    reinterpret_cast<uint32_t*>(info + ph)[w] = reinterpret_cast<const uint32_t*>(&phases[ph].info)[w];
+  }
+  if (warp_idx == 0 && lane == 0) {
+    for (int ph = 0; ph < num_phases; ++ph) {
+      tma_prefetch_desc(&phases[ph].a_hi);
+      tma_prefetch_desc(&phases[ph].w_hi);
+    }
+    for (int s = 0; s < kStagesA; ++s) {
+      mbar_init(&bars->full_a[s], 1);
+      mbar_init(&bars->empty_a[s], 1);
+    }
+    for (int s = 0; s < kStagesW; ++s) {
+      mbar_init(&bars->full_w[s], 1);
+      mbar_init(&bars->empty_w[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->tmem_full[s], 1);
+      mbar_init(&bars->tmem_empty[s], 2 * 4 * kSlices);  // every (CTA, lane group, slice) arrives once per tile
+    }
+    for (int s = 0; s < kPublishBars; ++s) mbar_init(&bars->publish[s], kNumEpiWarps);
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc_2sm(&bars->tmem_base, kTmemCols);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // barrier inits + TMEM allocation visible to both CTAs
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp_idx == 0) {
+    // ===================================== TMA producer (both CTAs) =====================================
+    if (lane == 0) {
+      int sa = 0, sw = 0, ph = 0;
+      uint32_t pa = 0, pw = 0;
+      for (int seq = 0; seq < my_tiles; ++seq) {
+        const int tile = cluster_id + seq * num_clusters;
+        while (tile >= info[ph].tile_end) ++ph;
+        const ChainPhaseInfo& pi = info[ph];
+        const ChainPhaseDesc& pd = phases[ph];
+        const int local = tile - pi.tile_begin;
+        const int m_pair = local / pi.num_n_blocks;
+        const int m_blk = 2 * m_pair + (int)cta_rank;
+        const int n_blk = local % pi.num_n_blocks;
+        const int nplanes = (pi.p.nsplit == 3) ? 2 : 1;
+        const uint32_t tx_bytes = 2u * nplanes * kPlaneBytes;  // both CTAs' loads complete on the leader's barrier
+        long long c0 = clock64();
+        if (pi.wait_ctr) {
+          // the A rows of this row pair are written by an earlier phase of this launch
+          wait_counter(pi.wait_ctr + m_pair, pi.wait_target);
+          fence_proxy_async_all();
+        }
+        if (dbg_me) { dbg_me[ph * 16 + 0] += 1; dbg_me[ph * 16 + 1] += clock64() - c0; }
+        for (int kb = 0; kb < pi.num_k_blocks; ++kb) {
+          c0 = clock64();
+          mbar_wait(&bars->empty_w[sw], pw ^ 1);
+          uint8_t* dw = ring_w + (size_t)sw * kOperandBytes;
+          if (leader) mbar_arrive_expect_tx(&bars->full_w[sw], tx_bytes);
+          tma_load_2d_2sm(dw, &pd.w_hi, &bars->full_w[sw], kb * kBlockK, n_blk * kBlockN + (int)cta_rank * (kBlockN / 2));
+          if (nplanes == 2)
+            tma_load_2d_2sm(dw + kPlaneBytes, &pd.w_lo, &bars->full_w[sw], kb * kBlockK, n_blk * kBlockN + (int)cta_rank * (kBlockN / 2));
+          mbar_wait(&bars->empty_a[sa], pa ^ 1);
+          if (dbg_me) dbg_me[ph * 16 + 2] += clock64() - c0;
+          uint8_t* da = ring_a + (size_t)sa * kOperandBytes;
+          if (leader) mbar_arrive_expect_tx(&bars->full_a[sa], tx_bytes);
+          tma_load_2d_2sm(da, &pd.a_hi, &bars->full_a[sa], kb * kBlockK, m_blk * kBlockM);
+          if (nplanes == 2) tma_load_2d_2sm(da + kPlaneBytes, &pd.a_lo, &bars->full_a[sa], kb * kBlockK, m_blk * kBlockM);
+          if (++sa == kStagesA) { sa = 0; pa ^= 1; }
+          if (++sw == kStagesW) { sw = 0; pw ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx == 1) {
+    // ====================================== MMA issuer (leader CTA only) ======================================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * kBlockM, kBlockN, 0);
+      int sa = 0, sw = 0, ph = 0;
+      uint32_t pa = 0, pw = 0;
+      for (int seq = 0; seq < my_tiles; ++seq) {
+        const int tile = cluster_id + seq * num_clusters;
+        while (tile >= info[ph].tile_end) ++ph;
+        const ChainPhaseInfo& pi = info[ph];
+        const bool split = pi.p.nsplit == 3;
+        const int acc = seq & 1;
+        long long c0 = clock64();
+        mbar_wait(&bars->tmem_empty[acc], ((seq >> 1) & 1) ^ 1);
+        if (dbg_me) dbg_me[ph * 16 + 4] += clock64() - c0;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        for (int kb = 0; kb < pi.num_k_blocks; ++kb) {
+          c0 = clock64();
+          mbar_wait(&bars->full_w[sw], pw);
+          mbar_wait(&bars->full_a[sa], pa);
+          if (dbg_me) dbg_me[ph * 16 + 3] += clock64() - c0;
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(ring_a + (size_t)sa * kOperandBytes);
+          const uint32_t w_addr = smem_u32(ring_w + (size_t)sw * kOperandBytes);
+          const uint64_t da_hi = make_desc_kmajor_sw128(a_addr);
+          const uint64_t db_hi = make_desc_kmajor_sw128(w_addr);
+          if (split) {
+            const uint64_t da_lo = make_desc_kmajor_sw128(a_addr + kPlaneBytes);
+            const uint64_t db_lo = make_desc_kmajor_sw128(w_addr + kPlaneBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_ss_2sm(d_tmem, desc_advance(da_lo, k * kUmmaK * 2), desc_advance(db_hi, k * kUmmaK * 2), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_ss_2sm(d_tmem, desc_advance(da_hi, k * kUmmaK * 2), desc_advance(db_lo, k * kUmmaK * 2), idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_ss_2sm(d_tmem, desc_advance(da_hi, k * kUmmaK * 2), desc_advance(db_hi, k * kUmmaK * 2), idesc, 1u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_ss_2sm(d_tmem, desc_advance(da_hi, k * kUmmaK * 2), desc_advance(db_hi, k * kUmmaK * 2), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&bars->empty_a[sa], 0x3);  // frees the slots in BOTH CTAs
+          umma_commit_2sm(&bars->empty_w[sw], 0x3);
+          if (++sa == kStagesA) { sa = 0; pa ^= 1; }
+          if (++sw == kStagesW) { sw = 0; pw ^= 1; }
+        }
+        umma_commit_2sm(&bars->tmem_full[acc], 0x3);  // both CTAs' epilogues may read their half of the tile
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx == 2) {
+    // ============ publisher: one release fence + counter bump per tile, off the epilogue warps' critical path ============
+    if (lane == 0) {
+      int ph = 0;
+      for (int seq = 0; seq < my_tiles; ++seq) {
+        const int tile = cluster_id + seq * num_clusters;
+        while (tile >= info[ph].tile_end) ++ph;
+        const ChainPhaseInfo& pi = info[ph];
+        mbar_wait(&bars->publish[seq & (kPublishBars - 1)], (seq / kPublishBars) & 1);
+        if (pi.done_ctr) {
+          fence_proxy_async_all();
+          __threadfence();
+          atomicAdd(pi.done_ctr + (tile - pi.tile_begin) / pi.num_n_blocks, 1);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============ epilogue: 12 warps, three per TMEM lane group, 32-column slices handed round-robin ============
+    const int ew = warp_idx - kFirstEpiWarp;
+    const int lane_group = warp_idx & 3;  // the TMEM lanes a warp may touch: 32 * (warp index % 4)
+    const int j3 = ew >> 2;               // 0..2 within the lane group
+    const uint32_t epi_stage_addr = smem_u32(epi_stage + ew * kEpiStageBytes);
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(lane_group * 32) << 16);
+    int ph = 0, cur_seq = -1, stored_seq = -1;
+    int m_blk = 0, n_blk = 0, acc = 0;
+    RowStats rs{make_float2(0.f, 1.f), make_float2(0.f, 1.f)};
+    // everything this warp stored for tile `seq` is in memory: tell the publisher
+    auto publish = [&](int seq) {
+      __syncwarp();  // the other lanes' plain stores (row-mapped outputs, partial statistics) before lane 0's release
+      if (lane == 0) {
+        tma_store_wait_all();
+        mbar_arrive(&bars->publish[seq & (kPublishBars - 1)]);
+      }
+    };
+    const int total_slices = my_tiles * kSlices;
+    for (int g = j3; g < total_slices; g += 3) {
+      const int seq = g >> 3, slice = g & (kSlices - 1);
+      const bool new_tile = seq != cur_seq;
+      long long c0 = clock64(), c1 = c0, c2 = c0;
+      if (new_tile) {
+        const int tile = cluster_id + seq * num_clusters;
+        while (tile >= info[ph].tile_end) ++ph;
+        const int local = tile - info[ph].tile_begin;
+        m_blk = 2 * (local / info[ph].num_n_blocks) + (int)cta_rank;
+        n_blk = local % info[ph].num_n_blocks;
+        acc = seq & 1;
+        mbar_wait(&bars->tmem_full[acc], (seq >> 1) & 1);
+        c1 = clock64();
+        tc_fence_after();
+        if (stored_seq >= 0) {
+          publish(stored_seq);  // deferred from the previous tile: its stores have landed while the mainloop ran
+          stored_seq = -1;
+        }
+        c2 = clock64();
+        cur_seq = seq;
+      }
+      const ChainPhaseInfo& pi = info[ph];
+      epilogue_slice(pi.p, phases[ph], tmem_lane + acc * kAccStride, m_blk, n_blk, slice, lane_group, lane, epi_stage_addr, rs, new_tile,
+                     (dbg_me && ew == 0 && lane == 0) ? dbg_me + ph * 16 : nullptr);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_on_leader(&bars->tmem_empty[acc]);
+      stored_seq = seq;
+      long long c3 = clock64();
+      if (((g + 3) >> 3) != seq) {
+        // last slice of this tile for this warp.  If this cluster's next tile belongs to a later phase (or does not
+        // exist) it may depend on this one: publish now; otherwise at the start of the next tile.
+        const int next_tile = cluster_id + (seq + 1) * num_clusters;
+        if (next_tile >= pi.tile_end || pi.publish_now) {
+          publish(seq);
+          stored_seq = -1;
+        }
+      }
+      if (dbg_me && ew == 0 && lane == 0) {
+        dbg_me[ph * 16 + 5] += c1 - c0; dbg_me[ph * 16 + 6] += c3 - c2; dbg_me[ph * 16 + 7] += (c2 - c1) + (clock64() - c3);
+      }
+    }
+    if (stored_seq >= 0) publish(stored_seq);
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody touches the pair's TMEM / barriers after this point
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+cudaError_t configure_linear_chain_kernel() {
+  return cudaFuncSetAttribute(linear_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+}
+
+// how many CTA pairs of this kernel can be resident at once on the current device (they spin on each other's counters:
+// the launch must never exceed this)
+int linear_chain_max_clusters(int num_sms) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * (num_sms / 2));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, linear_chain_kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+cudaError_t launch_linear_chain(const ChainPhaseDesc* phases_dev, int num_phases, int total_tiles, int num_sms, cudaStream_t stream,
+                                long long* dbg) {
+  if (num_phases < 1 || num_phases > kMaxChainPhases || total_tiles < 1) {
+    set_last_error("launch_linear_chain: bad phase list (%d phases, %d tiles)", num_phases, total_tiles);
+    return cudaErrorInvalidValue;
+  }
+  static int max_clusters = -1;
+  if (max_clusters < 0) max_clusters = linear_chain_max_clusters(num_sms);
+  int clusters = num_sms / 2;
+  if (clusters > total_tiles) clusters = total_tiles;
+  if (clusters > max_clusters) {
+    set_last_error("launch_linear_chain: %d co-resident CTA pairs needed, the device offers %d", clusters, max_clusters);
+    return cudaErrorInvalidConfiguration;
+  }
+  // never a programmatic dependent launch: its CTAs must not become resident while a predecessor still holds SMs
+  return launch_kernel_ex(false, linear_chain_kernel, dim3(2 * clusters), dim3(kNumThreads), (size_t)kSmemBytes, stream, phases_dev,
+                          num_phases, total_tiles, dbg);
+}
+
+}  // namespace cmdi

@@ -91,6 +91,14 @@ __device__ __forceinline__ void store_block_tma(uint32_t stage, int lane, const 
   }
 }
 
+// 16-byte load that bypasses L1 (ld.global.cg): activation blocks may have been written by another CTA of the SAME
+// launch (chained linear layers, gemm_chain.cu), and L1 is not coherent across SMs
+__device__ __forceinline__ uint4 ld_global_cg_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
 // Inverse: fetch a 32-row x 128-byte block with coalesced 16-byte loads and hand every thread its own row.
 __device__ __forceinline__ void load_block_coalesced(uint32_t stage, int lane, uint32_t (&w)[32], const char* src_base,
                                                      const RowSlots& rows, long long pitch_bytes, int valid_chunks) {
@@ -100,7 +108,7 @@ __device__ __forceinline__ void load_block_coalesced(uint32_t stage, int lane, u
   for (int it = 0; it < 8; ++it) {
     v[it] = make_uint4(0u, 0u, 0u, 0u);
     if (((rows.ok >> it) & 1u) && c < valid_chunks)
-      v[it] = *reinterpret_cast<const uint4*>(src_base + (long long)rows.row[it] * pitch_bytes + c * 16);
+      v[it] = ld_global_cg_v4(src_base + (long long)rows.row[it] * pitch_bytes + c * 16);
   }
   __syncwarp();
 #pragma unroll
@@ -144,7 +152,7 @@ struct EpiStoreMaps {
 };
 
 template <int BLOCK_N>
-__device__ __forceinline__ void epilogue_tile(const LinearParams& p, const EpiStoreMaps& maps, uint32_t tmem_base, int acc,
+__device__ __forceinline__ void epilogue_tile(const LinearParams& p, const EpiStoreMaps& maps, uint32_t tmem_base, uint32_t acc_col,
                                               int m_blk, int n_blk, int lane_group, int col_part, int lane, uint32_t stage) {
   constexpr int kBlockM = kEpiBlockM;
   // the two column parts of a tile: halves, except BLOCK_N = 192 -> 128 + 64 (whole 64-column chunks per warp)
@@ -200,8 +208,8 @@ __device__ __forceinline__ void epilogue_tile(const LinearParams& p, const EpiSt
       __syncwarp();
     }
     uint32_t v0[32], v1[32];
-    tmem_ld32(tmem_addr(tmem_base, lane_group * 32, acc * BLOCK_N + col_in_tile), v0);
-    tmem_ld32(tmem_addr(tmem_base, lane_group * 32, acc * BLOCK_N + col_in_tile + 32), v1);
+    tmem_ld32(tmem_addr(tmem_base, lane_group * 32, acc_col + col_in_tile), v0);
+    tmem_ld32(tmem_addr(tmem_base, lane_group * 32, acc_col + col_in_tile + 32), v1);
     if (n0 >= p.N) {  // warp-uniform: nothing to write for this chunk
       tmem_ld_wait();
       continue;

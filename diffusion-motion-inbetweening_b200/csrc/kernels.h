@@ -42,6 +42,17 @@ struct LinearParams {
   const float2* ln_stats;
   const float* ln_gamma;
   const float* ln_beta;
+  // ---- chained launches only (gemm_chain.cu) ----
+  // ... or from the 16 partial statistics per row a producer epilogue published (stats_out below) instead of ln_stats
+  const float2* ln_partials;
+  // LayerNorm folded into THIS linear layer (the A operand is the un-normalised v, the W operand is W * gamma):
+  //   LN(v) W^T = rstd * (v (W.gamma)^T - mean * c) + d,   c[n] = sum_k W[n,k] gamma[k],  d[n] = sum_k W[n,k] beta[k] + b[n]
+  // fold_stats: [rows][16] partial (mean, M2) of the A rows (16 x 32 columns); fold_c: [N]; `bias` carries d.
+  const float2* fold_stats;
+  const float* fold_c;
+  // publish the partial statistics of the OUTPUT rows: stats_out[row * 16 + (col / 32)] = (mean, sum of squared
+  // deviations) over the 32 output columns starting at col (N must be 512); consumed by ln_partials / fold_stats
+  float2* stats_out;
   const __nv_bfloat16* res_hi;  // the same residual as bf16 hi/lo planes [rows, ld_res_bf] (x = hi + lo), or null:
   const __nv_bfloat16* res_lo;  // lets LayerNorm skip its fp32 output (the planes are what the next GEMM reads anyway)
   int ld_res_bf;
@@ -75,6 +86,30 @@ cudaError_t configure_linear2_kernels();
 cudaError_t launch_linear_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                const CUtensorMap& w_lo, const LinearParams& p, int block_n, int num_sms,
                                cudaStream_t stream, const LinearStoreMaps* st = nullptr);
+
+// A chain of linear layers in ONE persistent launch (gemm_chain.cu): the tiles of all phases form one list walked by
+// the 74 CTA pairs; a tile whose A rows are produced by an earlier phase of the same launch waits on a per-row-pair
+// counter the producing epilogues bump.  Removes the kernel boundaries and the per-kernel tile quantisation.
+constexpr int kMaxChainPhases = 4;
+struct ChainPhaseInfo {
+  LinearParams p;
+  int block_n;                 // 256 (the epilogue distributes the eight 32-column slices of a tile over its warps)
+  int num_m_pairs, num_n_blocks, num_k_blocks;
+  int tile_begin, tile_end;    // global tile index range of this phase (tile = m_pair * num_n_blocks + n_blk)
+  int* wait_ctr;               // [num_m_pairs] or null: A rows of pair m are complete when wait_ctr[m] >= wait_target
+  int wait_target;
+  int* done_ctr;               // [num_m_pairs] or null: each CTA adds 1 once its half of a tile is in memory
+  int publish_now;             // 1: bump done_ctr as soon as a tile's stores have landed (the warp waits for them); 0: at its next tile
+};
+struct alignas(128) ChainPhaseDesc {
+  CUtensorMap a_hi, a_lo, w_hi, w_lo, o_hi, o_lo, o_f32;
+  ChainPhaseInfo info;
+};
+cudaError_t configure_linear_chain_kernel();
+// phases: device array; returns cudaErrorInvalidConfiguration if `num_sms / 2` clusters cannot be co-resident
+cudaError_t launch_linear_chain(const ChainPhaseDesc* phases_dev, int num_phases, int total_tiles, int num_sms,
+                                cudaStream_t stream, long long* dbg = nullptr);
+int linear_chain_max_clusters(int num_sms);
 
 // Linear + residual + LayerNorm over full 512-wide rows (out-proj + norm1, linear2 + norm2).   (gemm2_ln.cu)
 struct LinearLnParams {
@@ -228,6 +263,9 @@ cudaError_t launch_fill_normal_ref(float* out, int B, size_t per_sample, unsigne
                                    unsigned long long stream_id, unsigned long long sample_offset, cudaStream_t stream);
 cudaError_t launch_set_int(int* p, int v, cudaStream_t stream);
 
+// LayerNorm folded into its consumer: Wf = W * gamma (fp32 [N,K]), c[n] = sum_k Wf[n,k], d[n] = sum_k W[n,k] beta[k] + bias[n]
+cudaError_t launch_fold_ln(const float* W, int N, int K, const float* gamma, const float* beta, const float* bias, float* Wf,
+                           float* c, float* d, cudaStream_t stream);
 // fp32 [rows, cols] -> bf16 planes [rows, ld] (zero padded columns)
 cudaError_t launch_split_planes(const float* in, int rows, int cols, int ld_in, __nv_bfloat16* hi, __nv_bfloat16* lo,
                                 int ld_out, cudaStream_t stream);

@@ -49,7 +49,7 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return make_tmap_2d(out, base, 2, rows, cols, ld, box_cols, box_rows);
 }
 
-// elem_bytes: 2 (bf16) or 4 (fp32); the box must be exactly one 128-byte swizzle row wide
+// elem_bytes: 2 (bf16) or 4 (fp32); the box is one swizzle row wide: 128 bytes (SWIZZLE_128B) or 64 bytes (SWIZZLE_64B)
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_cols, uint32_t box_rows) {
   PFN_encodeTiled fn = get_encode_fn();
@@ -57,7 +57,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t ro
     set_last_error("cuTensorMapEncodeTiled not available from the driver");
     return 1;
   }
-  if ((ld * elem_bytes) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) % 16) != 0 || box_cols * elem_bytes != 128 ||
+  if ((ld * elem_bytes) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) % 16) != 0 || (box_cols * elem_bytes != 128 && box_cols * elem_bytes != 64) ||
       box_rows > 256 || (elem_bytes != 2 && elem_bytes != 4)) {
     set_last_error("make_tmap_2d: bad geometry (ld=%llu box=%ux%u)", (unsigned long long)ld, box_cols, box_rows);
     return 1;
@@ -67,7 +67,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t ro
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols * elem_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed: CUresult %d (rows=%llu cols=%llu ld=%llu box=%ux%u)", (int)r,

@@ -188,13 +188,19 @@ class Engine:
         with torch.cuda.device(self.device):
             capi.check(self.lib.cmdi_profile_pass(self._h, batch, int(cfg), int(repeats), ms, cap, ctypes.byref(count), _stream_ptr(self.device)),
                        "cmdi_profile_pass")
-        fused = count.value == 2 + 5 * self.cfg.num_layers + 1
-        per_layer = ["qkv", "attention", "out_proj_ln1", "ffn1", "ffn2_ln2"] if fused else \
-            ["qkv", "attention", "out_proj", "ln1", "ffn1", "ffn2", "ln2"]
-        names = ["token_rows", "frame_embed"]
-        for _ in range(self.cfg.num_layers):
-            names += per_layer
-        names += ["out_head"]
+        nl = self.cfg.num_layers
+        if count.value == 3 + 2 * nl:  # chained path: token rows, frame embedding, QKV_0, then {attention, chain} per layer
+            names = ["token_rows", "frame_embed", "qkv"]
+            for l in range(nl):
+                names += ["attention", "chain" if l + 1 < nl else "chain_last"]
+        else:
+            fused = count.value == 2 + 5 * nl + 1
+            per_layer = ["qkv", "attention", "out_proj_ln1", "ffn1", "ffn2_ln2"] if fused else \
+                ["qkv", "attention", "out_proj", "ln1", "ffn1", "ffn2", "ln2"]
+            names = ["token_rows", "frame_embed"]
+            for _ in range(nl):
+                names += per_layer
+            names += ["out_head"]
         return list(zip(names, [ms[i] for i in range(count.value)]))
 
     # kernel-level entry points for the parity tests -------------------------------------------------
