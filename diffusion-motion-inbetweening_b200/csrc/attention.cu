@@ -43,14 +43,6 @@ constexpr uint32_t kColS = 0, kColPHi = 0, kColPLo = 208, kColO = 320, kTmemCols
 // key chunks (16 keys each) per half: half 0 -> chunks [0,7), half 1 -> chunks [7,13)
 constexpr int kChunks0 = 7, kChunks1 = 6;
 
-struct __align__(8) AttnBarriers {
-  uint64_t qk_full[2], vhi_full, vlo_full, s_full, p_full, o_full;
-  uint32_t tmem_base;
-  uint32_t pad;
-  float red_max[2][128];
-  float red_sum[2][128];
-};
-
 __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -97,220 +89,6 @@ __device__ __forceinline__ float softmax_half(uint32_t trow, int S, bool split, 
     if (split) tmem_st8(trow + kColPLo + (CHUNK0 + c) * 8, pl);
   }
   return sum;
-}
-
-__global__ void __launch_bounds__(kThreads, 1)
-attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
-                 const __grid_constant__ CUtensorMap map_kv_hi, const __grid_constant__ CUtensorMap map_kv_lo,
-                 const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
-                 const AttnParams p) {
-  griddep_launch_dependents();
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(smem + kSmemTiles);
-
-  const int warp_idx = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int qtile = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
-  const int S = p.seq_len;
-  const bool split = (p.nsplit == 3);
-  const int row0 = seq * S;  // first token row of this sequence
-  const int q_col = head * kHeadDim;
-  const int k_col = p.num_heads * kHeadDim + head * kHeadDim;
-  const int v_col = 2 * p.num_heads * kHeadDim + head * kHeadDim;
-
-  if (warp_idx == 0 && lane == 0) {
-    tma_prefetch_desc(&map_q_hi);
-    tma_prefetch_desc(&map_kv_hi);
-    mbar_init(&bars->qk_full[0], 1);
-    mbar_init(&bars->qk_full[1], 1);
-    mbar_init(&bars->vhi_full, 1);
-    mbar_init(&bars->vlo_full, 1);
-    mbar_init(&bars->s_full, 1);
-    mbar_init(&bars->p_full, kNumSoftmaxWarps * 32);
-    mbar_init(&bars->o_full, 1);
-    fence_barrier_init();
-  }
-  if (warp_idx == 1) {
-    tmem_alloc(&bars->tmem_base, kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
-  griddep_wait();
-
-  if (warp_idx == 0) {
-    if (lane == 0) {
-      // Q + K, one barrier per 64-wide head-dim block so the first MMAs start after half the bytes
-      for (int j = 0; j < 2; ++j) {
-        mbar_arrive_expect_tx(&bars->qk_full[j], (split ? 2 : 1) * (kQBlockBytes + kKVBlockBytes));
-        tma_load_2d(smem + kOffQHi + j * kQBlockBytes, &map_q_hi, &bars->qk_full[j], q_col + j * 64, row0 + qtile * kQTile);
-        tma_load_2d(smem + kOffKHi + j * kKVBlockBytes, &map_kv_hi, &bars->qk_full[j], k_col + j * 64, row0);
-        if (split) {
-          tma_load_2d(smem + kOffQLo + j * kQBlockBytes, &map_q_lo, &bars->qk_full[j], q_col + j * 64, row0 + qtile * kQTile);
-          tma_load_2d(smem + kOffKLo + j * kKVBlockBytes, &map_kv_lo, &bars->qk_full[j], k_col + j * 64, row0);
-        }
-      }
-      // V_hi (own buffer, lands while S is being computed)
-      mbar_arrive_expect_tx(&bars->vhi_full, kKVPlane);
-      for (int j = 0; j < 2; ++j)
-        tma_load_2d(smem + kOffVHi + j * kKVBlockBytes, &map_kv_hi, &bars->vhi_full, v_col + j * 64, row0);
-      if (split) {
-        // V_lo overwrites K once the S MMAs have consumed it
-        mbar_wait(&bars->s_full, 0);
-        mbar_arrive_expect_tx(&bars->vlo_full, kKVPlane);
-        for (int j = 0; j < 2; ++j)
-          tma_load_2d(smem + kOffVLo + j * kKVBlockBytes, &map_kv_lo, &bars->vlo_full, v_col + j * 64, row0);
-      }
-    }
-    __syncwarp();
-  } else if (warp_idx == 1) {
-    if (lane == 0) {
-      const uint32_t sbase = smem_u32(smem);
-      // ---------------- S = Q K^T ----------------
-      constexpr uint32_t idesc_s = make_idesc_bf16(kQTile, kKeyPad, 0);
-      uint32_t accum = 0;
-      const int nterms = split ? 3 : 1;
-      long long tm[8];
-      tm[0] = clock64();
-      for (int j = 0; j < 2; ++j) {
-        mbar_wait(&bars->qk_full[j], 0);
-        tm[1 + j] = clock64();
-        tc_fence_after();
-        for (int term = 0; term < nterms; ++term) {
-          // split order: Q_lo*K_hi, Q_hi*K_lo, Q_hi*K_hi ; fast mode: Q_hi*K_hi
-          const uint32_t qo = (split && term == 0) ? kOffQLo : kOffQHi;
-          const uint32_t ko = (split && term == 1) ? kOffKLo : kOffKHi;
-          const uint64_t da = make_desc_kmajor_sw128(sbase + qo + j * kQBlockBytes);
-          const uint64_t db = make_desc_kmajor_sw128(sbase + ko + j * kKVBlockBytes);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            umma_ss(tmem_base + kColS, desc_advance(da, kk * 32), desc_advance(db, kk * 32), idesc_s, accum);
-            accum = 1;
-          }
-        }
-      }
-      umma_commit(&bars->s_full);
-      tm[3] = clock64();
-      // ---------------- O = P V ----------------
-      constexpr uint32_t idesc_o = make_idesc_bf16(kQTile, kHeadDim, 1);
-      mbar_wait(&bars->p_full, 0);
-      tm[4] = clock64();
-      mbar_wait(&bars->vhi_full, 0);
-      tm[5] = clock64();
-      tc_fence_after();
-      const uint64_t dv_hi = make_desc_mnmajor_sw128(sbase + kOffVHi, kKVBlockBytes);
-      accum = 0;
-      if (split) {
-#pragma unroll 1
-        for (int ks = 0; ks < kKeyPad / 16; ++ks) {
-          umma_ts(tmem_base + kColO, tmem_base + kColPLo + ks * 8, desc_advance(dv_hi, ks * 2048), idesc_o, accum);
-          accum = 1;
-        }
-      }
-#pragma unroll 1
-      for (int ks = 0; ks < kKeyPad / 16; ++ks) {
-        umma_ts(tmem_base + kColO, tmem_base + kColPHi + ks * 8, desc_advance(dv_hi, ks * 2048), idesc_o, accum);
-        accum = 1;
-      }
-      tm[6] = clock64();
-      if (split) {
-        mbar_wait(&bars->vlo_full, 0);
-        tc_fence_after();
-        const uint64_t dv_lo = make_desc_mnmajor_sw128(sbase + kOffVLo, kKVBlockBytes);
-#pragma unroll 1
-        for (int ks = 0; ks < kKeyPad / 16; ++ks)
-          umma_ts(tmem_base + kColO, tmem_base + kColPHi + ks * 8, desc_advance(dv_lo, ks * 2048), idesc_o, 1u);
-      }
-      umma_commit(&bars->o_full);
-      tm[7] = clock64();
-      if (p.dbg_cycles) {
-        long long* d = p.dbg_cycles + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16;
-        for (int i = 1; i < 8; ++i) d[i - 1] = tm[i] - tm[0];
-      }
-    }
-    __syncwarp();
-  } else {
-    // ---------------- softmax: two threads per query row ----------------
-    const int sw = warp_idx - 2;
-    const int lane_group = warp_idx & 3;
-    const int half = sw >> 2;
-    const int row = lane_group * 32 + lane;
-    const uint32_t trow = tmem_base + ((uint32_t)(lane_group * 32) << 16);
-    const float c_scale = 0.08838834764831845f * 1.4426950408889634f;  // 1/sqrt(128) * log2(e)
-
-    const long long ts0 = clock64();
-    mbar_wait(&bars->s_full, 0);
-    const long long ts1 = clock64();
-    tc_fence_after();
-    float sum;
-    if (half == 0) {
-      sum = softmax_half<0, kChunks0>(trow, S, split, c_scale, bars->red_max, 0, row, p.trunc_split != 0);
-    } else {
-      sum = softmax_half<kChunks0, kChunks1>(trow, S, split, c_scale, bars->red_max, 1, row, p.trunc_split != 0);
-    }
-    bars->red_sum[half][row] = sum;
-    tmem_st_wait();
-    tc_fence_before();
-    mbar_arrive(&bars->p_full);
-    named_barrier_sync(1, kNumSoftmaxWarps * 32);  // red_sum of both halves visible
-    const float inv = 1.0f / (bars->red_sum[0][row] + bars->red_sum[1][row]);
-
-    // ---------------- output: this thread's row, 64 of the 128 head-dim columns ----------------
-    const long long ts2 = clock64();
-    mbar_wait(&bars->o_full, 0);
-    const long long ts3 = clock64();
-    tc_fence_after();
-    // all MMAs are complete: the Q tile region is free and becomes the store-staging area (8 x 4 KB)
-    const uint32_t stage = smem_u32(smem + kOffQHi + sw * kEpiStageBytes);
-    RowSlots rows;
-    rows.ok = 0;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int qp = qtile * kQTile + lane_group * 32 + it * 4 + (lane >> 3);
-      rows.row[it] = (qp < S) ? (row0 + qp) : 0;
-      if (qp < S) rows.ok |= 1u << it;
-    }
-    const long long pitch = (long long)p.ld_out * 2;
-    uint32_t v0[32], v1[32];
-    tmem_ld32(trow + kColO + half * 64, v0);
-    tmem_ld32(trow + kColO + half * 64 + 32, v1);
-    tmem_ld_wait();
-    uint32_t hw[32], lw[32];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      split_bf16x2(__uint_as_float(v0[2 * j]) * inv, __uint_as_float(v0[2 * j + 1]) * inv, hw[j], lw[j]);
-      split_bf16x2(__uint_as_float(v1[2 * j]) * inv, __uint_as_float(v1[2 * j + 1]) * inv, hw[16 + j], lw[16 + j]);
-    }
-    const int group_row0 = qtile * kQTile + lane_group * 32;  // first query of this warp's 32 rows
-    if (group_row0 + 32 <= S) {
-      // all 32 rows belong to this sequence: one bulk tensor store per plane straight from the staging tile
-      store_block_tma(stage, lane, hw, &map_o_hi, head * kHeadDim + half * 64, row0 + group_row0);
-      if (p.nsplit_out == 3) store_block_tma(stage, lane, lw, &map_o_lo, head * kHeadDim + half * 64, row0 + group_row0);
-      if (lane == 0) tma_store_wait_read();
-    } else {
-      // the group straddles the end of the sequence: masked coalesced stores
-      char* dst_hi = reinterpret_cast<char*>(p.out_hi + head * kHeadDim + half * 64);
-      store_block_coalesced(stage, lane, hw, dst_hi, rows, pitch, 8, 1, 0);
-      if (p.nsplit_out == 3) {
-        char* dst_lo = reinterpret_cast<char*>(p.out_lo + head * kHeadDim + half * 64);
-        store_block_coalesced(stage, lane, lw, dst_lo, rows, pitch, 8, 1, 0);
-      }
-    }
-    if (p.dbg_cycles && sw == 0 && lane == 0) {
-      long long* d = p.dbg_cycles + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16;
-      d[8] = ts1 - ts0; d[9] = ts2 - ts1; d[10] = ts3 - ts2; d[11] = clock64() - ts3;
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp_idx == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -615,12 +393,7 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap map_q_hi, const 
 
 }  // namespace
 
-bool g_attn_persistent = true;  // CMDI_ATTN=oneshot selects the CTA-per-item kernel
-
 cudaError_t configure_attention_kernel() {
-  cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(1024 + kSmemTiles + sizeof(AttnBarriers)));
-  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(attention_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)(1024 + kSmemTiles + sizeof(AttnBarriers2)));
 }
@@ -632,22 +405,17 @@ cudaError_t launch_attention(const CUtensorMap& q_hi, const CUtensorMap& q_lo, c
     set_last_error("launch_attention: unsupported seq_len=%d nsplit=%d", p.seq_len, p.nsplit);
     return cudaErrorInvalidValue;
   }
-  if (g_attn_persistent) {
-    static int num_sms = 0;
-    if (num_sms == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    const int q_tiles = (p.seq_len + kQTile - 1) / kQTile;
-    const int num_items = q_tiles * p.num_heads * p.num_seqs;
-    const size_t smem2 = 1024 + kSmemTiles + sizeof(AttnBarriers2);
-    return launch_kernel(attention_persistent_kernel, dim3(num_items < num_sms ? num_items : num_sms), dim3(kThreads), smem2,
-                         stream, q_hi, q_lo, kv_hi, kv_lo, o_hi, o_lo, p, num_items, q_tiles);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const size_t smem = 1024 + kSmemTiles + sizeof(AttnBarriers);
-  dim3 grid((p.seq_len + kQTile - 1) / kQTile, p.num_heads, p.num_seqs);
-  return launch_kernel(attention_kernel, grid, dim3(kThreads), smem, stream, q_hi, q_lo, kv_hi, kv_lo, o_hi, o_lo, p);
+  const int q_tiles = (p.seq_len + kQTile - 1) / kQTile;
+  const int num_items = q_tiles * p.num_heads * p.num_seqs;
+  const size_t smem2 = 1024 + kSmemTiles + sizeof(AttnBarriers2);
+  return launch_kernel(attention_persistent_kernel, dim3(num_items < num_sms ? num_items : num_sms), dim3(kThreads), smem2,
+                       stream, q_hi, q_lo, kv_hi, kv_lo, o_hi, o_lo, p, num_items, q_tiles);
 }
 
 }  // namespace cmdi

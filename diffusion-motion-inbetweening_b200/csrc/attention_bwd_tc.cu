@@ -463,7 +463,6 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap qkv_t_hi, const __gr
 
 }  // namespace
 
-bool g_attn_bwd_tc = true;  // CMDI_ATTN_BWD=simt selects the fp32 CUDA-core kernel of backward.cu
 
 cudaError_t configure_attention_bwd_tc_kernel() {
   return cudaFuncSetAttribute(attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

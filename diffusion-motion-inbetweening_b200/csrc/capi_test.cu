@@ -62,14 +62,13 @@ extern "C" int cmdi_test_linear(const float* A, const float* W, const float* bia
   CK(w_lo.alloc((size_t)Np * Kp * 2));
   CK(launch_split_planes(A, M, K, K, a_hi.as<__nv_bfloat16>(), a_lo.as<__nv_bfloat16>(), Kp, stream));
   CK(launch_split_planes(W, N, K, K, w_hi.as<__nv_bfloat16>(), w_lo.as<__nv_bfloat16>(), Kp, stream));
-  const bool pair = block_n < 0;  // negative block_n selects the CTA-pair kernel
-  if (pair) block_n = -block_n;
+  const bool pair = true;  // every linear layer runs on the CTA-pair kernel (the sign of block_n is accepted and ignored)
+  if (block_n < 0) block_n = -block_n;
   CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
   if (make_tmap_bf16_2d(&ma_hi, a_hi.p, Mp, Kp, Kp, 64, 128)) return 1;
   if (make_tmap_bf16_2d(&ma_lo, a_lo.p, Mp, Kp, Kp, 64, 128)) return 1;
   if (make_tmap_bf16_2d(&mw_hi, w_hi.p, Np, Kp, Kp, 64, pair ? block_n / 2 : block_n)) return 1;
   if (make_tmap_bf16_2d(&mw_lo, w_lo.p, Np, Kp, Kp, 64, pair ? block_n / 2 : block_n)) return 1;
-  CK(configure_linear_kernels());
   CUtensorMap mc_f32;
   if (make_tmap_2d(&mc_f32, C, 4, M, N, N, 32, 32)) return 1;
   LinearStoreMaps stm;
@@ -90,14 +89,6 @@ extern "C" int cmdi_test_linear(const float* A, const float* W, const float* bia
     CK(launch_layernorm512(residual, ln_g.as<float>(), ln_b.as<float>(), 1e-5f, M, nullptr, nullptr, nullptr, stream, ln_s.as<float2>()));
     p.residual = nullptr; p.ln_src = residual; p.ld_ln = N; p.ln_stats = ln_s.as<float2>();
     p.ln_gamma = ln_g.as<float>(); p.ln_beta = ln_b.as<float>();
-  }
-  DevBuf r_hi, r_lo;
-  if (residual && getenv("CMDI_TEST_RES_PLANES")) {
-    // the same residual handed over as bf16 hi/lo planes (what the engine does between encoder sublayers)
-    CK(r_hi.alloc((size_t)M * N * 2));
-    CK(r_lo.alloc((size_t)M * N * 2));
-    CK(launch_split_planes(residual, M, N, N, r_hi.as<__nv_bfloat16>(), r_lo.as<__nv_bfloat16>(), N, stream));
-    p.residual = nullptr; p.res_hi = r_hi.as<__nv_bfloat16>(); p.res_lo = r_lo.as<__nv_bfloat16>(); p.ld_res_bf = N;
   }
   p.act = act; p.rowmap = ROWMAP_IDENTITY;
   p.out_f32 = C; p.ld_f32 = N;
@@ -140,8 +131,6 @@ extern "C" int cmdi_test_linear(const float* A, const float* W, const float* bia
              acc[0] / n_lead, acc[1] / n_lead, acc[2] / n_lead, acc[4] / n_all, acc[5] / n_all, acc[6] / n_all, acc[7] / n_all, n_lead, n_all);
       fflush(stdout);
     }
-  } else {
-    CK(launch_linear(ma_hi, ma_lo, mw_hi, mw_lo, p, block_n, num_sms_of_current_device(), stream, stp));
   }
   CK(cudaStreamSynchronize(stream));  // staging buffers are freed on return
   return 0;
@@ -196,7 +185,7 @@ extern "C" int cmdi_test_attention(const float* qkv, float* O, int num_seqs, int
     CK(cudaStreamSynchronize(stream));
     CK(cudaMemcpy(h.data(), adbg.p, h.size() * 8, cudaMemcpyDeviceToHost));
     double a[16] = {0};
-    if (g_attn_persistent) {
+    {
       // persistent kernel: per-CTA sums over its items; slot 7 = item count
       double items = 0;
       for (int c = 0; c < nctas; ++c) items += (double)h[(size_t)c * 16 + 7];
@@ -221,15 +210,6 @@ extern "C" int cmdi_test_attention(const float* qkv, float* O, int num_seqs, int
       fflush(stdout);
       p.dbg_cycles = nullptr;
     }
-  }
-  if (p.dbg_cycles) {
-    std::vector<long long> h((size_t)nctas * 16);
-    CK(cudaMemcpy(h.data(), adbg.p, h.size() * 8, cudaMemcpyDeviceToHost));
-    double a[16] = {0};
-    for (int c = 0; c < nctas; ++c) for (int k = 0; k < 12; ++k) a[k] += (double)h[(size_t)c * 16 + k] / nctas;
-    printf("attn dbg cycles (mean per CTA, MMA thread, since start): qk0=%.0f qk1=%.0f S-issued=%.0f P-ready=%.0f Vhi=%.0f PV1-issued=%.0f all-issued=%.0f | softmax warp: wait_S=%.0f softmax=%.0f wait_O=%.0f store=%.0f\n",
-           a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[8], a[9], a[10], a[11]);
-    fflush(stdout);
   }
   // O = hi + lo (fp32) for the test
   {
@@ -268,54 +248,6 @@ extern "C" int cmdi_test_normal(float* out, int B, long long per_sample, unsigne
   return 0;
 }
 
-extern "C" int cmdi_test_linear_ln(const float* A, const float* W, const float* bias, const float* residual, const float* gamma,
-                                   const float* beta, float* out, int M, int K, int precision, void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const int N = 512, Kp = round_up(K, 8), Mp = round_up(M, 256);
-  DevBuf a_hi, a_lo, w_hi, w_lo, o_hi, o_lo;
-  CK(a_hi.alloc((size_t)Mp * Kp * 2)); CK(a_lo.alloc((size_t)Mp * Kp * 2));
-  CK(w_hi.alloc((size_t)N * Kp * 2)); CK(w_lo.alloc((size_t)N * Kp * 2));
-  CK(o_hi.alloc((size_t)Mp * N * 2)); CK(o_lo.alloc((size_t)Mp * N * 2));
-  CK(launch_split_planes(A, M, K, K, a_hi.as<__nv_bfloat16>(), a_lo.as<__nv_bfloat16>(), Kp, stream));
-  CK(launch_split_planes(W, N, K, K, w_hi.as<__nv_bfloat16>(), w_lo.as<__nv_bfloat16>(), Kp, stream));
-  CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mo_hi, mo_lo, mo_f32;
-  if (make_tmap_bf16_2d(&ma_hi, a_hi.p, Mp, Kp, Kp, 64, 128)) return 1;
-  if (make_tmap_bf16_2d(&ma_lo, a_lo.p, Mp, Kp, Kp, 64, 128)) return 1;
-  if (make_tmap_bf16_2d(&mw_hi, w_hi.p, N, Kp, Kp, 64, 128)) return 1;
-  if (make_tmap_bf16_2d(&mw_lo, w_lo.p, N, Kp, Kp, 64, 128)) return 1;
-  if (make_tmap_bf16_2d(&mo_hi, o_hi.p, Mp, N, N, 64, 32)) return 1;
-  if (make_tmap_bf16_2d(&mo_lo, o_lo.p, Mp, N, N, 64, 32)) return 1;
-  if (make_tmap_2d(&mo_f32, out, 4, M, N, N, 32, 32)) return 1;
-  CK(configure_linear_ln_kernel());
-  LinearLnParams p{};
-  p.M = M; p.K = K; p.nsplit = precision; p.nsplit_out = 3; p.bias = bias; p.residual = residual; p.gamma = gamma; p.beta = beta;
-  p.eps = 1e-5f;
-  CK(launch_linear_ln(ma_hi, ma_lo, mw_hi, mw_lo, mo_hi, mo_lo, mo_f32, p, num_sms_of_current_device(), stream));
-  CK(cudaStreamSynchronize(stream));
-  // the bf16 planes must reproduce the fp32 output: report the worst |f32 - (hi + lo)| through last_error when it is off
-  {
-    std::vector<uint16_t> hh((size_t)M * N), hl((size_t)M * N);
-    std::vector<float> ho((size_t)M * N);
-    CK(cudaMemcpy(hh.data(), o_hi.p, hh.size() * 2, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(hl.data(), o_lo.p, hl.size() * 2, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(ho.data(), out, ho.size() * 4, cudaMemcpyDeviceToHost));
-    double worst = 0;
-    for (size_t i = 0; i < ho.size(); ++i) {
-      uint32_t a = (uint32_t)hh[i] << 16, b = (uint32_t)hl[i] << 16;
-      float fa, fb;
-      memcpy(&fa, &a, 4);
-      memcpy(&fb, &b, 4);
-      const double d = fabs((double)ho[i] - ((double)fa + (double)fb)), tol = 1.6e-5 * fabs((double)ho[i]) + 1e-30;
-      if (d > tol && d > worst) worst = d;
-    }
-    if (worst > 0) {
-      set_last_error("linear_ln: bf16 planes disagree with the fp32 output by %.3e", worst);
-      return 1;
-    }
-  }
-  return 0;
-}
-
 extern "C" int cmdi_test_layernorm_bwd(const float* dy, const float* v, const float* gamma, float* dv, int rows, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   DevBuf hi;
@@ -344,7 +276,7 @@ extern "C" int cmdi_test_attention_bwd(const float* qkv, const float* dO, float*
   p.do_hi = d_hi.as<__nv_bfloat16>(); p.do_lo = d_lo.as<__nv_bfloat16>(); p.ld_do = ldo;
   p.dqkv_hi = g_hi.as<__nv_bfloat16>(); p.dqkv_lo = g_lo.as<__nv_bfloat16>();
   p.ld_dqkv = ld; p.nsplit = 3; p.stats = stats.as<float2>();
-  if (g_attn_bwd_tc && !getenv("CMDI_TEST_ATTN_BWD_SIMT")) {
+  if (!getenv("CMDI_TEST_ATTN_BWD_SIMT")) {
     CUtensorMap qt_hi, qt_lo, qf_hi, qf_lo, dt_hi, dt_lo, df_hi, df_lo, o_hi, o_lo;
     if (make_tmap_bf16_2d(&qt_hi, q_hi.p, rows_p, ld, ld, 64, 128)) return 1;
     if (make_tmap_bf16_2d(&qt_lo, q_lo.p, rows_p, ld, ld, 64, 128)) return 1;

@@ -602,7 +602,7 @@ inline int grid_for(size_t n, int block) {
 
 cudaError_t launch_layernorm512(const float* v, const float* gamma, const float* beta, float eps, int rows, float* out_f32,
                                 __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream, float2* stats_out) {
-  return launch_kernel_ex(g_use_pdl || g_pdl_light, layernorm512_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, v, gamma, beta, eps,
+  return launch_kernel(layernorm512_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, v, gamma, beta, eps,
                           rows, out_f32, out_hi, out_lo, stats_out);
 }
 

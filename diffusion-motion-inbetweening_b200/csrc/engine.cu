@@ -53,7 +53,6 @@ struct Planes {  // a bf16 hi/lo operand: [rows, ld] row-major, with TMA maps fo
   CUtensorMap pair_hi{}, pair_lo{};  // same planes, box height halved: W operand of the CTA-pair kernel
   CUtensorMap st_hi{}, st_lo{};      // same planes as a TMA-store target: box {64, 32}
   CUtensorMap st32_hi{}, st32_lo{};  // ... box {32, 32}, 64-byte swizzle (32-column slices of the chained epilogue)
-  CUtensorMap ln_hi{}, ln_lo{};      // W operand of the fused linear+LayerNorm kernel: box {64, 128}
 };
 
 struct LayerW {
@@ -98,16 +97,12 @@ struct cmdi_engine {
   int nsplit = 3;
   int bn_qkv = kBnWide;
   int debug = 0, bn_wide = kBnWide, bn_narrow = kBnNarrow;  // CMDI_DEBUG / CMDI_BN_WIDE / CMDI_BN_NARROW (bring-up knobs)
-  bool fuse_ln = false;   // CMDI_FUSE_LN=1: out-proj+norm1 and linear2+norm2 as one kernel each (correct, but 2-10% slower at B=64: its 3-pass epilogue is exposed with 50 tiles on 74 clusters; kept for larger batches / later tuning)
   int steps_per_graph = 1;  // CMDI_GRAPH_STEPS: consecutive steps captured into one graph (10 and 50 measured: no gain over 1)
   bool no_graph = false;    // CMDI_NO_GRAPH=1: plain stream launches even when the caller asks for graph replay
   int attn_prefetch_q = 1;   // CMDI_ATTN_PREFETCH=0
   int attn_trunc_split = 0;  // CMDI_ATTN_SPLIT=trunc
-  bool ln_residual = true;   // CMDI_RES=f32: LayerNorm also writes its fp32 output and the next epilogue reads that back
   float2 *ln_stats1 = nullptr, *ln_stats2 = nullptr;  // (mean, rstd) per token row published by norm1 / norm2
-  bool plane_residual = false;  // CMDI_RES=planes: residual stream from the bf16 hi/lo planes, LayerNorm skips its fp32 copy (+1.7 % steps/s, but the CFG-amplified error grows from 4.2e-5 to 7.1e-5 against the 1e-4 gate: off)
   bool tma_store = true;  // CMDI_EPI=stg selects the coalesced-STG epilogue everywhere
-  bool use_pair = true;  // CTA-pair (cta_group::2) linear kernels; CMDI_GEMM=single selects the 1-CTA kernels
   int D = 263, D_pad = 264, L = 196, S = 197, ff = 1024, H = 4, layers = 8, maxB = 0;
   int max_seqs = 0, seq_rows = 0, seq_rows_pad = 0, frame_rows = 0, frame_rows_pad = 0;
   std::vector<void*> allocs;
@@ -135,7 +130,7 @@ struct cmdi_engine {
   Planes xseq_p, x1_p, qkv_p, attn_p, ffh_p;
   CUtensorMap q_map_hi{}, q_map_lo{}, kv_map_hi{}, kv_map_lo{};
   CUtensorMap vsum_st{};  // fp32 TMA-store target for the pre-LayerNorm sums
-  CUtensorMap xseq_st{}, x1_st{};  // fp32 TMA-store targets of the fused linear+LayerNorm kernel
+  CUtensorMap xseq_st{}, x1_st{};  // fp32 TMA-store targets: xseq (backward pass), x1 (v1 of the chained forward path)
   uint8_t* obs_mask = nullptr;
   float *cond_emb = nullptr, *cond_proj = nullptr, *text_scale = nullptr;
   int* step_ctr = nullptr;  // [2]: step index, block-arrival counter
@@ -194,8 +189,6 @@ int alloc_planes(cmdi_engine* e, Planes* pl, int rows, int cols, int ld, int box
   CKI(make_tmap_bf16_2d(&pl->st_lo, pl->lo, rows, cols, ld, 64, 32));
   CKI(make_tmap_bf16_2d(&pl->st32_hi, pl->hi, rows, cols, ld, 32, 32));
   CKI(make_tmap_bf16_2d(&pl->st32_lo, pl->lo, rows, cols, ld, 32, 32));
-  CKI(make_tmap_bf16_2d(&pl->ln_hi, pl->hi, rows, cols, ld, 64, 128));
-  CKI(make_tmap_bf16_2d(&pl->ln_lo, pl->lo, rows, cols, ld, 64, 128));
   return 0;
 }
 
@@ -245,11 +238,7 @@ int run_linear(cmdi_engine* e, const Planes& a, const Planes& w, const LinearPar
   if (out_planes) { st.hi = &out_planes->st_hi; st.lo = &out_planes->st_lo; }
   st.f32 = out_f32;
   const LinearStoreMaps* stp = (e->tma_store && (out_planes || out_f32)) ? &st : nullptr;
-  if (e->use_pair) {
-    CK(launch_linear_pair(a.map_hi, a.map_lo, w.pair_hi, w.pair_lo, p, block_n, e->num_sms, s, stp));
-  } else {
-    CK(launch_linear(a.map_hi, a.map_lo, w.map_hi, w.map_lo, p, block_n, e->num_sms, s, stp));
-  }
+  CK(launch_linear_pair(a.map_hi, a.map_lo, w.pair_hi, w.pair_lo, p, block_n, e->num_sms, s, stp));
   return 0;
 }
 
@@ -282,22 +271,17 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
   for (int r_ = 0; r_ < reps; ++r_) CK(launch_token_rows(tk, s));
   CKI(mark());
 
-  // bf16x3, unfused LayerNorm: the residual stream lives in the hi/lo planes only (x = hi + lo to 2^-17) -- LayerNorm
-  // and the frame embedding skip their fp32 copy, the next sublayer's epilogue adds the planes back
-  const bool plane_res = e->plane_residual && e->nsplit == 3 && !e->fuse_ln;
-  // default: LayerNorm writes only the bf16 planes and its row statistics; the sublayer that needs its fp32 output as
-  // the residual re-derives it in the epilogue from LayerNorm's input (bit-identical, 26 MB less traffic per LayerNorm)
-  const bool ln_res = e->ln_residual && !plane_res && !e->fuse_ln;
+  // LayerNorm writes only the bf16 planes and its row statistics; the sublayer that needs its fp32 output as the
+  // residual re-derives it in the epilogue from LayerNorm's input (bit-identical, 26 MB less traffic per LayerNorm)
   LinearParams p{};
   // frame embedding + positional encoding (mdm.py:271, :279-280)
   p.M = B * e->L; p.N = kDModel; p.K = e->D; p.nsplit = e->nsplit; p.bias = e->b_in; p.pos_enc = e->pe;
   p.rowmap = ROWMAP_FRAMES_TO_SEQ; p.frames = e->L; p.dup_row_offset = dup ? B * e->S : 0;
-  p.out_f32 = plane_res ? nullptr : e->xseq; p.ld_f32 = kDModel; p.out_hi = e->xseq_p.hi; p.out_lo = e->xseq_p.lo; p.ld_bf = kDModel;
+  p.out_f32 = e->xseq; p.ld_f32 = kDModel; p.out_hi = e->xseq_p.hi; p.out_lo = e->xseq_p.lo; p.ld_bf = kDModel;
   p.nsplit_out = e->nsplit;
   for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->x_state_p, e->w_in, p, kBnNarrow, s));
   CKI(mark());
 
-  const bool fuse_ln = e->fuse_ln && !stash;
   for (int l = 0; l < e->layers; ++l) {
     const LayerW& w = e->lw[l];
     LayerStash* ls = stash ? &(*stash)[l] : nullptr;  // guided steps keep what the backward pass needs, per layer
@@ -317,20 +301,11 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
     for (int r_ = 0; r_ < reps; ++r_) CK(launch_attention(ls ? ls->q_hi : e->q_map_hi, ls ? ls->q_lo : e->q_map_lo, ls ? ls->kv_hi : e->kv_map_hi,
                                                          ls ? ls->kv_lo : e->kv_map_lo, e->attn_p.st_hi, e->attn_p.st_lo, a, s));
     CKI(mark());
-    // out-proj + residual + LayerNorm1
-    if (fuse_ln) {
-      LinearLnParams o{};
-      o.M = M; o.K = kDModel; o.nsplit = e->nsplit; o.nsplit_out = e->nsplit; o.bias = w.bo; o.residual = e->xseq;
-      o.gamma = w.g1; o.beta = w.be1; o.eps = 1e-5f;
-      for (int r_ = 0; r_ < reps; ++r_)
-        CK(launch_linear_ln(e->attn_p.map_hi, e->attn_p.map_lo, w.wo.ln_hi, w.wo.ln_lo, e->x1_p.st_hi, e->x1_p.st_lo, e->x1_st, o,
-                            e->num_sms, s));
-      CKI(mark());
-    } else {
+    // out-proj + residual, then LayerNorm1
+    {
       LinearParams o{};
       o.M = M; o.N = kDModel; o.K = kDModel; o.nsplit = e->nsplit; o.bias = w.bo; o.residual = e->xseq; o.ld_res = kDModel;
-      if (plane_res) { o.residual = nullptr; o.res_hi = e->xseq_p.hi; o.res_lo = e->xseq_p.lo; o.ld_res_bf = kDModel; }
-      if (ln_res && l > 0) {
+      if (l > 0) {
         // residual = norm2 of the previous layer, from its input (in place when that is the shared vsum buffer)
         o.residual = nullptr; o.ln_src = stash ? (*stash)[l - 1].v2 : e->vsum; o.ld_ln = kDModel; o.ln_stats = e->ln_stats2;
         o.ln_gamma = e->lw[l - 1].g2; o.ln_beta = e->lw[l - 1].be2;
@@ -339,8 +314,7 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
       for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->attn_p, w.wo, o, kBnNarrow, s, nullptr, ls ? nullptr : &e->vsum_st));
       CKI(mark());
       for (int r_ = 0; r_ < reps; ++r_)
-        CK(launch_layernorm512(v1_out, w.g1, w.be1, 1e-5f, M, (plane_res || ln_res) ? nullptr : e->x1, e->x1_p.hi,
-                               e->nsplit == 3 ? e->x1_p.lo : nullptr, s, ln_res ? e->ln_stats1 : nullptr));
+        CK(launch_layernorm512(v1_out, w.g1, w.be1, 1e-5f, M, nullptr, e->x1_p.hi, e->nsplit == 3 ? e->x1_p.lo : nullptr, s, e->ln_stats1));
       CKI(mark());
     }
     // FFN
@@ -350,27 +324,15 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
     if (ls) { f1.out_f32 = ls->pre; f1.ld_f32 = e->ff; f1.f32_pre = 1; }  // pre-activation for the GELU backward
     for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->x1_p, w.w1, f1, kBnWide, s, &e->ffh_p));
     CKI(mark());
-    if (fuse_ln) {
-      LinearLnParams f2{};
-      f2.M = M; f2.K = e->ff; f2.nsplit = e->nsplit; f2.nsplit_out = e->nsplit; f2.bias = w.b2; f2.residual = e->x1;
-      f2.gamma = w.g2; f2.beta = w.be2; f2.eps = 1e-5f;
-      for (int r_ = 0; r_ < reps; ++r_)
-        CK(launch_linear_ln(e->ffh_p.map_hi, e->ffh_p.map_lo, w.w2.ln_hi, w.w2.ln_lo, e->xseq_p.st_hi, e->xseq_p.st_lo, e->xseq_st,
-                            f2, e->num_sms, s));
-      CKI(mark());
-    } else {
+    {
       LinearParams f2{};
-      f2.M = M; f2.N = kDModel; f2.K = e->ff; f2.nsplit = e->nsplit; f2.bias = w.b2; f2.residual = e->x1; f2.ld_res = kDModel;
-      if (plane_res) { f2.residual = nullptr; f2.res_hi = e->x1_p.hi; f2.res_lo = e->x1_p.lo; f2.ld_res_bf = kDModel; }
-      if (ln_res) {
-        f2.residual = nullptr; f2.ln_src = v1_out; f2.ld_ln = kDModel; f2.ln_stats = e->ln_stats1; f2.ln_gamma = w.g1; f2.ln_beta = w.be1;
-      }
+      f2.M = M; f2.N = kDModel; f2.K = e->ff; f2.nsplit = e->nsplit; f2.bias = w.b2;
+      f2.ln_src = v1_out; f2.ld_ln = kDModel; f2.ln_stats = e->ln_stats1; f2.ln_gamma = w.g1; f2.ln_beta = w.be1;
       f2.out_f32 = v2_out; f2.ld_f32 = kDModel; f2.nsplit_out = e->nsplit;
       for (int r_ = 0; r_ < reps; ++r_) CKI(run_linear(e, e->ffh_p, w.w2, f2, kBnNarrow, s, nullptr, ls ? nullptr : &e->vsum_st));
       CKI(mark());
       for (int r_ = 0; r_ < reps; ++r_)
-        CK(launch_layernorm512(v2_out, w.g2, w.be2, 1e-5f, M, (plane_res || ln_res) ? nullptr : e->xseq, e->xseq_p.hi,
-                               e->nsplit == 3 ? e->xseq_p.lo : nullptr, s, ln_res ? e->ln_stats2 : nullptr));
+        CK(launch_layernorm512(v2_out, w.g2, w.be2, 1e-5f, M, nullptr, e->xseq_p.hi, e->nsplit == 3 ? e->xseq_p.lo : nullptr, s, e->ln_stats2));
       CKI(mark());
     }
   }
@@ -383,7 +345,7 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
   return 0;
 }
 bool chain_eligible(const cmdi_engine* e) {
-  return e->use_chain && e->use_pair && e->tma_store && !e->fuse_ln && !e->plane_residual && e->debug == 0 && e->layers >= 1;
+  return e->use_chain && e->tma_store && e->debug == 0 && e->layers >= 1;
 }
 
 // Phase lists for `nseq` sequences: layer l = [out-proj_l, FFN1_l, FFN2_l, QKV_{l+1} | output head].
@@ -541,11 +503,6 @@ int run_denoiser_chain(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool ha
 
 int ensure_stash(cmdi_engine* e) {
   if (e->stash_ready) return 0;
-  if (e->S > 197 && !g_attn_bwd_tc) {
-    set_last_error("the CUDA-core attention backward supports nframes <= 196");
-    return 1;
-  }
-  CK(configure_attention_bwd_kernel());
   CK(configure_attention_bwd_tc_kernel());
   e->stash.resize(e->layers);
   int rc = 0;
@@ -572,7 +529,7 @@ int ensure_stash(cmdi_engine* e) {
 // Backward pass of the (CFG-wrapped) denoiser w.r.t. its input, seeded with dL/dx0_hat of the reconstruction loss
 // (gaussian_diffusion.py:415-416).  Result: guide_grad[nseq * L, D_pad] (cond rows, then uncond rows under CFG).
 // Scratch: xseq / x1 (fp32 + planes) carry the running gradients; qkv_p / attn_p / ffh_p the per-layer ones.
-constexpr int kBackwardLaunchesPerLayer = 7;  // + 1 when the attention backward runs on tensor cores (two launches)
+constexpr int kBackwardLaunchesPerLayer = 8;  // the attention backward is two launches (dQ pass, dK/dV pass)
 int run_backward(cmdi_engine* e, int B, bool cfg, cudaStream_t s) {
   const int nseq = cfg ? 2 * B : B;
   const int M = nseq * e->S, MF = nseq * e->L;
@@ -614,13 +571,9 @@ int run_backward(cmdi_engine* e, int B, bool cfg, cudaStream_t s) {
     ab.num_seqs = nseq; ab.seq_len = e->S; ab.num_heads = e->H; ab.qkv_hi = ls.qkv.hi; ab.qkv_lo = ls.qkv.lo;
     ab.do_hi = e->attn_p.hi; ab.do_lo = e->attn_p.lo; ab.ld_do = kDModel; ab.dqkv_hi = e->qkv_p.hi; ab.dqkv_lo = e->qkv_p.lo;
     ab.ld_dqkv = 3 * kDModel; ab.nsplit = e->nsplit; ab.stats = e->attn_stats;
-    if (g_attn_bwd_tc) {
-      AttnBwdTcMaps bm{&ls.q_hi, &ls.q_lo, &ls.kv_hi, &ls.kv_lo, &e->attn_p.map_hi, &e->attn_p.map_lo, &e->do_f_hi, &e->do_f_lo,
-                       &e->qkv_p.st_hi, &e->qkv_p.st_lo};
-      CK(launch_attention_bwd_tc(bm, ab, s));
-    } else {
-      CK(launch_attention_bwd(ab, s));
-    }
+    AttnBwdTcMaps bm{&ls.q_hi, &ls.q_lo, &ls.kv_hi, &ls.kv_lo, &e->attn_p.map_hi, &e->attn_p.map_lo, &e->do_f_hi, &e->do_f_lo,
+                     &e->qkv_p.st_hi, &e->qkv_p.st_lo};
+    CK(launch_attention_bwd_tc(bm, ab, s));
     // QKV projection backward + the skip path: dX = dQKV Wqkv + dV1
     LinearParams bq{};
     bq.M = M; bq.N = kDModel; bq.K = 3 * kDModel; bq.nsplit = e->nsplit; bq.residual = e->x1; bq.ld_res = kDModel;
@@ -636,12 +589,12 @@ int run_backward(cmdi_engine* e, int B, bool cfg, cudaStream_t s) {
   return 0;
 }
 int launches_per_backward(const cmdi_engine* e) {
-  return 3 + e->layers * (kBackwardLaunchesPerLayer + (g_attn_bwd_tc ? 1 : 0)) + 1;
+  return 3 + e->layers * kBackwardLaunchesPerLayer + 1;
 }
 
 int launches_per_pass(const cmdi_engine* e, bool guided = false) {
   if (!guided && chain_eligible(e)) return 3 + 2 * e->layers;
-  return 1 + 1 + e->layers * ((e->fuse_ln && !guided) ? 5 : 7) + 1;
+  return 1 + 1 + e->layers * 7 + 1;
 }
 
 int check_ready(cmdi_engine* e, int B, bool need_schedule) {
@@ -688,32 +641,18 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
     set_last_error("unsupported model configuration (need latent_dim=512, 4 heads of 128, ff %% 256 == 0, nframes <= 207)");
     return 1;
   }
-  CK(configure_linear_kernels());
   CK(configure_linear2_kernels());
-  CK(configure_linear_ln_kernel());
   CK(configure_attention_kernel());
   CK(configure_linear_chain_kernel());
   cmdi_engine* e = new cmdi_engine();
-  if (const char* g = getenv("CMDI_GEMM")) e->use_pair = strcmp(g, "single") != 0;
   if (const char* g = getenv("CMDI_DEBUG")) e->debug = atoi(g);
   if (const char* g = getenv("CMDI_EPI")) e->tma_store = strcmp(g, "stg") != 0;
-  if (const char* g = getenv("CMDI_PDL")) {
-    g_pdl_light = strcmp(g, "ln") == 0;
-    g_use_pdl = !g_pdl_light && atoi(g) != 0;
-  }
   e->bn_qkv = kBnWide;  // 256 x 192 pair tiles (CMDI_BN_QKV=192) measured no faster than 256 x 256 despite the better round count
   if (const char* g = getenv("CMDI_BN_QKV")) e->bn_qkv = atoi(g);
   if (const char* g = getenv("CMDI_NO_GRAPH")) e->no_graph = atoi(g) != 0;
   if (const char* g = getenv("CMDI_GRAPH_STEPS")) e->steps_per_graph = atoi(g) > 0 ? atoi(g) : 1;
   if (const char* g = getenv("CMDI_ATTN_PREFETCH")) e->attn_prefetch_q = atoi(g) != 0;
   if (const char* g = getenv("CMDI_ATTN_SPLIT")) e->attn_trunc_split = strcmp(g, "trunc") == 0;
-  if (const char* g = getenv("CMDI_RES")) {
-    e->plane_residual = strcmp(g, "planes") == 0;
-    e->ln_residual = strcmp(g, "ln") == 0;
-  }
-  if (const char* g = getenv("CMDI_ATTN_BWD")) g_attn_bwd_tc = strcmp(g, "simt") != 0;
-  if (const char* g = getenv("CMDI_ATTN")) g_attn_persistent = strcmp(g, "oneshot") != 0;
-  if (const char* g = getenv("CMDI_FUSE_LN")) e->fuse_ln = atoi(g) != 0;
   if (const char* g = getenv("CMDI_CHAIN")) e->use_chain = atoi(g) != 0;
   if (const char* g = getenv("CMDI_CHAIN_PUBLISH")) e->chain_publish_now = strcmp(g, "deferred") != 0;
   e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount; e->nsplit = cfg->precision;

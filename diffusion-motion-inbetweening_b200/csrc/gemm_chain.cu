@@ -547,8 +547,7 @@ cudaError_t launch_linear_chain(const ChainPhaseDesc* phases_dev, int num_phases
     set_last_error("launch_linear_chain: %d co-resident CTA pairs needed, the device offers %d", clusters, max_clusters);
     return cudaErrorInvalidConfiguration;
   }
-  // never a programmatic dependent launch: its CTAs must not become resident while a predecessor still holds SMs
-  return launch_kernel_ex(false, linear_chain_kernel, dim3(2 * clusters), dim3(kNumThreads), (size_t)kSmemBytes, stream, phases_dev,
+  return launch_kernel(linear_chain_kernel, dim3(2 * clusters), dim3(kNumThreads), (size_t)kSmemBytes, stream, phases_dev,
                           num_phases, total_tiles, dbg);
 }
 

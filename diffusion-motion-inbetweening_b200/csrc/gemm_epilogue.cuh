@@ -270,22 +270,6 @@ __device__ __forceinline__ void epilogue_tile(const LinearParams& p, const EpiSt
         }
       }
     }
-    if (p.res_hi) {
-      // residual given as bf16 hi/lo planes: one 64-column block (128 B per row) per plane
-      const __nv_bfloat16* planes[2] = {p.res_hi, p.res_lo};
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (!planes[h]) continue;
-        uint32_t r[32];
-        load_block_coalesced(stage, lane, r, reinterpret_cast<const char*>(planes[h] + n0), rows, (long long)p.ld_res_bf * 2,
-                             (p.N - n0) / 8);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          f[2 * j] += __uint_as_float(r[j] << 16);
-          f[2 * j + 1] += __uint_as_float(r[j] & 0xFFFF0000u);
-        }
-      }
-    }
     if (p.grad_aux) {
       // GELU backward: dPre = dH * gelu'(pre), pre stashed by the forward pass
 #pragma unroll

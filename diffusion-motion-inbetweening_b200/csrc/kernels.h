@@ -53,9 +53,6 @@ struct LinearParams {
   // publish the partial statistics of the OUTPUT rows: stats_out[row * 16 + (col / 32)] = (mean, sum of squared
   // deviations) over the 32 output columns starting at col (N must be 512); consumed by ln_partials / fold_stats
   float2* stats_out;
-  const __nv_bfloat16* res_hi;  // the same residual as bf16 hi/lo planes [rows, ld_res_bf] (x = hi + lo), or null:
-  const __nv_bfloat16* res_lo;  // lets LayerNorm skip its fp32 output (the planes are what the next GEMM reads anyway)
-  int ld_res_bf;
   const float* pos_enc;  // fp32 [L+1, N] table added per output sequence position (ROWMAP_FRAMES_TO_SEQ); or null
   int act;               // 0 none, 1 exact erf GELU
   int f32_pre;           // 1: out_f32 receives the value BEFORE the activation (stash for the GELU backward)
@@ -74,12 +71,6 @@ struct LinearParams {
   long long* dbg_cycles;  // bring-up only: per-CTA cycle counters [gridDim.x][16] (see gemm2.cu) or null
   int tma_store;   // set by the launcher when LinearStoreMaps are given: outputs leave through cp.async.bulk.tensor stores
 };
-
-// block_n: 128 or 256. Tensor maps: bf16 row-major, box {64, 128} for A and {64, block_n} for W, 128B swizzle.
-cudaError_t configure_linear_kernels();
-cudaError_t launch_linear(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
-                          const CUtensorMap& w_lo, const LinearParams& p, int block_n, int num_sms,
-                          cudaStream_t stream, const LinearStoreMaps* st = nullptr);
 
 // CTA-pair (cta_group::2) version: 256-row tiles shared by two SMs of a cluster. W box is {64, block_n / 2}.   (gemm2.cu)
 cudaError_t configure_linear2_kernels();
@@ -111,22 +102,6 @@ cudaError_t launch_linear_chain(const ChainPhaseDesc* phases_dev, int num_phases
                                 cudaStream_t stream, long long* dbg = nullptr);
 int linear_chain_max_clusters(int num_sms);
 
-// Linear + residual + LayerNorm over full 512-wide rows (out-proj + norm1, linear2 + norm2).   (gemm2_ln.cu)
-struct LinearLnParams {
-  int M, K;               // rows, reduction extent; N is fixed at 512
-  int nsplit, nsplit_out;
-  const float* bias;      // [512]
-  const float* residual;  // fp32 [M, 512]
-  const float* gamma;     // [512]
-  const float* beta;      // [512]
-  float eps;
-};
-cudaError_t configure_linear_ln_kernel();
-// W map: box {64, 128} over [512, K]; o_*: TMA-store targets [rows, 512] (bf16 box {64, 32}, fp32 box {32, 32})
-cudaError_t launch_linear_ln(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
-                             const CUtensorMap& o_hi, const CUtensorMap& o_lo, const CUtensorMap& o_f32,
-                             const LinearLnParams& p, int num_sms, cudaStream_t stream);
-
 // ----------------------------------------------------------------------------------------------
 // self-attention core: O = softmax(Q K^T / sqrt(dh)) V per (sequence, head)      (attention.cu)
 // ----------------------------------------------------------------------------------------------
@@ -150,7 +125,6 @@ cudaError_t launch_attention(const CUtensorMap& q_hi, const CUtensorMap& q_lo, c
                              const CUtensorMap& kv_lo, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const AttnParams& p,
                              cudaStream_t stream);
 constexpr int kAttnKeyPad = 208;
-extern bool g_attn_persistent;  // persistent (one CTA per SM, prefetching) vs one CTA per item
 
 // ----------------------------------------------------------------------------------------------
 // elementwise / row kernels      (elementwise.cu)
@@ -300,13 +274,13 @@ struct AttnBwdParams {
   float2* stats;                 // [rows, H]: (max*c + log2(sum), delta) per query row, written by pass 0, read by pass 1
 };
 cudaError_t configure_attention_bwd_kernel();
-cudaError_t launch_attention_bwd(const AttnBwdParams& p, cudaStream_t stream);  // fp32 CUDA cores (backward.cu)
+cudaError_t launch_attention_bwd(const AttnBwdParams& p, cudaStream_t stream);  // fp32 CUDA cores: the independent
+                                                                               // implementation the unit tests compare against (attention_bwd_simt_test.cu)
 // tcgen05 version (attention_bwd_tc.cu).  Maps over the bf16 planes, box {64, rows}: *_t = 128-row tiles, *_f = 208-row
 // operands; out_* = the dqkv planes as TMA-store targets, box {64, 32}.
 struct AttnBwdTcMaps {
   const CUtensorMap *qkv_t_hi, *qkv_t_lo, *qkv_f_hi, *qkv_f_lo, *do_t_hi, *do_t_lo, *do_f_hi, *do_f_lo, *out_hi, *out_lo;
 };
-extern bool g_attn_bwd_tc;
 cudaError_t configure_attention_bwd_tc_kernel();
 cudaError_t launch_attention_bwd_tc(const AttnBwdTcMaps& m, const AttnBwdParams& p, cudaStream_t stream);
 cudaError_t launch_transpose_split(const float* w, int R, int C, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_out,
@@ -324,26 +298,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t ro
 
 void set_last_error(const char* fmt, ...);
 
-// Launch helper: with `pdl` the kernel is allowed to overlap its prologue with the tail of the previous kernel in
-// the stream (programmatic dependent launch; every such kernel calls griddep_wait() before touching global memory).
-extern bool g_use_pdl;     // CMDI_PDL=1 turns programmatic dependent launch on (off by default: slower in graph replay)
-extern bool g_pdl_light;   // CMDI_PDL=ln: only the kernels without shared memory / TMEM (LayerNorm), which can become resident
-                           // next to a running GEMM, are launched as programmatic dependents
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_kernel_ex(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                                    Args&&... args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
+// Launch helper (cudaLaunchKernelEx so cluster-dimensioned kernels and plain ones share one path).  Programmatic
+// dependent launch was built and measured in round 1 (graph replay 3.5 % SLOWER with the programmatic edges) and removed.
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                  Args&&... args) {
@@ -352,11 +308,7 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cfg.numAttrs = 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 const char* get_last_error();

@@ -8,9 +8,6 @@
 
 namespace cmdi {
 
-bool g_pdl_light = false;
-bool g_use_pdl = false;  // measured: with programmatic edges the graph-replayed step is 3.5 % slower (451 vs 467 steps/s)
-
 namespace {
 thread_local char g_last_error[1024] = "";
 

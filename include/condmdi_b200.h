@@ -145,9 +145,6 @@ CMDI_API const char* cmdi_version(void);
 /* C[M,N] = act(A[M,K] W[N,K]^T + bias) (+ residual); block_n in {128, 256}: one CTA per tile; {-128, -256}: CTA-pair kernel */
 CMDI_API int cmdi_test_linear(const float* A, const float* W, const float* bias, const float* residual, float* C, int M, int N,
                      int K, int act, int precision, int block_n, void* stream);
-/* out[M,512] = LayerNorm(residual + A[M,K] W[512,K]^T + bias) * gamma + beta  (fused out-proj/linear2 + norm kernel) */
-CMDI_API int cmdi_test_linear_ln(const float* A, const float* W, const float* bias, const float* residual, const float* gamma,
-                        const float* beta, float* out, int M, int K, int precision, void* stream);
 /* O = softmax(Q K^T / sqrt(128)) V for `num_seqs` sequences of length S and H heads; qkv: [num_seqs*S, 3*H*128] */
 CMDI_API int cmdi_test_attention(const float* qkv, float* O, int num_seqs, int S, int H, int precision, void* stream);
 CMDI_API int cmdi_test_layernorm(const float* v, const float* gamma, const float* beta, float* out, int rows, void* stream);

@@ -58,3 +58,22 @@ def test_clock_summary_windows():
     short.window("timed", 10.0, 10.1)      # one sample only: the end-to-end region is added
     short.window("e2e", 11.0, 11.1)
     assert short.summary()["window"] == "timed+e2e" and short.summary()["samples"] == 2
+
+
+def test_peak_choice_and_chain_flops():
+    b = _load_bench()
+    short, long_ = b.measured_peaks(0.04), b.measured_peaks(2.1)
+    assert "burst" in short["source"] and "sustained" in long_["source"] and short["bf16_tflops"] >= long_["bf16_tflops"]
+    # one chained launch = out-proj + FFN1 + FFN2 + next QKV
+    k = b.KERNEL_FLOPS
+    assert abs(k["chain"](64) - (k["out_proj"](64) + k["ffn1"](64) + k["ffn2"](64) + k["qkv"](64))) < 1.0
+
+
+def test_nvml_sampler_summary_without_nvml():
+    b = _load_bench()
+    s = b.NvmlSampler(0)
+    s.max_mhz = 1965.0
+    s.rows = [(10.001, 1965.0, 0), (10.006, 1950.0, 0x4), (10.011, 1950.0, 0x4), (10.5, 1200.0, 0x8)]
+    s.window("timed", 10.0, 10.04)
+    out = s.summary()
+    assert out["samples"] == 3 and out["sm_mhz"] == 1950.0 and out["reasons"] == ["sw_power_cap"] and out["window"] == "timed"

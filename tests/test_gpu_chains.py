@@ -337,3 +337,37 @@ def test_guidance_imputes_without_reading_replacement_distribution(texty, gi):
     y3 = dict(y, replacement_distribution="marginal")
     c = d.p_sample_loop(m, (B, D, 1, L), model_kwargs={"y": y3}, skip_timesteps=997, init_image=x_obs)
     assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_engine_knobs_are_per_engine_state(monkeypatch, gi):
+    """An engine keeps the configuration it was created under; creating another one under different settings does not
+    change it (round 1 kept some of these switches in process globals).  CMDI_CHAIN=0 selects the unchained forward path
+    (one launch per linear layer + LayerNorm kernels): 59 launches per pass instead of 19."""
+    sd = O.random_state_dict(seed=7)
+    x = gi["x"].to(DEV)
+    want = O.mdm_forward(sd, gi["x"], torch.tensor([41, 41]))
+
+    def make():
+        m = C.MDM()
+        m.load_state_dict(sd, strict=False)
+        return m.cuda()
+
+    monkeypatch.setenv("CMDI_CHAIN", "0")
+    m_plain = make()
+    e_plain = m_plain.engine_for(torch.device(DEV), max_batch=B)
+    monkeypatch.delenv("CMDI_CHAIN")
+    m_chain = make()
+    e_chain = m_chain.engine_for(torch.device(DEV), max_batch=B)   # created AFTER, under the default settings
+
+    def launches(eng):
+        n0 = eng.launch_count
+        out = eng.forward(x, 41)
+        return eng.launch_count - n0, out
+
+    launches(e_plain), launches(e_chain)   # the first call of an engine also tabulates the timestep embedding
+    n_plain, out_plain = launches(e_plain)
+    n_chain, out_chain = launches(e_chain)
+    n_plain2, _ = launches(e_plain)
+    assert n_plain == n_plain2 == 2 + 7 * 8 + 1 + 4 and n_chain == 3 + 2 * 8 + 4
+    assert close(out_plain, want, "unchained path vs oracle") and close(out_chain, want, "chained path vs oracle")
+    assert not torch.equal(out_plain, out_chain)  # different arithmetic order (LayerNorm folded) -- both within the gate

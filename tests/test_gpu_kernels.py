@@ -66,15 +66,6 @@ def test_linear_epilogues(act, res, bn):
 
 
 @pytest.mark.parametrize("bn", [-256, -128, 128])
-def test_linear_residual_from_bf16_planes(monkeypatch, bn):
-    """the residual stream between encoder sublayers is handed over as bf16 hi/lo planes (x = hi + lo to 2^-17)"""
-    monkeypatch.setenv("CMDI_TEST_RES_PLANES", "1")
-    out, ref = run_linear(777, 512, 512, 3, bn, act=0, res=True)
-    assert torch.allclose(out, ref, **GATE)
-    assert (out - ref).abs().max() < 1e-4
-
-
-@pytest.mark.parametrize("bn", [-256, -128, 128])
 def test_linear_residual_rederived_from_layernorm_input(monkeypatch, bn):
     """default residual path between encoder sublayers: LayerNorm publishes (mean, rstd) per row and writes only the
     bf16 planes; the next epilogue re-derives LayerNorm's fp32 output from its input"""
@@ -110,23 +101,6 @@ def test_linear_large_magnitudes_and_zero_rows():
     C.capi.check(_lib().cmdi_test_linear(_p(A), _p(W), None, None, _p(out), 256, 512, 512, 0, 3, 128, None))
     torch.cuda.synchronize()
     assert torch.equal(out, torch.zeros_like(out))
-
-
-@pytest.mark.parametrize("M,K", [(256, 512), (300, 512), (12608, 512), (12608, 1024), (25216, 1024)])
-def test_linear_layernorm_fused_meets_fp32_gate(M, K):
-    """out-proj + norm1 / linear2 + norm2 as one kernel: LayerNorm(residual + A W^T + b) * gamma + beta"""
-    g = torch.Generator(device="cuda").manual_seed(M + K)
-    A = torch.randn(M, K, device="cuda", generator=g)
-    W = torch.randn(512, K, device="cuda", generator=g) / K ** 0.5
-    b, gamma, beta = (torch.randn(512, device="cuda", generator=g) for _ in range(3))
-    res = torch.randn(M, 512, device="cuda", generator=g) * 2 + 0.3
-    out = torch.full((M, 512), float("nan"), device="cuda")
-    C.capi.check(_lib().cmdi_test_linear_ln(_p(A), _p(W), _p(b), _p(res), _p(gamma), _p(beta), _p(out), M, K, 3, None))
-    torch.cuda.synchronize()
-    v = res.double() + A.double() @ W.double().t() + b.double()
-    ref = torch.nn.functional.layer_norm(v, (512,), gamma.double(), beta.double(), 1e-5)
-    assert torch.allclose(out.double(), ref, **GATE)
-    assert (out.double() - ref).abs().max() < 1e-4
 
 
 def ref_attention(qkv, nseq, S, H):
@@ -206,7 +180,7 @@ def test_attention_backward_matches_autograd(nseq, S, H):
 
 
 def test_attention_backward_cuda_core_kernel_agrees(monkeypatch):
-    """the fp32 CUDA-core kernel (CMDI_ATTN_BWD=simt) stays as the independent implementation of the same math"""
+    """the fp32 CUDA-core kernel (test-only TU attention_bwd_simt_test.cu) stays as the independent implementation of the same math"""
     monkeypatch.setenv("CMDI_TEST_ATTN_BWD_SIMT", "1")
     nseq, S, H = 2, 197, 4
     g = torch.Generator(device="cuda").manual_seed(5)
