@@ -11,6 +11,7 @@ from .engine import Engine  # noqa: F401
 from .model import MDM, ClassifierFreeSampleModel, resolve_model  # noqa: F401
 from .adapter import accelerate, install  # noqa: F401
 from .distributed import sharded_sample  # noqa: F401
+from .eval_loop import EvalJob, build_jobs, run_eval_jobs  # noqa: F401
 
 __version__ = "0.1.0"
 from .motion_process import recover_from_ric, sample_to_joints  # noqa: F401

@@ -213,6 +213,8 @@ __global__ void __launch_bounds__(256) diffusion_step_kernel(const StepParams p)
   const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int t = *p.step_ptr;
+  // first step index of the running call: a kernel argument, or (step graphs shared by every skip_timesteps) device memory
+  const int tape_t0 = p.tape_t0 >= 0 ? p.tape_t0 : p.step_ptr[2];
 
   // ---- noise tile (reference layout [b][c][l], l contiguous) ----
   const bool want_noise = p.sampler != 2;  // the reference draws noise at every step, including t == 0
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(256) diffusion_step_kernel(const StepParams p)
     if (!p.noise_ref && p.rng) rng = *p.rng;
     if (!p.noise_ref && rng.mode == 1) {
       // torch.randn_like stream: draw number (tape_t0 - t) of this loop, element index in the (B, D, 1, L) layout
-      const unsigned long long off = rng.aten_offset + (unsigned long long)(p.tape_t0 - t) * rng.aten_increment;
+      const unsigned long long off = rng.aten_offset + (unsigned long long)(tape_t0 - t) * rng.aten_increment;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int c = c0 + ty + i * 8, l = l0 + tx;
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(256) diffusion_step_kernel(const StepParams p)
         float nz = 0.f;
         if (c < p.D && l < p.L) {
           const size_t e = (size_t)c * p.L + l;
-          nz = p.noise_ref ? p.noise_ref[((size_t)(p.tape_t0 - t) * p.B + b) * p.D * p.L + e]
+          nz = p.noise_ref ? p.noise_ref[((size_t)(tape_t0 - t) * p.B + b) * p.D * p.L + e]
                            : philox_normal(rng.seed, (unsigned long long)(t + 1), rng.sample_offset + b, e);
         }
         s_noise[ty + i * 8][tx] = nz;

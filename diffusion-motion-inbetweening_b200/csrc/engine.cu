@@ -1134,7 +1134,8 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
   CKI(prepare_cond(e, B, a->cond_emb, host, s));
   if (a->cfg) CK(cudaMemcpyAsync(e->text_scale, a->text_scale, (size_t)B * 4, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
   CK(launch_set_int(e->step_ctr, t0, s));
-  e->launches += 1;
+  CK(launch_set_int(e->step_ctr + 2, t0, s));
+  e->launches += 2;
 
   const float* tape = a->noise_tape;
   if (tape && host) {
@@ -1152,7 +1153,7 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
     sp.x_t = e->x_state; sp.impute = a->imputate != 0; sp.stop_imputation_at = a->stop_imputation_at;
     sp.x_obs = e->x_obs; sp.obs_mask = e->obs_mask;
     sp.guided = guided; sp.guide_grad = e->guide_grad; sp.guide_coef = e->guide_coef;
-    sp.noise_ref = tape; sp.tape_t0 = t0; sp.rng = e->rng;
+    sp.noise_ref = tape; sp.tape_t0 = -1; sp.rng = e->rng;  // first step index: step_ctr[2] (graphs do not depend on it)
     sp.x_next = e->x_state; sp.x_next_hi = e->x_state_p.hi; sp.x_next_lo = e->nsplit == 3 ? e->x_state_p.lo : nullptr;
     sp.pred_xstart = e->pred_x0;
     CK(launch_diffusion_step(sp, st));
@@ -1164,7 +1165,7 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
     memset(&key, 0, sizeof(key));
     key.B = B; key.cfg = a->cfg != 0; key.sampler = a->sampler; key.impute = a->imputate != 0;
     key.stop_at = a->stop_imputation_at; key.tape_mode = tape != nullptr; key.has_cond = has_cond; key.eta = a->eta;
-    key.tape = tape; key.t0 = t0; key.uncond = a->uncond != 0;
+    key.tape = tape; key.t0 = 0; key.uncond = a->uncond != 0;  // the first step index lives in device memory
     key.guided = guided; key.group = group;
     auto it = e->graphs.find(key);
     if (it != e->graphs.end()) {
@@ -1204,9 +1205,21 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
     // utils/editing_util.py:325-333: guidance is active while t >= stop_recguidance_at (t is uniform over the batch)
     const bool guided = guided_at(k);
     int run = 1;
-    // calls of one or two steps (the *_progressive generators issue one native call per step, each with its own t0)
-    // are launched directly: capturing and instantiating a graph costs more than it saves there
-    if (a->use_graph && !e->no_graph && nsteps >= 3) {
+    // use_graph 1: calls of one or two steps are launched directly unless a step graph of this configuration already
+    // exists (capturing and instantiating one costs more than it saves there); use_graph 2 (the *_progressive
+    // generators: one native call per step, many calls): always through the step graph
+    // (a noise tape -- test aid -- is addressed through a kernel argument: per-step calls with a moving tape pointer
+    //  would capture a new graph every step, so they are launched directly)
+    bool via_graph = a->use_graph && !e->no_graph && (nsteps >= 3 || (a->use_graph >= 2 && !tape));
+    if (a->use_graph && !e->no_graph && !via_graph) {
+      GraphKey probe{};
+      memset(&probe, 0, sizeof(probe));
+      probe.B = B; probe.cfg = a->cfg != 0; probe.sampler = a->sampler; probe.impute = a->imputate != 0;
+      probe.stop_at = a->stop_imputation_at; probe.tape_mode = tape != nullptr; probe.has_cond = has_cond; probe.eta = a->eta;
+      probe.tape = tape; probe.uncond = a->uncond != 0; probe.guided = guided; probe.group = 1;
+      via_graph = e->graphs.count(probe) != 0;
+    }
+    if (via_graph) {
       const bool dump_in_group = a->dump_xstart && dump_i < a->n_dump && a->dump_steps[dump_i] < k + group;
       if (group > 1 && k + group <= nsteps && !dump_in_group && guided_at(k + group - 1) == guided) {
         if (!execg[guided]) CKI(get_exec(guided, group, &execg[guided]));

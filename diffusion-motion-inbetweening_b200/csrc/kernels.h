@@ -177,7 +177,8 @@ struct RngState {
 };
 struct StepParams {
   StepTables tab;
-  int* step_ptr;            // device: current step t; decremented by the kernel's last block when advance != 0
+  int* step_ptr;            // device [3]: current step t (decremented by the kernel's last block when advance != 0),
+                            // block-arrival counter, first step index of the call
   int advance;
   int B, L, D, D_pad;
   int sampler;              // 0 = ancestral DDPM (p_sample), 1 = DDIM (ddim_sample_with_grad, cond_fn=None),
@@ -199,7 +200,7 @@ struct StepParams {
   // noise
   const float* noise_ref;      // tape base, reference layout [steps][B, D, 1, L]; slice (tape_t0 - t) is this step's
                                // randn_like draw; null -> in-kernel Philox
-  int tape_t0;
+  int tape_t0;                 // >= 0: the call's first step index; -1: read it from step_ptr[2]
   // generator state, device-resident so a captured step graph does not depend on it (RngState below).
   // rng_mode 0: engine generator keyed by (seed, t + 1, global sample index, element quad);
   // rng_mode 1: the stream of torch.randn_like on this device (ATen's Philox offsets / thread mapping), draw

@@ -267,6 +267,7 @@ class GaussianDiffusion:
         for k in range(n):
             if common.get("rng_mode", capi.RNG_ENGINE) == capi.RNG_TORCH:
                 common["aten_offset"] = off0 + k * inc  # each one-step call starts at its own draw of the stream
+            common["use_graph"] = 2 if common.get("use_graph", True) else 0  # one native call per step, same step graph every time
             res = eng.sample(skip_timesteps=skip_timesteps + k, num_steps=1, resume=(k > 0), init_image=init_image if k == 0 else None,
                              x_T=state, noise_tape=None if tape is None else tape[k:], want_pred_xstart=True, **common)
             state = res["sample"]

@@ -126,7 +126,8 @@ typedef struct {
   const int32_t* dump_steps;    /* host array of loop-iteration indices (ascending), p_sample_loop's dump_steps (:1208-1213) */
   int32_t n_dump;
   int32_t host_buffers;         /* 1: every pointer above and `out` are HOST pointers (copies happen inside the call) */
-  int32_t use_graph;            /* 1: replay one captured CUDA graph per step (default), 0: plain launches */
+  int32_t use_graph;            /* 0: plain launches; 1: one captured CUDA graph replayed per step for calls of >= 3 steps
+                                   (default); 2: also for one-step calls (the *_progressive generators) */
 } cmdi_sample_args;
 
 CMDI_API int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_engine** out);

@@ -371,3 +371,59 @@ def test_engine_knobs_are_per_engine_state(monkeypatch, gi):
     assert n_plain == n_plain2 == 2 + 7 * 8 + 1 + 4 and n_chain == 3 + 2 * 8 + 4
     assert close(out_plain, want, "unchained path vs oracle") and close(out_chain, want, "chained path vs oracle")
     assert not torch.equal(out_plain, out_chain)  # different arithmetic order (LayerNorm folded) -- both within the gate
+
+
+# ------------------------------------------------------------------------------------------------
+# evaluation-loop caller and the generator loops through the step graph
+# ------------------------------------------------------------------------------------------------
+def test_eval_loop_jobs_on_the_engine(texty, gi):
+    """`run_eval_jobs` (the reference's double loop of comp_v6_model_dataset_condmdi.py:190-356 as a job list): merged
+    engine batches give bit-identical motions to one call per job, and rng='torch' reproduces a fixseed + direct call."""
+    m, _ = texty
+    w = C.ClassifierFreeSampleModel(m)
+    d = C.create_gaussian_diffusion()
+    conds = [torch.randn(B, 512, generator=torch.Generator().manual_seed(40 + i)).to(DEV) for i in range(3)]
+    state = {"i": 0}
+    x_obs, kf = gi["x_obs"].to(DEV), gi["kf_mask"].to(DEV)
+
+    def y_of(i):
+        return {"text": [f"job{i}a", f"job{i}b"], "text_scale": gi["text_scale"].to(DEV), "mask": gi["y_mask"].to(DEV),
+                "lengths": gi["lengths"], "imputate": 1, "stop_imputation_at": 1, "replacement_distribution": "conditional",
+                "inpainted_motion": x_obs + 0.1 * i, "inpainting_mask": kf}
+
+    table = {f"job{i}{s}": conds[i][k] for i in range(3) for k, s in enumerate("ab")}
+    old = m.encode_text
+    m.encode_text = lambda texts: torch.stack([table[t] for t in texts])
+    try:
+        jobs = C.build_jobs([((B, D, 1, L), {"y": y_of(i)}) for i in range(3)], seed=10, mm_idxs=[2], mm_num_repeats=2)
+        assert len(jobs) == 4
+        one = C.run_eval_jobs(d, w, jobs, seed=5, merge=1, skip_timesteps=996)
+        two = C.run_eval_jobs(d, w, jobs, seed=5, merge=2, skip_timesteps=996)
+        four = C.run_eval_jobs(d, w, jobs, seed=5, merge=4, skip_timesteps=996)
+        for i in range(4):
+            assert one[i].shape == (B, D, 1, L) and torch.equal(one[i], two[i]) and torch.equal(one[i], four[i])
+        assert not torch.equal(one[2], one[3])        # the two repetitions of the multimodality batch differ (other motions)
+        # the reference's own seeding, call by call
+        ref_style = C.run_eval_jobs(d, w, jobs, rng="torch", skip_timesteps=996)
+        torch.manual_seed(jobs[1].seed_number)
+        direct = d.p_sample_loop(w, (B, D, 1, L), clip_denoised=False, model_kwargs=jobs[1].model_kwargs, skip_timesteps=996)
+        assert torch.equal(ref_style[1], direct) and d.rng == "torch"
+    finally:
+        m.encode_text = old
+    del state
+
+
+def test_progressive_loops_replay_the_step_graph(plain):
+    """One native call per step (the generator loops): every call replays the same captured step graph -- the first step
+    index of a call lives in device memory, so neither skip_timesteps nor the step number re-captures."""
+    m, _ = plain
+    d = C.create_gaussian_diffusion(timestep_respacing="ddim50")
+    d.rng, d.engine_seed = "engine", 77
+    eng = m.engine_for(torch.device(DEV), max_batch=B)
+    fused = d.ddim_sample_loop(m, (B, D, 1, L), model_kwargs={"y": {}}, skip_timesteps=40, eta=1.0).clone()
+    n0 = eng.launch_count
+    outs = list(d.ddim_sample_loop_progressive(m, (B, D, 1, L), model_kwargs={"y": {}}, skip_timesteps=40, eta=1.0))
+    assert len(outs) == 10 and torch.equal(outs[-1]["sample"], fused)
+    other = list(d.ddim_sample_loop_progressive(m, (B, D, 1, L), model_kwargs={"y": {}}, skip_timesteps=45, eta=1.0))
+    assert len(other) == 5 and torch.isfinite(other[-1]["sample"]).all()
+    assert eng.launch_count > n0
