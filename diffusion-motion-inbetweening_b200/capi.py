@@ -16,6 +16,7 @@ PRECISION_BF16 = 1
 RNG_ENGINE, RNG_TORCH = 0, 1
 SAMPLER_DDPM = 0
 SAMPLER_DDIM = 1
+ARCH_TRANS_ENC, ARCH_UNET = 0, 1
 
 EXPORTS = [
     "cmdi_engine_create", "cmdi_engine_destroy", "cmdi_load_weights", "cmdi_set_schedule", "cmdi_model_forward",
@@ -28,7 +29,8 @@ EXPORTS = [
 class ModelCfg(Structure):
     _fields_ = [("njoints", c_int32), ("nframes", c_int32), ("latent_dim", c_int32), ("ff_size", c_int32),
                 ("num_layers", c_int32), ("num_heads", c_int32), ("max_batch", c_int32), ("has_text", c_int32),
-                ("precision", c_int32)]
+                ("precision", c_int32), ("arch", c_int32), ("unet_levels", c_int32), ("unet_dim_mults", c_int32 * 4),
+                ("keyframe_conditioned", c_int32)]
 
 
 class TensorDesc(Structure):
@@ -37,7 +39,7 @@ class TensorDesc(Structure):
 
 class ForwardArgs(Structure):
     _fields_ = [("batch", c_int32), ("x", c_void_p), ("timestep", c_int32), ("cond_emb", c_void_p), ("uncond", c_int32),
-                ("cfg", c_int32), ("text_scale", c_void_p), ("host_buffers", c_int32)]
+                ("cfg", c_int32), ("text_scale", c_void_p), ("host_buffers", c_int32), ("obs_x0", c_void_p), ("obs_mask", c_void_p)]
 
 
 class SampleArgs(Structure):
@@ -49,7 +51,7 @@ class SampleArgs(Structure):
                 ("inpainted_motion", c_void_p), ("inpainting_mask", c_void_p), ("recon_guidance", c_int32),
                 ("stop_recguidance_at", c_int32), ("recon_coef", POINTER(c_float)), ("pred_xstart_out", c_void_p),
                 ("dump_xstart", c_void_p), ("dump_steps", POINTER(c_int32)), ("n_dump", c_int32),
-                ("host_buffers", c_int32), ("use_graph", c_int32)]
+                ("host_buffers", c_int32), ("use_graph", c_int32), ("obs_x0", c_void_p), ("obs_mask", c_void_p)]
 
 
 class LibraryMissing(RuntimeError):

@@ -24,6 +24,8 @@
 
 using namespace cmdi;
 
+struct UnetModel;  // engine_unet.inc
+
 namespace {
 
 #define CK(expr)                                                                                    \
@@ -160,6 +162,7 @@ struct cmdi_engine {
   int max_m_pairs = 0;
   long long* chain_dbg = nullptr;               // CMDI_CHAIN_DBG=1: cycle counters of layer 1's chain during cmdi_profile_pass
   std::map<int, ChainTables> chain_tables;
+  UnetModel* unet = nullptr;  // MDM_UNET denoiser (cfg.arch == CMDI_ARCH_UNET): engine_unet.inc
   std::map<GraphKey, cudaGraphExec_t> graphs;
   int64_t launches = 0;
 };
@@ -242,6 +245,10 @@ int run_linear(cmdi_engine* e, const Planes& a, const Planes& w, const LinearPar
   return 0;
 }
 
+}  // namespace
+#include "engine_unet.inc"
+namespace {
+
 bool chain_eligible(const cmdi_engine* e);
 int prepare_chain(cmdi_engine* e, int nseq);
 int run_denoiser_chain(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond, const int* tmap_dev, cudaStream_t s,
@@ -251,6 +258,7 @@ int run_denoiser_chain(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool ha
 // with dup the frame embedding is written for sequences [0,B) and [B,2B)).
 int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond, const int* tmap_dev, cudaStream_t s,
                  std::vector<cudaEvent_t>* evs = nullptr, int reps = 1, std::vector<LayerStash>* stash = nullptr) {
+  if (e->unet) return unet_run(e, e->unet, B, dup, n_cond_seqs, has_cond, tmap_dev, s);
   if (!stash && chain_eligible(e)) return run_denoiser_chain(e, B, dup, n_cond_seqs, has_cond, tmap_dev, s, evs, reps);
   auto mark = [&]() -> int {
     if (!evs) return 0;
@@ -593,6 +601,7 @@ int launches_per_backward(const cmdi_engine* e) {
 }
 
 int launches_per_pass(const cmdi_engine* e, bool guided = false) {
+  if (e->unet) return unet_launches_per_pass(e->unet);
   if (!guided && chain_eligible(e)) return 3 + 2 * e->layers;
   return 1 + 1 + e->layers * 7 + 1;
 }
@@ -635,9 +644,14 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
     set_last_error("device %d is sm_%d%d; this library contains sm_100a code only (B200)", device, prop.major, prop.minor);
     return 1;
   }
-  if (cfg->latent_dim != kDModel || cfg->num_heads * 128 != cfg->latent_dim || cfg->ff_size % 256 != 0 ||
-      cfg->nframes + 1 > kAttnKeyPad || cfg->njoints < 8 || cfg->max_batch < 1 ||
-      (cfg->precision != CMDI_PRECISION_BF16X3 && cfg->precision != CMDI_PRECISION_BF16)) {
+  const bool is_unet = cfg->arch == CMDI_ARCH_UNET;
+  if (cfg->arch != CMDI_ARCH_TRANS_ENC && !is_unet) {
+    set_last_error("unknown architecture %d", cfg->arch);
+    return 1;
+  }
+  if (cfg->latent_dim != kDModel || cfg->njoints < 8 || cfg->max_batch < 1 ||
+      (cfg->precision != CMDI_PRECISION_BF16X3 && cfg->precision != CMDI_PRECISION_BF16) ||
+      (!is_unet && (cfg->num_heads * 128 != cfg->latent_dim || cfg->ff_size % 256 != 0 || cfg->nframes + 1 > kAttnKeyPad))) {
     set_last_error("unsupported model configuration (need latent_dim=512, 4 heads of 128, ff %% 256 == 0, nframes <= 207)");
     return 1;
   }
@@ -659,7 +673,8 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   // the chained launches spin on counters other CTA pairs bump: every pair must be resident at once
   if (e->use_chain && linear_chain_max_clusters(e->num_sms) < e->num_sms / 2) e->use_chain = false;
   e->D = cfg->njoints; e->D_pad = round_up(cfg->njoints, 8); e->L = cfg->nframes; e->S = cfg->nframes + 1;
-  e->ff = cfg->ff_size; e->H = cfg->num_heads; e->layers = cfg->num_layers; e->maxB = cfg->max_batch;
+  e->ff = is_unet ? 256 : cfg->ff_size; e->H = cfg->num_heads; e->layers = is_unet ? 0 : cfg->num_layers; e->maxB = cfg->max_batch;
+  if (is_unet) e->S = 2;  // the transformer's sequence buffers are not used: keep them tiny
   e->max_seqs = 2 * e->maxB;
   e->seq_rows = e->max_seqs * e->S;
   e->seq_rows_pad = round_up(e->seq_rows, 128) + 256;  // attention K/V boxes of the last sequence read 208 rows
@@ -723,7 +738,7 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   A(dev_alloc(e, &e->cond_emb, (size_t)e->maxB * 512));
   A(dev_alloc(e, &e->cond_proj, (size_t)e->maxB * kDModel));
   A(dev_alloc(e, &e->text_scale, e->maxB));
-  A(dev_alloc(e, &e->step_ctr, 2));
+  A(dev_alloc(e, &e->step_ctr, 4));
   A(dev_alloc(e, &e->rng, 1));
   // chained forward path: folded weights, partial row statistics, dependency counters
   e->f_qkv.resize(e->layers);
@@ -763,6 +778,13 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
     cmdi_engine_destroy(e);
     return 1;
   }
+  if (is_unet) {
+    e->unet = new UnetModel();
+    if (unet_create(e, e->unet, cfg)) {
+      cmdi_engine_destroy(e);
+      return 1;
+    }
+  }
   // default positional-encoding buffer (mdm.py:322-330); overwritten if the state dict carries 'sequence_pos_encoder.pe'
   {
     std::vector<float> pe((size_t)5000 * kDModel);
@@ -783,6 +805,7 @@ extern "C" int cmdi_engine_destroy(cmdi_engine* e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  delete e->unet;
   for (void* p : e->allocs) cudaFree(p);
   if (e->tables) cudaFree(e->tables);
   if (e->d_tmap) cudaFree(e->d_tmap);
@@ -829,10 +852,12 @@ extern "C" int cmdi_load_weights(cmdi_engine* e, const cmdi_tensor_desc* tensors
     const cmdi_tensor_desc* t_ = get(key);                                      \
     if (t_) rc = rc || upload_planes(e, pl, *t_, rows, cols, scratch, s, tr);   \
   } while (0)
-  LOAD_PL(e->w_in, "input_process.poseEmbedding.weight", kDModel, e->D, &e->w_inT);
-  LOAD_F32(e->b_in, "input_process.poseEmbedding.bias", kDModel);
-  LOAD_PL(e->w_out, "output_process.poseFinal.weight", e->D, kDModel, &e->w_outT);
-  LOAD_F32(e->b_out, "output_process.poseFinal.bias", (size_t)e->D);
+  if (!e->unet) {
+    LOAD_PL(e->w_in, "input_process.poseEmbedding.weight", kDModel, e->D, &e->w_inT);
+    LOAD_F32(e->b_in, "input_process.poseEmbedding.bias", kDModel);
+    LOAD_PL(e->w_out, "output_process.poseFinal.weight", e->D, kDModel, &e->w_outT);
+    LOAD_F32(e->b_out, "output_process.poseFinal.bias", (size_t)e->D);
+  }
   LOAD_F32(e->te_w0, "embed_timestep.time_embed.0.weight", (size_t)kDModel * kDModel);
   LOAD_F32(e->te_b0, "embed_timestep.time_embed.0.bias", kDModel);
   LOAD_F32(e->te_w2, "embed_timestep.time_embed.2.weight", (size_t)kDModel * kDModel);
@@ -842,6 +867,7 @@ extern "C" int cmdi_load_weights(cmdi_engine* e, const cmdi_tensor_desc* tensors
     LOAD_F32(e->et_b, "embed_text.bias", kDModel);
   }
   if (by_name.count("sequence_pos_encoder.pe")) LOAD_F32(e->pe, "sequence_pos_encoder.pe", (size_t)5000 * kDModel);
+  if (e->unet && !rc) rc = unet_load_weights(e, e->unet, by_name, missing, s);
   for (int l = 0; l < e->layers; ++l) {
     LayerW& w = e->lw[l];
     const std::string p = "seqTransEncoder.layers." + std::to_string(l) + ".";
@@ -861,7 +887,7 @@ extern "C" int cmdi_load_weights(cmdi_engine* e, const cmdi_tensor_desc* tensors
 #undef LOAD_F32
 #undef LOAD_PL
   // ---- LayerNorm folded into the layers that consume it (chained forward path): W * gamma planes, c, d ----
-  if (missing.empty() && !rc) {
+  if (missing.empty() && !rc && !e->unet) {
     float* folded = nullptr;
     CK(cudaMalloc(&folded, scratch_elems * 4));
     ScratchGuard folded_guard{folded};
@@ -988,6 +1014,31 @@ int prepare_cond(cmdi_engine* e, int B, const float* cond_emb_user, bool host, c
   return 0;
 }
 
+// model_kwargs['obs_x0'] / ['obs_mask'] of a keyframe-conditioned MDM_UNET (mdm_unet.py:765-783): staged frame-major once
+// per call; the transformer ignores them (SURVEY 8b note 2)
+int stage_keyframe_input(cmdi_engine* e, int B, const float* obs_x0, const uint8_t* obs_mask, bool host, cudaStream_t s) {
+  if (!e->unet) return 0;
+  if ((obs_x0 == nullptr) != (obs_mask == nullptr)) {
+    set_last_error("with spatial conditioning, both obs_x0 and obs_mask must be provided (mdm_unet.py:775)");
+    return 1;
+  }
+  if (e->unet->kf && !obs_x0) {
+    set_last_error("a keyframe-conditioned UNet needs obs_x0 and obs_mask");
+    return 1;
+  }
+  e->unet->has_kf = e->unet->kf && obs_x0 != nullptr;
+  if (!e->unet->has_kf) return 0;
+  int rc = 0;
+  const size_t n = (size_t)B * e->D * e->L;
+  const float* obs = (const float*)stage_in(obs_x0, e->ref_b, n * 4, host, s, &rc);
+  const uint8_t* msk = (const uint8_t*)stage_in(obs_mask, e->ref_mask, n, host, s, &rc);
+  if (rc) return 1;
+  CK(launch_ref_to_frames(obs, B, e->D, e->L, e->D_pad, e->unet->kf_obs, nullptr, nullptr, s));
+  CK(launch_mask_to_frames(msk, nullptr, B, e->D, e->L, e->D_pad, e->unet->kf_mask, s));
+  e->launches += 2;
+  return 0;
+}
+
 }  // namespace
 
 extern "C" int cmdi_model_forward(cmdi_engine* e, const cmdi_forward_args* a, float* out, void* stream_) {
@@ -1014,7 +1065,8 @@ extern "C" int cmdi_model_forward(cmdi_engine* e, const cmdi_forward_args* a, fl
   int rc = 0;
   const float* x = (const float*)stage_in(a->x, e->ref_a, n * 4, host, s, &rc);
   if (rc) return 1;
-  CK(launch_ref_to_frames(x, B, e->D, e->L, e->D_pad, nullptr, e->x_state_p.hi, e->x_state_p.lo, s));
+  CK(launch_ref_to_frames(x, B, e->D, e->L, e->D_pad, e->unet ? e->x_state : nullptr, e->x_state_p.hi, e->x_state_p.lo, s));  // the UNet's input builder reads fp32
+  CKI(stage_keyframe_input(e, B, a->obs_x0, a->obs_mask, host, s));
   CKI(prepare_cond(e, B, a->cond_emb, host, s));
   if (a->cfg) CK(cudaMemcpyAsync(e->text_scale, a->text_scale, (size_t)B * 4, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
   CK(launch_set_int(e->step_ctr, a->timestep, s));
@@ -1056,6 +1108,10 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
   }
   if ((a->imputate || a->recon_guidance) && (!a->inpainted_motion || !a->inpainting_mask)) {
     set_last_error("imputate / reconstruction_guidance need inpainted_motion and inpainting_mask (editing_util.py:330, :343)");
+    return 1;
+  }
+  if (a->recon_guidance && e->unet) {
+    set_last_error("reconstruction guidance (the denoiser's input-VJP) is implemented for the transformer denoiser only");
     return 1;
   }
   if (a->recon_guidance) {
@@ -1130,6 +1186,7 @@ extern "C" int cmdi_sample(cmdi_engine* e, const cmdi_sample_args* a, float* out
     CK(launch_mask_to_frames(msk, ym, B, e->D, e->L, e->D_pad, e->obs_mask, s));
     e->launches += 2;
   }
+  CKI(stage_keyframe_input(e, B, a->obs_x0, a->obs_mask, host, s));
   // ---- conditioning ----
   CKI(prepare_cond(e, B, a->cond_emb, host, s));
   if (a->cfg) CK(cudaMemcpyAsync(e->text_scale, a->text_scale, (size_t)B * 4, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
@@ -1327,6 +1384,10 @@ extern "C" int cmdi_profile_pass(cmdi_engine* e, int batch, int cfg, int repeats
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   CK(cudaSetDevice(e->device));
   CKI(check_ready(e, batch, false));
+  if (e->unet) {
+    set_last_error("cmdi_profile_pass is implemented for the transformer denoiser");
+    return 1;
+  }
   CKI(ensure_temb(e, s));
   CK(launch_set_int(e->step_ctr, 500, s));
   std::vector<cudaEvent_t> evs;

@@ -69,6 +69,7 @@ linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int num_clusters = gridDim.x >> 1;
   const int num_tiles = num_m_pairs * num_n_blocks;
   const int num_k_blocks = (p.K + kBlockK - 1) / kBlockK;
+  const int kb_per_tap = p.num_taps > 0 ? p.k_per_tap / kBlockK : num_k_blocks;  // convolution taps: see LinearParams
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi);
@@ -111,11 +112,16 @@ linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             continue;
           }
           if (leader) mbar_arrive_expect_tx(&bars->full[stage], 2 * stage_bytes);
-          tma_load_2d_2sm(sa, &map_a_hi, &bars->full[stage], kb * kBlockK, m_blk * kBlockM);
-          tma_load_2d_2sm(sb, &map_w_hi, &bars->full[stage], kb * kBlockK, n_blk * BLOCK_N + (int)cta_rank * kHalfN);
+          int a_col = kb * kBlockK, w_col = a_col, a_row = m_blk * kBlockM;
+          if (p.num_taps > 0) {
+            const int tap = kb / kb_per_tap, kc = (kb - tap * kb_per_tap) * kBlockK;
+            a_col = p.tap_a_col[tap] + kc; w_col = p.tap_w_col[tap] + kc; a_row += p.tap_row[tap];
+          }
+          tma_load_2d_2sm(sa, &map_a_hi, &bars->full[stage], a_col, a_row);
+          tma_load_2d_2sm(sb, &map_w_hi, &bars->full[stage], w_col, n_blk * BLOCK_N + (int)cta_rank * kHalfN);
           if (nplanes == 2) {
-            tma_load_2d_2sm(sa + kABytes, &map_a_lo, &bars->full[stage], kb * kBlockK, m_blk * kBlockM);
-            tma_load_2d_2sm(sb + kBBytes, &map_w_lo, &bars->full[stage], kb * kBlockK, n_blk * BLOCK_N + (int)cta_rank * kHalfN);
+            tma_load_2d_2sm(sa + kABytes, &map_a_lo, &bars->full[stage], a_col, a_row);
+            tma_load_2d_2sm(sb + kBBytes, &map_w_lo, &bars->full[stage], w_col, n_blk * BLOCK_N + (int)cta_rank * kHalfN);
           }
           if (++stage == num_stages) {
             stage = 0;

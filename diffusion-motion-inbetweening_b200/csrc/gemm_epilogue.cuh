@@ -25,6 +25,9 @@ constexpr int kEpiStageBytes = 32 * 128;  // per epilogue warp
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// nn.Mish: x * tanh(softplus(x)), softplus with PyTorch's threshold 20
+__device__ __forceinline__ float mish_f(float x) { return x * tanhf(x > 20.0f ? x : log1pf(expf(x))); }
+
 // d/dx [0.5 x (1 + erf(x / sqrt 2))]
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
@@ -140,6 +143,12 @@ __device__ __forceinline__ bool map_row(const LinearParams& p, int a_row, long l
     const int s = a_row - b * S;
     valid = valid && (s > 0);
     out_row = (long long)b * p.frames + (s - 1);
+  }
+  else if (p.rowmap == ROWMAP_HALO_TO_FRAMES) {
+    const int b = a_row / p.row_period;
+    const int l = a_row - b * p.row_period - p.row_lo;
+    valid = valid && l >= 0 && l < p.frames;
+    out_row = (long long)b * p.frames + l;
   }
   if (!valid) out_row = 0;
   return valid;
@@ -302,7 +311,19 @@ __device__ __forceinline__ void epilogue_tile(const LinearParams& p, const EpiSt
     if (p.act == 1) {
 #pragma unroll
       for (int j = 0; j < 64; ++j) f[j] = gelu_erf(f[j]);
+    } else if (p.act == 3) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) f[j] = mish_f(f[j]);
     }
+    if (p.row_period && p.rowmap == ROWMAP_IDENTITY) {
+      // halo rows between sequences: the value computed there is meaningless, the consumer relies on zeros
+      const int rr = (warp_row0 + lane) % p.row_period;
+      if (rr < p.row_lo || rr >= p.row_hi) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) f[j] = 0.f;
+      }
+    }
+    const int oc = n0 + ((p.n_split > 0 && n0 >= p.n_split) ? p.n_gap : 0);  // output column of this chunk
     if (p.tma_store) {
       // identity row map: the staging tile goes out as one bulk tensor store per 32 x 128 B block
       if (p.out_f32 && !p.f32_pre) {
@@ -311,15 +332,15 @@ __device__ __forceinline__ void epilogue_tile(const LinearParams& p, const EpiSt
           uint32_t w[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(f[h * 32 + j]);
-          if (n0 + h * 32 < p.N) store_block_tma(stage, lane, w, maps.f32, n0 + h * 32, warp_row0);
+          if (n0 + h * 32 < p.N) store_block_tma(stage, lane, w, maps.f32, oc + h * 32, warp_row0);
         }
       }
       if (p.out_hi) {
         uint32_t hw[32], lw[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) split_bf16x2(f[2 * j], f[2 * j + 1], hw[j], lw[j]);
-        store_block_tma(stage, lane, hw, maps.hi, n0, warp_row0);
-        if (p.nsplit_out == 3) store_block_tma(stage, lane, lw, maps.lo, n0, warp_row0);
+        store_block_tma(stage, lane, hw, maps.hi, oc, warp_row0);
+        if (p.nsplit_out == 3) store_block_tma(stage, lane, lw, maps.lo, oc, warp_row0);
       }
       continue;
     }

@@ -15,7 +15,9 @@ enum RowMap : int {
   ROWMAP_IDENTITY = 0,
   ROWMAP_FRAMES_TO_SEQ = 1,  // A row b*L + l      -> out row b*(L+1) + l + 1   (frame embed, mdm.py:279)
   ROWMAP_SEQ_TO_FRAMES = 2,  // A row b*(L+1) + s  -> out row b*L + s - 1, s=0 dropped (mdm.py:284 "[1:]")
+  ROWMAP_HALO_TO_FRAMES = 3, // A row b*row_period + row_lo + l -> out row b*frames + l for l < frames (UNet output, mdm_unet.py:822)
 };
+constexpr int kMaxTaps = 10;
 
 // Output tensor maps for the TMA-store epilogue (identity row map only): bf16 planes with box {64, 32}, fp32 with
 // box {32, 32}; `rows` of each map must equal the number of valid output rows (TMA clips the M tail).
@@ -54,7 +56,7 @@ struct LinearParams {
   // deviations) over the 32 output columns starting at col (N must be 512); consumed by ln_partials / fold_stats
   float2* stats_out;
   const float* pos_enc;  // fp32 [L+1, N] table added per output sequence position (ROWMAP_FRAMES_TO_SEQ); or null
-  int act;               // 0 none, 1 exact erf GELU
+  int act;               // 0 none, 1 exact erf GELU, 3 Mish (x tanh(softplus(x)), nn.Mish)
   int f32_pre;           // 1: out_f32 receives the value BEFORE the activation (stash for the GELU backward)
   const float* grad_aux; // fp32 [rows, ld_aux] or null: multiply by gelu'(grad_aux[row, col])  (GELU backward)
   int ld_aux;
@@ -67,6 +69,16 @@ struct LinearParams {
   __nv_bfloat16* out_lo;  // written only when nsplit_out == 3
   int ld_bf;
   int nsplit_out;  // 1 or 3: whether the consumer of out_hi/out_lo wants the lo plane
+  // ---- 1-D convolutions as GEMMs over a channel-last [rows, C] activation (UNet denoiser, gemm2.cu) ----
+  // The reduction runs over num_taps blocks of k_per_tap columns; block j reads A at (row + tap_row[j], tap_a_col[j] + k)
+  // and W at column tap_w_col[j] + k.  A rows outside the tensor are zero-filled by TMA.  num_taps = 0: a plain linear layer.
+  int num_taps, k_per_tap;
+  int tap_row[kMaxTaps], tap_a_col[kMaxTaps], tap_w_col[kMaxTaps];
+  // rows are valid outputs when row_lo <= row % row_period < row_hi (the others are the zero halo between sequences and
+  // are WRITTEN AS ZEROS); row_period = 0: every row < M is valid
+  int row_period, row_lo, row_hi;
+  // output columns n >= n_split land at column n + n_gap (transposed-convolution even / odd phases into interleaved rows)
+  int n_split, n_gap;
   int debug;       // bring-up only (CMDI_DEBUG): 1 = skip global stores, 2 = skip MMA issue, 4 = skip TMA loads
   long long* dbg_cycles;  // bring-up only: per-CTA cycle counters [gridDim.x][16] (see gemm2.cu) or null
   int tma_store;   // set by the launcher when LinearStoreMaps are given: outputs leave through cp.async.bulk.tensor stores
@@ -244,6 +256,48 @@ cudaError_t launch_fold_ln(const float* W, int N, int K, const float* gamma, con
 // fp32 [rows, cols] -> bf16 planes [rows, ld] (zero padded columns)
 cudaError_t launch_split_planes(const float* in, int rows, int cols, int ld_in, __nv_bfloat16* hi, __nv_bfloat16* lo,
                                 int ld_out, cudaStream_t stream);
+
+// ----------------------------------------------------------------------------------------------
+// MDM_UNET denoiser pieces      (unet_kernels.cu; the convolutions run on the pair GEMM, gemm2.cu)
+// ----------------------------------------------------------------------------------------------
+struct UnetInputParams {
+  int B, L, D, D_pad;          // frame-major sources [B*L, D_pad]
+  const float* x_t;
+  const float* obs;            // observed keyframes (null: not keyframe-conditioned)
+  const uint8_t* obs_mask;
+  int copies;                  // 2 under CFG: sequences b and b + B receive the same input
+  int row_period, row_lo;      // halo layout of the destination
+  int ld;                      // destination row pitch (elements, even)
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+};
+cudaError_t launch_unet_input(const UnetInputParams& p, cudaStream_t stream);
+// emb planes [num_seqs, 512]; TokenParams::seq_len carries B (conditioning row = seq % B), x_f32 is unused
+cudaError_t launch_unet_emb(const TokenParams& p, cudaStream_t stream);
+struct GroupNormParams {
+  int C, groups, L;            // channels, groups, positions per sequence
+  int row_period, row_lo;      // halo layout (rows of sequence b: b * row_period + row_lo + l)
+  float eps;
+  const float* y;              // fp32 [rows, ld_y] convolution output (bias included)
+  int ld_y;
+  const float* gamma;
+  const float* beta;
+  const float* ada;            // [num_seqs, ld_ada] fp32: [scale (C) | shift (C)] per sequence, or null
+  int ld_ada;
+  const float* res_f32;        // residual added AFTER the activation: fp32 [rows, ld_res] ...
+  const __nv_bfloat16* res_hi; // ... or bf16 hi/lo planes [rows, ld_res] (x = hi + lo), or none
+  const __nv_bfloat16* res_lo;
+  int ld_res;
+  __nv_bfloat16* out_hi;       // planes [rows, ld_out] (pointer already offset to the first output column)
+  __nv_bfloat16* out_lo;
+  int ld_out;
+};
+cudaError_t configure_groupnorm_kernel();
+cudaError_t launch_groupnorm_mish(const GroupNormParams& p, int num_seqs, cudaStream_t stream);
+// weight re-layouts: Conv1d [Co,Ci,k] -> tap-major planes [Co, k*Cp]; ConvTranspose1d(4,2,1) [Ci,Co,4] -> planes [2Co, 3Ci]
+cudaError_t launch_conv_weight_planes(const float* w, int Co, int Ci, int k, int Cp, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld,
+                                      cudaStream_t stream);
+cudaError_t launch_convt_weight_planes(const float* w, int Ci, int Co, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld, cudaStream_t stream);
 
 // ----------------------------------------------------------------------------------------------
 // backward pieces for reconstruction guidance      (backward.cu)

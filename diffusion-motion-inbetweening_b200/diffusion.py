@@ -248,7 +248,14 @@ class GaussianDiffusion:
             init_image = torch.zeros(tuple(shape), device=device, dtype=torch.float32)
         if init_image is not None:
             init_image = init_image.to(device=device, dtype=torch.float32)
+        # keyframe INPUT conditioning (MDM_UNET.forward's obs_x0 / obs_mask): top-level model_kwargs, as
+        # sample/conditional_synthesis.py:159-162 passes them; the transformer ignores them
+        kf_obs, kf_mask = None, None
+        if eng.arch == capi.ARCH_UNET and model_kwargs.get("obs_x0") is not None:
+            kf_obs = model_kwargs["obs_x0"].to(device=device, dtype=torch.float32)
+            kf_mask = model_kwargs["obs_mask"].to(device=device)
         common = dict(batch=B, sampler=sampler, eta=eta, cond_emb=cond_emb, uncond=uncond, cfg=is_cfg, text_scale=text_scale,
+                      obs_x0=kf_obs, obs_mask=kf_mask,
                       y_mask=y_mask, imputate=imputate, stop_imputation_at=stop_at, inpainted_motion=obs,
                       inpainting_mask=mask, seed=seed, sample_offset=self.sample_offset, use_graph=self.use_graph,
                       recon_guidance=recon, stop_recguidance_at=stop_rg, recon_coef=coef, **rng_args)

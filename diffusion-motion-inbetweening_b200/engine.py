@@ -23,7 +23,8 @@ class Engine:
 
     def __init__(self, device: torch.device, njoints: int = 263, nframes: int = 196, latent_dim: int = 512,
                  ff_size: int = 1024, num_layers: int = 8, num_heads: int = 4, max_batch: int = 64, has_text: bool = False,
-                 precision: int = capi.PRECISION_BF16X3):
+                 precision: int = capi.PRECISION_BF16X3, arch: int = capi.ARCH_TRANS_ENC, unet_dim_mults: Sequence[int] = (),
+                 keyframe_conditioned: bool = False):
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("condmdi_b200 runs on CUDA devices only (no CPU fallback)")
@@ -31,8 +32,10 @@ class Engine:
             raise RuntimeError("no CUDA device available: condmdi_b200 has no CPU fallback")
         self.lib = capi.load()
         self.device = torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
+        mults = (ctypes.c_int32 * 4)(*([int(m) for m in unet_dim_mults] + [0] * (4 - len(unet_dim_mults))))
         self.cfg = capi.ModelCfg(njoints, nframes, latent_dim, ff_size, num_layers, num_heads, max_batch, int(has_text),
-                                 precision)
+                                 precision, int(arch), len(unet_dim_mults), mults, int(keyframe_conditioned))
+        self.arch = int(arch)
         self.njoints, self.nframes, self.max_batch, self.has_text, self.precision = njoints, nframes, max_batch, has_text, precision
         handle = ctypes.c_void_p()
         capi.check(self.lib.cmdi_engine_create(ctypes.byref(self.cfg), self.device.index, ctypes.byref(handle)),
@@ -83,7 +86,8 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, timestep: int, cond_emb: Optional[torch.Tensor] = None, uncond: bool = False,
-                cfg: bool = False, text_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+                cfg: bool = False, text_scale: Optional[torch.Tensor] = None, obs_x0: Optional[torch.Tensor] = None,
+                obs_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """MDM.forward / ClassifierFreeSampleModel.forward for a batch sharing one (original) timestep."""
         host = not x.is_cuda
         x = x.to(torch.float32).contiguous()
@@ -96,8 +100,12 @@ class Engine:
             t = t.to(torch.float32).contiguous()
             return t.cpu() if host else t.to(self.device)
 
-        cond_emb, text_scale = prep(cond_emb), prep(text_scale)
-        a = capi.ForwardArgs(B, _ptr(x), int(timestep), _ptr(cond_emb), int(uncond), int(cfg), _ptr(text_scale), int(host))
+        cond_emb, text_scale, obs_x0 = prep(cond_emb), prep(text_scale), prep(obs_x0)
+        if obs_mask is not None:
+            obs_mask = obs_mask.to(torch.uint8).contiguous()
+            obs_mask = obs_mask.cpu() if host else obs_mask.to(self.device)
+        a = capi.ForwardArgs(B, _ptr(x), int(timestep), _ptr(cond_emb), int(uncond), int(cfg), _ptr(text_scale), int(host),
+                             _ptr(obs_x0), _ptr(obs_mask))
         with torch.cuda.device(self.device):
             capi.check(self.lib.cmdi_model_forward(self._h, ctypes.byref(a), out.data_ptr(), _stream_ptr(self.device)),
                        "cmdi_model_forward")
@@ -113,7 +121,8 @@ class Engine:
                inpainted_motion: Optional[torch.Tensor] = None, inpainting_mask: Optional[torch.Tensor] = None,
                recon_guidance: bool = False, stop_recguidance_at: int = 0, recon_coef: Optional[Sequence[float]] = None,
                want_pred_xstart: bool = False, dump_steps: Optional[Sequence[int]] = None, host_buffers: bool = False,
-               use_graph: bool = True, out: Optional[torch.Tensor] = None):
+               use_graph: bool = True, out: Optional[torch.Tensor] = None, obs_x0: Optional[torch.Tensor] = None,
+               obs_mask: Optional[torch.Tensor] = None):
         """The whole sampling loop in one native call. Tensors are in the reference layout (B, njoints, 1, nframes).
 
         host_buffers=False: every tensor must live on this engine's device; the result is a device tensor and the
@@ -139,6 +148,7 @@ class Engine:
         y_mask = prep(y_mask, torch.uint8, (batch, self.nframes))
         inpainted_motion = prep(inpainted_motion, shp=shape)
         inpainting_mask = prep(inpainting_mask, torch.uint8, shape)
+        obs_x0, obs_mask = prep(obs_x0, shp=shape), prep(obs_mask, torch.uint8, shape)
         if noise_tape is not None:
             noise_tape = noise_tape.to(torch.float32).contiguous()
             if noise_tape.device != self.device:
@@ -169,7 +179,7 @@ class Engine:
                             _ptr(y_mask), int(imputate), int(stop_imputation_at), _ptr(inpainted_motion),
                             _ptr(inpainting_mask), int(recon_guidance), int(stop_recguidance_at), coef_arr, _ptr(pred), _ptr(dump),
                             dump_arr, n_dump, int(host_buffers),
-                            int(use_graph))
+                            int(use_graph), _ptr(obs_x0), _ptr(obs_mask))
         with torch.cuda.device(self.device):
             capi.check(self.lib.cmdi_sample(self._h, ctypes.byref(a), out.data_ptr(), _stream_ptr(self.device)),
                        "cmdi_sample")

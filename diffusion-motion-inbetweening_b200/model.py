@@ -49,15 +49,27 @@ def engine_for(self, device: torch.device, max_batch: int = 64, precision: int =
     sd = None
     if eng is None or eng.max_batch < max_batch:
         sd = {k: v for k, v in self.state_dict().items() if not k.startswith("clip_model.")}
-        num_layers = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("seqTransEncoder.layers."))
-        ff = sd["seqTransEncoder.layers.0.linear1.weight"].shape[0]
-        d = sd["input_process.poseEmbedding.weight"].shape[0]
-        njoints = sd["input_process.poseEmbedding.weight"].shape[1]
         if eng is not None:
             eng.close()
-        eng = Engine(device, njoints=njoints, nframes=nframes, latent_dim=d, ff_size=ff, num_layers=num_layers,
-                     num_heads=int(getattr(self, "num_heads", 4)), max_batch=max_batch,
-                     has_text="embed_text.weight" in sd, precision=precision)
+        if "unet.time_mlp.0.weight" in sd:
+            # MDM_UNET (model/mdm_unet.py): geometry read off the state dict
+            levels = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("unet.downs."))
+            d = sd["unet.time_mlp.0.weight"].shape[1]
+            mults = [sd[f"unet.downs.{l}.0.blocks.0.block1.0.weight"].shape[0] // d for l in range(levels)]
+            njoints = sd["unet.final_conv.1.weight"].shape[0]
+            in_ch = sd["unet.downs.0.0.blocks.0.block1.0.weight"].shape[1]
+            if in_ch not in (njoints, 2 * njoints) or "unet.downs.0.0.blocks.0.block.0.weight" in sd:
+                raise NotImplementedError("the B200 engine implements MDM_UNET with adagn=True and input_feats or 2 * input_feats channels")
+            eng = Engine(device, njoints=njoints, nframes=nframes, latent_dim=d, max_batch=max_batch, has_text="embed_text.weight" in sd,
+                         precision=precision, arch=capi.ARCH_UNET, unet_dim_mults=mults, keyframe_conditioned=in_ch == 2 * njoints)
+        else:
+            num_layers = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("seqTransEncoder.layers."))
+            ff = sd["seqTransEncoder.layers.0.linear1.weight"].shape[0]
+            d = sd["input_process.poseEmbedding.weight"].shape[0]
+            njoints = sd["input_process.poseEmbedding.weight"].shape[1]
+            eng = Engine(device, njoints=njoints, nframes=nframes, latent_dim=d, ff_size=ff, num_layers=num_layers,
+                         num_heads=int(getattr(self, "num_heads", 4)), max_batch=max_batch,
+                         has_text="embed_text.weight" in sd, precision=precision)
         eng._fingerprint = None
         cache[key] = eng
     fp = _state_fingerprint(self)
@@ -157,7 +169,114 @@ class MDM(nn.Module):
         return _forward_any(self, x, timesteps, y, cfg=False)
 
 
-def _forward_any(inner, x, timesteps, y, cfg: bool, text_scale=None):
+class MDM_UNET(nn.Module):
+    """The UNet denoiser of the published CondMDI checkpoints (reference: model/mdm_unet.py:561-849; arch='unet',
+    adagn, no attention), inference only, engine-backed.  Parameters live under the reference's state-dict keys."""
+
+    def __init__(self, modeltype="", njoints=263, nfeats=1, num_actions=1, translation=True, pose_rep="rot6d", glob=True,
+                 glob_rot=True, latent_dim=512, dim_mults=(2, 2, 2, 2), attention=False, ablation=None, legacy=False,
+                 data_rep="hml_vec", dataset="humanml", clip_dim=512, emb_trans_dec=False, clip_version=None, adagn=True,
+                 zero=True, arch="unet", unet_out_mult=8, xz_only=False, train_keypoint_mask="none", keyframe_conditioned=False,
+                 keyframe_selection_scheme="in-between", zero_keyframe_loss=False, **kwargs):
+        super().__init__()
+        if arch != "unet" or attention or not adagn or xz_only or train_keypoint_mask != "none" or nfeats != 1:
+            raise NotImplementedError("the B200 engine implements MDM_UNET arch='unet', adagn=True, attention=False")
+        if len(set(dim_mults)) != 1 or not 2 <= len(dim_mults) <= 4:
+            raise NotImplementedError("dim_mults must be 2..4 equal multipliers (every published configuration)")
+        self.njoints, self.nfeats, self.latent_dim, self.dim_mults = njoints, nfeats, latent_dim, tuple(dim_mults)
+        self.data_rep, self.dataset, self.arch, self.translation = data_rep, dataset, arch, translation
+        self.keyframe_conditioned = keyframe_conditioned
+        self.cond_mode = kwargs.get("cond_mode", "no_cond")
+        self.cond_mask_prob = kwargs.get("cond_mask_prob", 0.)
+        self.input_feats = njoints * nfeats
+        self.max_frames = kwargs.get("max_frames", 196)
+        self.rot2xyz = None
+        P, d = nn.Parameter, latent_dim
+        g = torch.Generator().manual_seed(0)
+
+        def uni(shape, bound):
+            return (torch.rand(*shape, generator=g) * 2 - 1) * bound
+
+        def put(key, t):
+            mod, leaf = self._container(key)
+            mod.register_parameter(leaf, P(t))
+
+        def conv(key, co, ci, k, transposed=False, zero_=False):
+            bound = 1.0 / math.sqrt(ci * k)
+            w = uni((ci, co, k) if transposed else (co, ci, k), bound)
+            put(key + ".weight", torch.zeros_like(w) if zero_ else w)
+            put(key + ".bias", torch.zeros(co) if zero_ else uni((co,), bound))
+
+        def lin(key, co, ci, zero_=False):
+            bound = 1.0 / math.sqrt(ci)
+            put(key + ".weight", torch.zeros(co, ci) if zero_ else uni((co, ci), bound))
+            put(key + ".bias", torch.zeros(co) if zero_ else uni((co,), bound))
+
+        def rtb(pre, ci, co):
+            conv(pre + "blocks.0.block1.0", co, ci, 5)
+            put(pre + "blocks.0.block1.2.weight", torch.ones(co)); put(pre + "blocks.0.block1.2.bias", torch.zeros(co))
+            conv(pre + "blocks.1.block.0", co, co, 5, zero_=zero)      # mdm_unet.py:53-56
+            put(pre + "blocks.1.block.2.weight", torch.ones(co)); put(pre + "blocks.1.block.2.bias", torch.zeros(co))
+            lin(pre + "time_mlp.1", 2 * co, d, zero_=True)             # :190-193
+            if ci != co:
+                conv(pre + "residual_conv", co, ci, 1)
+
+        lin("unet.time_mlp.0", 4 * d, d)
+        lin("unet.time_mlp.2", d, 4 * d)
+        dims = [self.input_feats] + [int(d * m) for m in dim_mults]
+        added = self.input_feats if keyframe_conditioned else 0
+        n = len(dim_mults)
+        for l in range(n):
+            rtb(f"unet.downs.{l}.0.", dims[l] + (added if l == 0 else 0), dims[l + 1])
+            rtb(f"unet.downs.{l}.1.", dims[l + 1], dims[l + 1])
+            if l + 1 < n:
+                conv(f"unet.downs.{l}.3.conv", dims[l + 1], dims[l + 1], 3)
+        rtb("unet.mid_block1.", dims[-1], dims[-1])
+        rtb("unet.mid_block2.", dims[-1], dims[-1])
+        for i, l in enumerate(range(n - 1, 0, -1)):
+            rtb(f"unet.ups.{i}.0.", dims[l + 1] * 2, dims[l])
+            rtb(f"unet.ups.{i}.1.", dims[l], dims[l])
+            conv(f"unet.ups.{i}.3.conv", dims[l], dims[l], 4, transposed=True)
+        conv("unet.final_conv.0.block.0", dims[1], dims[1], 5)
+        put("unet.final_conv.0.block.2.weight", torch.ones(dims[1])); put("unet.final_conv.0.block.2.bias", torch.zeros(dims[1]))
+        conv("unet.final_conv.1", self.input_feats, dims[1], 1, zero_=zero)
+        mod, leaf = self._container("sequence_pos_encoder.pe")
+        mod.register_buffer(leaf, _positional_encoding(d))
+        lin("embed_timestep.time_embed.0", d, d)
+        lin("embed_timestep.time_embed.2", d, d)
+        self._modules["embed_timestep"].add_module("sequence_pos_encoder", self._modules["sequence_pos_encoder"])
+        if "text" in self.cond_mode:
+            lin("embed_text", d, clip_dim)
+        for prm in self.parameters():
+            prm.requires_grad_(False)
+
+    def _container(self, path: str):
+        mod = self
+        parts = path.split(".")
+        for part in parts[:-1]:
+            if part not in mod._modules:
+                mod.add_module(part, nn.Module())
+            mod = mod._modules[part]
+        return mod, parts[-1]
+
+    engine_for = engine_for
+
+    def encode_text(self, raw_text):
+        raise NotImplementedError("attach a text encoder: model.encode_text = lambda texts: <(B,512) float tensor>")
+
+    def mask_cond(self, cond, force_mask=False):
+        return torch.zeros_like(cond) if force_mask else cond
+
+    def parameters_wo_clip(self):
+        return [p for name, p in self.named_parameters() if not name.startswith("clip_model.")]
+
+    def forward(self, x, timesteps, y=None, obs_x0=None, obs_mask=None):
+        """mdm_unet.py:765-783."""
+        assert (obs_x0 is None) == (obs_mask is None), 'with spatial-conditioning, both obs_x0 and obs_mask must be provided'
+        return _forward_any(self, x, timesteps, y, cfg=False, obs_x0=obs_x0, obs_mask=obs_mask)
+
+
+def _forward_any(inner, x, timesteps, y, cfg: bool, text_scale=None, obs_x0=None, obs_mask=None):
     y = {} if y is None else y
     if not x.is_cuda:
         raise RuntimeError("condmdi_b200 runs on CUDA tensors only (no CPU fallback)")
@@ -173,13 +292,17 @@ def _forward_any(inner, x, timesteps, y, cfg: bool, text_scale=None):
                 ysub["text"] = [ysub["text"][i] for i in idx.tolist()]
             if text_scale is not None:
                 ysub["text_scale"] = y["text_scale"][idx]
-            out[idx] = _forward_any(inner, x[idx], ts[idx], ysub, cfg, None if text_scale is None else text_scale[idx])
+            out[idx] = _forward_any(inner, x[idx], ts[idx], ysub, cfg, None if text_scale is None else text_scale[idx],
+                                    None if obs_x0 is None else obs_x0[idx], None if obs_mask is None else obs_mask[idx])
         return out
     eng = inner.engine_for(x.device, max_batch=x.shape[0], nframes=x.shape[-1])
     cond_emb = None
     if "text" in getattr(inner, "cond_mode", "no_cond"):
         cond_emb = inner.encode_text(y["text"]).to(device=x.device, dtype=torch.float32)
-    return eng.forward(x, t0, cond_emb=cond_emb, uncond=bool(y.get("uncond", False)), cfg=cfg, text_scale=text_scale)
+    if eng.arch != capi.ARCH_UNET:
+        obs_x0 = obs_mask = None  # the transformer accepts and ignores them (SURVEY 8b note 2)
+    return eng.forward(x, t0, cond_emb=cond_emb, uncond=bool(y.get("uncond", False)), cfg=cfg, text_scale=text_scale,
+                       obs_x0=obs_x0, obs_mask=obs_mask)
 
 
 class ClassifierFreeSampleModel(nn.Module):
@@ -203,7 +326,8 @@ class ClassifierFreeSampleModel(nn.Module):
         cond_mode = self.model.cond_mode
         assert cond_mode in ['text', 'action']
         # the caller's y is never mutated (the reference deep-copies it, cfg_sampler.py:28)
-        return _forward_any(self.model, x, timesteps, y, cfg=True, text_scale=y['text_scale'].reshape(-1))
+        return _forward_any(self.model, x, timesteps, y, cfg=True, text_scale=y['text_scale'].reshape(-1), obs_x0=obs_x0,
+                            obs_mask=obs_mask)
 
 
 def resolve_model(model) -> Tuple[nn.Module, bool]:
@@ -217,11 +341,11 @@ def resolve_model(model) -> Tuple[nn.Module, bool]:
         is_cfg = True
         inner = inner.model
     arch = getattr(inner, "arch", "trans_enc")
-    if arch != "trans_enc":
-        raise NotImplementedError(f"the B200 engine implements MDM arch='trans_enc' (got {arch!r}); MDM_UNET/DiT are out of scope")
+    if arch not in ("trans_enc", "unet"):
+        raise NotImplementedError(f"the B200 engine implements MDM arch='trans_enc' and MDM_UNET arch='unet' (got {arch!r})")
     if not hasattr(inner, "engine_for"):
         keys = inner.state_dict().keys()
-        if "seqTransEncoder.layers.0.self_attn.in_proj_weight" not in keys:
-            raise NotImplementedError(f"{type(inner).__name__} is not an MDM transformer encoder")
+        if "seqTransEncoder.layers.0.self_attn.in_proj_weight" not in keys and "unet.time_mlp.0.weight" not in keys:
+            raise NotImplementedError(f"{type(inner).__name__} is neither an MDM transformer encoder nor an MDM_UNET")
         inner.engine_for = types.MethodType(engine_for, inner)  # reference model: attach the engine accessor
     return inner, is_cfg

@@ -49,6 +49,7 @@ enum {
 };
 
 enum { CMDI_SAMPLER_DDPM = 0, CMDI_SAMPLER_DDIM = 1 };
+enum { CMDI_ARCH_TRANS_ENC = 0, CMDI_ARCH_UNET = 1 };
 enum { CMDI_RNG_ENGINE = 0, CMDI_RNG_TORCH = 1 };
 
 typedef struct {
@@ -61,6 +62,11 @@ typedef struct {
   int32_t max_batch;   /* largest B a call may use (buffers are sized for 2*max_batch sequences) */
   int32_t has_text;    /* cond_mode contains 'text': embed_text weights are expected             mdm.py:137-139 */
   int32_t precision;   /* CMDI_PRECISION_* */
+  /* denoiser architecture: the MDM transformer encoder above, or MDM_UNET (model/mdm_unet.py, arch='unet', AdaGN) */
+  int32_t arch;                  /* CMDI_ARCH_TRANS_ENC / CMDI_ARCH_UNET                          model_util.py:26-35 */
+  int32_t unet_levels;           /* len(dim_mults), 2..4                                           configs/model.py:28-67 */
+  int32_t unet_dim_mults[4];     /* channels of level l = latent_dim * unet_dim_mults[l] (equal across levels) */
+  int32_t keyframe_conditioned;  /* the input is cat([obs_x0*M + x*~M, M]) (2 * njoints channels)  mdm_unet.py:636-643, :778-783 */
 } cmdi_model_cfg;
 
 typedef struct {
@@ -81,6 +87,9 @@ typedef struct {
   int32_t cfg;                /* ClassifierFreeSampleModel.forward */
   const float* text_scale;    /* (B,) when cfg */
   int32_t host_buffers;
+  const float* obs_x0;        /* ref layout observed keyframes and ... */
+  const uint8_t* obs_mask;    /* ... their bool mask: the obs_x0 / obs_mask arguments of MDM_UNET.forward (mdm_unet.py:765);
+                                 NULL for the transformer (which ignores them, SURVEY 8b note 2) */
 } cmdi_forward_args;
 
 typedef struct {
@@ -128,6 +137,10 @@ typedef struct {
   int32_t host_buffers;         /* 1: every pointer above and `out` are HOST pointers (copies happen inside the call) */
   int32_t use_graph;            /* 0: plain launches; 1: one captured CUDA graph replayed per step for calls of >= 3 steps
                                    (default); 2: also for one-step calls (the *_progressive generators) */
+  /* keyframe INPUT conditioning of MDM_UNET: model_kwargs['obs_x0'] / ['obs_mask'] (sample/conditional_synthesis.py:159-162),
+     constant over the loop; NULL for models that do not consume them */
+  const float* obs_x0;          /* ref layout */
+  const uint8_t* obs_mask;      /* ref layout, bool bytes (NOT and-ed with y['mask']) */
 } cmdi_sample_args;
 
 CMDI_API int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_engine** out);

@@ -200,6 +200,138 @@ def cfg_forward(sd, x, timesteps, cond_emb, text_scale: torch.Tensor, num_heads:
 
 
 # ------------------------------------------------------------------------------------------------
+# MDM_UNET (model/mdm_unet.py): the denoiser of the published CondMDI checkpoints  
+# ------------------------------------------------------------------------------------------------
+def _conv_gn(x, sd, conv: str, gn: str, groups: int = 8):
+    """Conv1d(k, padding=k//2) -> GroupNorm(8)   (Conv1dBlock / Conv1dAdaGNBlock.block1, mdm_unet.py:33-88)"""
+    w = sd[conv + ".weight"]
+    x = F.conv1d(x, w, sd[conv + ".bias"], padding=w.shape[-1] // 2)
+    return F.group_norm(x, groups, sd[gn + ".weight"], sd[gn + ".bias"], 1e-5)
+
+
+def _residual_temporal_block(x, emb_mish, sd, pre: str):
+    """ResidualTemporalBlock with adagn=True (mdm_unet.py:163-218): x (B, C_in, L), emb_mish = Mish(c) (B, 512)"""
+    cond = F.linear(emb_mish, sd[pre + "time_mlp.1.weight"], sd[pre + "time_mlp.1.bias"]).unsqueeze(-1)  # (B, 2*C_out, 1)
+    scale, shift = cond.chunk(2, dim=1)
+    out = _conv_gn(x, sd, pre + "blocks.0.block1.0", pre + "blocks.0.block1.2")
+    out = F.mish(out * (1 + scale) + shift)                                  # ada_shift_scale (:159-160) then Mish
+    out = F.mish(_conv_gn(out, sd, pre + "blocks.1.block.0", pre + "blocks.1.block.2"))
+    if pre + "residual_conv.weight" in sd:
+        x = F.conv1d(x, sd[pre + "residual_conv.weight"], sd[pre + "residual_conv.bias"])
+    return out + x
+
+
+def unet_levels_of(sd) -> int:
+    return 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("unet.downs."))
+
+
+def unet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, timesteps: torch.Tensor, cond_emb: Optional[torch.Tensor] = None,
+                 uncond: bool = False, obs_x0: Optional[torch.Tensor] = None, obs_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """MDM_UNET.forward + forward_core + TemporalUnet.forward (mdm_unet.py:765-849, :309-350), arch='unet', adagn,
+    no attention, hml_vec.  keyframe-conditioned when obs_x0 / obs_mask are given (:778-783)."""
+    assert (obs_x0 is None) == (obs_mask is None)
+    if obs_x0 is not None:
+        x = obs_x0 * obs_mask + x * (~obs_mask)
+        x = torch.cat([x, obs_mask.to(x.dtype)], dim=1)
+    bs, njoints, nfeats, nframes = x.shape
+    pe = sd["sequence_pos_encoder.pe"] if "sequence_pos_encoder.pe" in sd else sd["embed_timestep.sequence_pos_encoder.pe"]
+    emb = F.linear(F.silu(F.linear(pe[timesteps], sd["embed_timestep.time_embed.0.weight"], sd["embed_timestep.time_embed.0.bias"])),
+                   sd["embed_timestep.time_embed.2.weight"], sd["embed_timestep.time_embed.2.bias"]).permute(1, 0, 2)  # (1, B, d)
+    if cond_emb is not None:
+        cmask = torch.zeros_like(cond_emb) if uncond else cond_emb
+        emb = emb + F.linear(cmask, sd["embed_text.weight"], sd["embed_text.bias"])
+    emb = emb.squeeze(0)
+    h = x.permute(3, 0, 1, 2).reshape(nframes, bs, njoints * nfeats)
+    h = F.pad(h, (0, 0, 0, 0, 0, 224 - nframes), value=0)            # right-pad to the training length (:817)
+    h = h.permute(1, 2, 0)                                            # 's b d -> b d s'
+    c = F.linear(F.mish(F.linear(emb, sd["unet.time_mlp.0.weight"], sd["unet.time_mlp.0.bias"])),
+                 sd["unet.time_mlp.2.weight"], sd["unet.time_mlp.2.bias"])
+    cm = F.mish(c)                                                    # every block's time_mlp starts with Mish (:183)
+    levels = unet_levels_of(sd)
+    skips = []
+    for l in range(levels):
+        h = _residual_temporal_block(h, cm, sd, f"unet.downs.{l}.0.")
+        h = _residual_temporal_block(h, cm, sd, f"unet.downs.{l}.1.")
+        skips.append(h)
+        if l + 1 < levels:
+            h = F.conv1d(h, sd[f"unet.downs.{l}.3.conv.weight"], sd[f"unet.downs.{l}.3.conv.bias"], stride=2, padding=1)
+    h = _residual_temporal_block(h, cm, sd, "unet.mid_block1.")
+    h = _residual_temporal_block(h, cm, sd, "unet.mid_block2.")
+    for i in range(levels - 1):
+        h = torch.cat((h, skips.pop()), dim=1)
+        h = _residual_temporal_block(h, cm, sd, f"unet.ups.{i}.0.")
+        h = _residual_temporal_block(h, cm, sd, f"unet.ups.{i}.1.")
+        h = F.conv_transpose1d(h, sd[f"unet.ups.{i}.3.conv.weight"], sd[f"unet.ups.{i}.3.conv.bias"], stride=2, padding=1)
+    h = F.mish(_conv_gn(h, sd, "unet.final_conv.0.block.0", "unet.final_conv.0.block.2"))
+    h = F.conv1d(h, sd["unet.final_conv.1.weight"], sd["unet.final_conv.1.bias"])
+    out = h.permute(2, 0, 1)[:nframes]                                # 'b d s -> s b d', drop the padding
+    njoints_out = out.shape[-1]
+    return out.reshape(nframes, bs, njoints_out, 1).permute(1, 2, 3, 0).float()
+
+
+def random_unet_state_dict(seed: int = 0, dim: int = 512, mults: Sequence[int] = (2, 2, 2, 2), feats: int = 263,
+                           keyframe_conditioned: bool = True, text: bool = False) -> Dict[str, torch.Tensor]:
+    """Random weights with the MDM_UNET state-dict key set (arch='unet', adagn) at PyTorch-default-like scales -- every
+    tensor non-zero (the reference's `zero=True` init would make a random-init model output zeros)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def uni(shape, bound):
+        return (torch.rand(*shape, generator=g) * 2 - 1) * bound
+
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(key, co, ci, k, transposed=False):
+        bound = 1.0 / math.sqrt(ci * k)
+        sd[key + ".weight"] = uni((ci, co, k) if transposed else (co, ci, k), bound)
+        sd[key + ".bias"] = uni((co,), bound)
+
+    def gn(key, c):
+        sd[key + ".weight"] = 1.0 + 0.1 * uni((c,), 1.0)
+        sd[key + ".bias"] = 0.1 * uni((c,), 1.0)
+
+    def lin(key, co, ci, gain=1.0):
+        bound = gain / math.sqrt(ci)
+        sd[key + ".weight"] = uni((co, ci), bound)
+        sd[key + ".bias"] = uni((co,), bound)
+
+    def rtb(pre, ci, co):
+        conv(pre + "blocks.0.block1.0", co, ci, 5)
+        gn(pre + "blocks.0.block1.2", co)
+        conv(pre + "blocks.1.block.0", co, co, 5)
+        gn(pre + "blocks.1.block.2", co)
+        lin(pre + "time_mlp.1", 2 * co, dim, gain=0.5)
+        if ci != co:
+            conv(pre + "residual_conv", co, ci, 1)
+
+    lin("unet.time_mlp.0", dim * 4, dim)
+    lin("unet.time_mlp.2", dim, dim * 4)
+    dims = [feats] + [int(dim * m) for m in mults]
+    added = feats if keyframe_conditioned else 0
+    n = len(mults)
+    for l in range(n):
+        rtb(f"unet.downs.{l}.0.", dims[l] + (added if l == 0 else 0), dims[l + 1])
+        rtb(f"unet.downs.{l}.1.", dims[l + 1], dims[l + 1])
+        if l + 1 < n:
+            conv(f"unet.downs.{l}.3.conv", dims[l + 1], dims[l + 1], 3)
+    rtb("unet.mid_block1.", dims[-1], dims[-1])
+    rtb("unet.mid_block2.", dims[-1], dims[-1])
+    for i, l in enumerate(range(n - 1, 0, -1)):           # reversed(in_out[1:]): (dim_in, dim_out) = (dims[l], dims[l + 1])
+        rtb(f"unet.ups.{i}.0.", dims[l + 1] * 2, dims[l])
+        rtb(f"unet.ups.{i}.1.", dims[l], dims[l])
+        conv(f"unet.ups.{i}.3.conv", dims[l], dims[l], 4, transposed=True)
+    conv("unet.final_conv.0.block.0", dims[1], dims[1], 5)
+    gn("unet.final_conv.0.block.2", dims[1])
+    conv("unet.final_conv.1", feats, dims[1], 1)
+    sd["sequence_pos_encoder.pe"] = positional_encoding(dim)
+    sd["embed_timestep.sequence_pos_encoder.pe"] = sd["sequence_pos_encoder.pe"]
+    for j in (0, 2):
+        lin(f"embed_timestep.time_embed.{j}", dim, dim)
+    if text:
+        lin("embed_text", dim, 512)
+    return sd
+
+
+# ------------------------------------------------------------------------------------------------
 # keyframe masks and guidance schedule
 # ------------------------------------------------------------------------------------------------
 
@@ -312,9 +444,22 @@ class Conditioning:
     gradient_schedule: Optional[str] = None
     diffusion_steps: int = 1000
     stop_recguidance_at: int = 0
+    # top-level model_kwargs of sample/conditional_synthesis.py:159-162 (consumed by MDM_UNET.forward, ignored by MDM)
+    obs_x0: Optional[torch.Tensor] = None
+    obs_mask: Optional[torch.Tensor] = None      # bool (B,263,1,L)
+
+
+def is_unet(sd) -> bool:
+    return "unet.time_mlp.0.weight" in sd
 
 
 def _model(sd, x, t_model, c: Conditioning):
+    if is_unet(sd):
+        if c.cfg:
+            out = unet_forward(sd, x, t_model, c.cond_emb, False, c.obs_x0, c.obs_mask)
+            out_u = unet_forward(sd, x, t_model, c.cond_emb, True, c.obs_x0, c.obs_mask)
+            return out_u + (c.text_scale.view(-1, 1, 1, 1) * (out - out_u))  # cfg_sampler.py:25-35
+        return unet_forward(sd, x, t_model, c.cond_emb, False, c.obs_x0, c.obs_mask)
     if c.cfg:
         return cfg_forward(sd, x, t_model, c.cond_emb, c.text_scale)
     return mdm_forward(sd, x, t_model, c.cond_emb)

@@ -327,13 +327,67 @@ def golden_chains():
     np.savez_compressed(os.path.join(GOLDEN, "chains.npz"), **out)
 
 
+def golden_unet():
+    """MDM_UNET (arch='unet', adagn, dim 512 x (2,2,2,2), keyframe-conditioned: configs/model.py `motion_unet_adagn_xl`): one
+    evaluation, the CFG-wrapped evaluation, and p_sample_loop steps with the keyframes given as top-level obs_x0 / obs_mask
+    model_kwargs the way sample/conditional_synthesis.py:159-162 passes them."""
+    print("MDM_UNET")
+    ref = RH.import_reference()
+    out = {}
+    gi = O.golden_inputs()
+    x, cond, x_obs, tape, scale, lengths, y_mask, kf_mask = (gi[k] for k in (
+        "x", "cond", "x_obs", "tape", "text_scale", "lengths", "y_mask", "kf_mask"))
+    sd = O.random_unet_state_dict(seed=11, text=True)
+    m = RH.build_reference_unet(text=True)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    m._synthetic_text_emb = cond
+    t_model = torch.tensor([999, 37])
+    with torch.no_grad():
+        r = m(x, t_model, y={"text": ["a", "b"]}, obs_x0=x_obs, obs_mask=kf_mask)
+        r_u = m(x, t_model, y={"text": ["a", "b"], "uncond": True}, obs_x0=x_obs, obs_mask=kf_mask)
+        cfgm = ref.cfg_sampler.ClassifierFreeSampleModel(m)
+        r_cfg = cfgm(x, torch.tensor([500, 500]), y={"text": ["a", "b"], "text_scale": scale}, obs_x0=x_obs, obs_mask=kf_mask)
+    close(r, O.unet_forward(sd, x, t_model, cond, False, x_obs, kf_mask), 1e-5, "unet forward (text, keyframes)")
+    close(r_u, O.unet_forward(sd, x, t_model, cond, True, x_obs, kf_mask), 1e-5, "unet forward (uncond)")
+    c = O.Conditioning(cond_emb=cond, cfg=True, text_scale=scale, obs_x0=x_obs, obs_mask=kf_mask)
+    close(r_cfg, O._model(sd, x, torch.tensor([500, 500]), c), 2e-5, "unet cfg forward")
+    out["fwd.t"] = t_model.numpy()
+    out["fwd.out"] = r.numpy()
+    out["fwd_uncond.out"] = r_u.numpy()
+    out["fwd_cfg.out"] = r_cfg.numpy()
+
+    diff = RH.build_reference_diffusion("")
+    tab = O.make_tables("")
+    kw = {"y": {"text": ["a", "b"], "text_scale": scale, "mask": y_mask, "lengths": lengths}, "obs_x0": x_obs, "obs_mask": kf_mask}
+    print("p_sample_loop, CFG + keyframe-conditioned UNet, 3 steps from t = 999 and the last 4 steps")
+    outs = []
+    with RH.noise_tape(tape):
+        for k, o_ in enumerate(diff.p_sample_loop_progressive(cfgm, (B, D, 1, L), model_kwargs=kw, device="cpu", clip_denoised=False)):
+            outs.append(o_)
+            if k == 2:
+                break
+    o = O.sample_loop(sd, tab, (B, D, 1, L), c, tape, "ddpm", max_steps=3, return_all=True)
+    close(outs[-1]["sample"], o[-1]["sample"], 5e-5, "unet ddpm 3 steps")
+    out["ddpm3.sample"] = outs[-1]["sample"].numpy()
+    out["ddpm3.pred_xstart"] = outs[-1]["pred_xstart"].numpy()
+    with RH.noise_tape(tape):
+        r_tail = diff.p_sample_loop(cfgm, (B, D, 1, L), model_kwargs=kw, device="cpu", clip_denoised=False, skip_timesteps=996,
+                                    init_image=x_obs)
+    o_tail = O.sample_loop(sd, tab, (B, D, 1, L), c, tape, "ddpm", skip_timesteps=996, init_image=x_obs)
+    close(r_tail, o_tail, 5e-5, "unet ddpm tail")
+    out["tail4.sample"] = r_tail.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "unet.npz"), **out)
+
+
 def main():
     if not RH.available():
         raise SystemExit("the reference tree is required to (re)generate golden vectors")
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     parts = {"schedules": golden_schedules, "masks": golden_masks, "sampler": golden_model_and_sampler,
-             "postprocess": golden_postprocess, "long_loop": golden_long_loop, "chains": golden_chains}
+             "postprocess": golden_postprocess, "long_loop": golden_long_loop, "chains": golden_chains,
+             "unet": golden_unet}
     for name in (sys.argv[1:] or list(parts)):  # `python -m oracle.make_golden chains` regenerates one fixture file
         parts[name]()
     for f in sorted(os.listdir(GOLDEN)):

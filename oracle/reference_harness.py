@@ -97,6 +97,24 @@ def build_reference_model(seed: int = 0, text: bool = False, layers: int = 8, la
     return model
 
 
+def build_reference_unet(dim_mults=(2, 2, 2, 2), latent_dim: int = 512, keyframe_conditioned: bool = True, text: bool = False):
+    """MDM_UNET as utils/model_util.py:30-32 builds it for configs/model.py `motion_unet_adagn_xl` (arch='unet', adagn, zero)."""
+    import_reference()
+    import model.mdm_unet as ref_unet  # noqa: E402
+    with contextlib.redirect_stdout(open(os.devnull, "w")):
+        model = ref_unet.MDM_UNET(modeltype="", njoints=263, nfeats=1, num_actions=1, translation=True, pose_rep="rot6d", glob=True,
+                                  glob_rot=True, latent_dim=latent_dim, dim_mults=tuple(dim_mults), data_rep="hml_vec",
+                                  dataset="humanml", cond_mode="no_cond", cond_mask_prob=0.1, adagn=True, zero=True, arch="unet",
+                                  keyframe_conditioned=keyframe_conditioned)
+    if text:
+        model.cond_mode = "text"
+        model.embed_text = torch.nn.Linear(512, latent_dim)
+        model._synthetic_text_emb = None
+        model.encode_text = lambda raw_text: model._synthetic_text_emb
+    model.eval()
+    return model
+
+
 def build_reference_diffusion(respacing: str = "", steps: int = 1000):
     """utils/model_util.py:122-165 with noise_schedule='cosine', sigma_small, predict_xstart."""
     ref = import_reference()

@@ -31,7 +31,7 @@ def test_struct_layouts_match_header_field_counts():
                        ("cmdi_forward_args", C.capi.ForwardArgs), ("cmdi_sample_args", C.capi.SampleArgs)):
         body = re.search(r"typedef struct \{([^}]*)\} " + cname + ";", header).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-        fields = [f.strip().split()[-1].lstrip("*") for f in body.split(";") if f.strip()]
+        fields = [re.sub(r"\[\d+\]$", "", f.strip().split()[-1].lstrip("*")) for f in body.split(";") if f.strip()]
         assert fields == [f[0] for f in cls._fields_], cname
 
 

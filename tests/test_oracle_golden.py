@@ -176,3 +176,20 @@ def test_oracle_long_chains_vs_reference_golden(golden_dir):
     got = O.sample_loop(sdt, O.make_tables(""), (B, D, 1, L), c, tape[torch.arange(51) % 8], "ddpm", skip_timesteps=950,
                         init_image=gi["x_obs"])
     assert torch.allclose(got, torch.from_numpy(g["cfg_impute50.sample"]), rtol=1e-4, atol=5e-5)
+
+
+def test_oracle_unet_vs_reference_golden(golden_dir):
+    """tests/golden/unet.npz: the reference's MDM_UNET (dim 512 x (2,2,2,2), AdaGN, keyframe-conditioned, text)."""
+    g = np.load(os.path.join(golden_dir, "unet.npz"))
+    gi = O.golden_inputs()
+    sd = O.random_unet_state_dict(seed=11, text=True)
+    assert O.is_unet(sd) and O.unet_levels_of(sd) == 4
+    t = torch.from_numpy(g["fwd.t"])
+    with torch.no_grad():
+        got = O.unet_forward(sd, gi["x"], t, gi["cond"], False, gi["x_obs"], gi["kf_mask"])
+        got_u = O.unet_forward(sd, gi["x"], t, gi["cond"], True, gi["x_obs"], gi["kf_mask"])
+    assert torch.allclose(got, torch.from_numpy(g["fwd.out"]), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(got_u, torch.from_numpy(g["fwd_uncond.out"]), rtol=1e-5, atol=1e-6)
+    c = O.Conditioning(cond_emb=gi["cond"], cfg=True, text_scale=gi["text_scale"], obs_x0=gi["x_obs"], obs_mask=gi["kf_mask"])
+    tail = O.sample_loop(sd, O.make_tables(""), (B, D, 1, L), c, gi["tape"], "ddpm", skip_timesteps=996, init_image=gi["x_obs"])
+    assert torch.allclose(tail, torch.from_numpy(g["tail4.sample"]), rtol=1e-5, atol=2e-6)
