@@ -21,15 +21,13 @@
 //   consumer epilogue: ordered after the TMA lane's acquire through full[] -> MMA -> tmem_full[]; its reads of
 //                      activations written in this launch use ld.global.cg
 //
-// Epilogue.  Measured on the first version of this kernel (8 epilogue warps, 64-column chunks): the epilogue, not the
-// tensor pipe, set the pace -- 13k .. 44k cycles per tile against a 12.3k-cycle K = 512 mainloop -- because two warps
-// per scheduler cannot hide the global-load, TMA-store-readout and fence latencies of a long serial per-chunk
-// program.  Now: TWELVE epilogue warps (three per TMEM lane group; 128 registers each), the accumulator tile is cut
-// into eight 32-column slices handed round-robin to the three warps of a lane group (so the next tile's slices start
-// while the previous tile's are still being written), a slice is one fp32 TMA store + one store of both bf16 planes
-// through 64-byte-swizzled boxes, per-column constants come from broadcast loads instead of shuffles, and the
-// release fence / counter bump lives in a warp of its own.  Shared memory: A ring 3 x 32 KB, W ring 2 x 32 KB
-// (separate barriers), 12 x 4 KB staging tiles.
+// Epilogue (see also the note at CMDI_CHAIN_EPI_WARPS).  The first version of this kernel processed 64-column chunks
+// per warp with shuffled per-column constants and a release fence per warp: 13k .. 44k cycles of epilogue per tile against
+// a 12.3k-cycle K = 512 mainloop.  Now the accumulator tile is cut into eight 32-column slices handed round-robin to the
+// warps of a TMEM lane group (the next tile's slices start while the previous tile's are still being written); a slice
+// is one fp32 TMA store + one store of both bf16 planes through 64-byte-swizzled boxes; per-column constants come from
+// broadcast loads instead of shuffles; GELU uses a branch-free rational erf; and the release fence / counter bump lives
+// in a warp of its own.  Shared memory: A ring 3 x 32 KB, W ring 3 x 32 KB (separate barriers), 8 x 4 KB staging tiles.
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include "kernels.h"
@@ -42,10 +40,21 @@ constexpr int kBlockM = 128;  // per CTA; 256 per pair
 constexpr int kBlockN = 256;
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
-constexpr int kNumEpiWarps = 12;
+// Epilogue warps and W-ring depth are tied through shared memory: 8 warps x 4 KB staging leave room for 3 + 3 operand
+// stages, 12 warps only for 3 + 2.  Measured at B = 64 (same box, A/B/A/B): 12 warps / 3 + 2 stages 482 steps/s,
+// 12 warps with 2 KB tiles / 3 + 3 stages 504, 8 warps / 3 + 3 stages 520 -- the FFN1 (GELU) epilogue is issue-bound, not
+// latency-bound, so more warps at 128 registers lose to fewer at 168, and the deeper W ring is worth 6 %.
+#ifndef CMDI_CHAIN_EPI_WARPS
+#define CMDI_CHAIN_EPI_WARPS 8
+#endif
+#ifndef CMDI_CHAIN_STAGES_W
+#define CMDI_CHAIN_STAGES_W 3
+#endif
+constexpr int kNumEpiWarps = CMDI_CHAIN_EPI_WARPS;
+constexpr int kWarpsPerLaneGroup = kNumEpiWarps / 4;
 constexpr int kFirstEpiWarp = 3;
 constexpr int kNumThreads = (kFirstEpiWarp + kNumEpiWarps) * 32;
-constexpr int kStagesA = 3, kStagesW = 2;
+constexpr int kStagesA = 3, kStagesW = CMDI_CHAIN_STAGES_W;
 constexpr int kPlaneBytes = kBlockM * kBlockK * 2;   // one bf16 plane of a 128-row x 64-column operand block = 16 KB
 constexpr int kOperandBytes = 2 * kPlaneBytes;       // hi + lo
 constexpr int kSlices = kBlockN / 32;                // 32-column slices per tile
@@ -86,27 +95,33 @@ __device__ __forceinline__ void wait_counter(const int* ctr, int target) {
   }
 }
 
-// (mean, rstd) of a 512-wide row from the 16 partial statistics (mean_j, M2_j) of its 32-column slices
-// (Chan et al. parallel combination with equal counts; fp32 throughout)
+// Partial LayerNorm statistics: every epilogue warp Chan-combines the (mean, M2) of its slices of a tile in registers and
+// publishes ONE partial per row, so a 512-wide row has kRowPartials = (512 / 256) * kWarpsPerLaneGroup partials of
+// 512 / kRowPartials columns each.
+static_assert(kSlices % kWarpsPerLaneGroup == 0, "equal column counts per partial");
+constexpr int kRowPartials = 2 * kWarpsPerLaneGroup;
+constexpr int kPartialStride = 16;  // float2 per row in the statistics arrays (engine.cu allocates 16)
+
+// (mean, rstd) of a 512-wide row from its partial statistics (Chan et al. parallel combination, equal counts; fp32)
 __device__ __forceinline__ float2 combine_row_stats(const float2* partials_row) {
-  float m[16], q = 0.f, s = 0.f;
+  float m[kRowPartials], q = 0.f, s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < kRowPartials / 2; ++i) {
     const uint4 a = ld_global_cg_v4(partials_row + 2 * i);
     m[2 * i] = __uint_as_float(a.x);
     m[2 * i + 1] = __uint_as_float(a.z);
     q += __uint_as_float(a.y) + __uint_as_float(a.w);
   }
 #pragma unroll
-  for (int i = 0; i < 16; ++i) s += m[i];
-  const float mean = s * (1.0f / 16.0f);
+  for (int i = 0; i < kRowPartials; ++i) s += m[i];
+  const float mean = s * (1.0f / kRowPartials);
   float dev = 0.f;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < kRowPartials; ++i) {
     const float d = m[i] - mean;
     dev = fmaf(d, d, dev);
   }
-  const float var = (q + 32.0f * dev) * (1.0f / 512.0f);
+  const float var = (q + (512.0f / kRowPartials) * dev) * (1.0f / 512.0f);
   return make_float2(mean, rsqrtf(var + 1e-5f));  // nn.LayerNorm default eps, as nn.TransformerEncoderLayer uses it
 }
 
@@ -132,21 +147,69 @@ __device__ __forceinline__ void store_planes_tma(uint32_t stage, int lane, const
   }
 }
 
-struct RowStats {   // per-tile cache of the row statistics this thread needs (its row of the tile)
-  float2 fold, ln;
+// erf(x) as a rational function of the clamped argument (numerator degree 13, denominator degree 8 in x; max abs error
+// 3.7e-7 over the real line, checked against math.erf in tests/test_host_logic.py): branch-free, 14 FMAs + one division.
+// The FFN1 epilogue is issue-bound and CUDA's erff (two polynomial branches + exp) was its largest single item (8 % of
+// the chain kernel's samples); |GELU error| <= 6.4e-7 against 2^-17 ~ 7.6e-6 relative of the bf16x3 products around it.
+__device__ __forceinline__ float erf_rational(float x) {
+  x = fminf(fmaxf(x, -4.0f), 4.0f);
+  const float x2 = x * x;
+  float p = -2.72614225801306e-10f;
+  p = fmaf(p, x2, 2.77068142495902e-08f);
+  p = fmaf(p, x2, -2.10102402082508e-06f);
+  p = fmaf(p, x2, -5.69250639462346e-05f);
+  p = fmaf(p, x2, -7.34990630326855e-04f);
+  p = fmaf(p, x2, -2.95459980854025e-03f);
+  p = fmaf(p, x2, -1.60960333262415e-02f);
+  float q = -1.45660718464996e-05f;
+  q = fmaf(q, x2, -2.13374055278905e-04f);
+  q = fmaf(q, x2, -1.68282697438203e-03f);
+  q = fmaf(q, x2, -7.37332916720468e-03f);
+  q = fmaf(q, x2, -1.42647390514189e-02f);
+  return __fdividef(x * p, q);
+}
+__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_rational(x * 0.70710678118654752440f)); }
+
+constexpr int kSlicesPerWarp = (kSlices + kWarpsPerLaneGroup - 1) / kWarpsPerLaneGroup;  // of one tile
+
+struct RowStats {   // per-tile cache of what this thread needs for its slices of the tile
+  float2 fold, ln;                 // (mean, rstd) of its row: folded LayerNorm of the A operand / LayerNorm of the residual
+  // Per-COLUMN constants (bias, folded-LN c, LayerNorm gamma / beta of the residual): lane l holds column l of the warp's
+  // k-th slice of the tile, loaded with one coalesced request per vector at the tile's first slice and handed out by
+  // shuffle.  (Fetched per use they were ~15 % of this kernel's stall samples: the tile's constants are rarely in the
+  // ~25 KB of L1 left beside 224 KB of shared memory, and an L2 round trip costs 2-3 us under this load.)
+  float bias[kSlicesPerWarp], c[kSlicesPerWarp], g[kSlicesPerWarp], b[kSlicesPerWarp];
+  float run_mean, run_m2;          // running statistics of this thread's output row over the warp's slices of the tile
 };
+__device__ __forceinline__ float pick(const float (&a)[kSlicesPerWarp], int k) {
+  float v = a[0];
+#pragma unroll
+  for (int i = 1; i < kSlicesPerWarp; ++i) v = (k == i) ? a[i] : v;
+  return v;
+}
 
 // One 32-column slice of a 128-row accumulator: TMEM -> registers -> [folded LayerNorm] -> bias -> [residual] ->
 // [partial statistics] -> [GELU] -> fp32 rows and/or bf16 hi/lo planes.
 __device__ __forceinline__ void epilogue_slice(const LinearParams& p, const ChainPhaseDesc& pd, uint32_t tmem_acc, int m_blk, int n_blk,
-                                               int slice, int lane_group, int lane, uint32_t stage, RowStats& rs, bool new_tile, long long* dbg) {
+                                               int slice, int k_in_tile, int lane_group, int lane, uint32_t stage, RowStats& rs, bool new_tile, uint4 (&rv)[8],
+                                               bool& rv_ready, int next_slice, int warp_in_group, long long* dbg) {
   long long t0 = clock64(), t1;
 #define CMDI_T(i) do { if (dbg) { t1 = clock64(); dbg[i] += t1 - t0; t0 = t1; } } while (0)
   const int warp_row0 = m_blk * kBlockM + lane_group * 32;
   const int row = warp_row0 + lane;
   if (new_tile) {
-    if (p.fold_stats) rs.fold = combine_row_stats(p.fold_stats + (size_t)row * 16);
-    if (p.ln_partials) rs.ln = combine_row_stats(p.ln_partials + (size_t)row * 16);
+#pragma unroll
+    for (int k = 0; k < kSlicesPerWarp; ++k) {
+      const int n = n_blk * kBlockN + (slice + k * kWarpsPerLaneGroup) * 32 + lane;
+      const bool ok = slice + k * kWarpsPerLaneGroup < kSlices && n < p.N;
+      rs.bias[k] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
+      rs.c[k] = (ok && p.fold_stats) ? __ldg(p.fold_c + n) : 0.f;
+      rs.g[k] = (ok && p.ln_src) ? __ldg(p.ln_gamma + n) : 0.f;
+      rs.b[k] = (ok && p.ln_src) ? __ldg(p.ln_beta + n) : 0.f;
+    }
+    if (p.fold_stats) rs.fold = combine_row_stats(p.fold_stats + (size_t)row * kPartialStride);
+    if (p.ln_partials) rs.ln = combine_row_stats(p.ln_partials + (size_t)row * kPartialStride);
+    rs.run_mean = 0.f; rs.run_m2 = 0.f;
   }
   const int n0 = n_blk * kBlockN + slice * 32;
   if (n0 >= p.N) return;  // warp-uniform: columns beyond the layer's width (output head)
@@ -156,14 +219,16 @@ __device__ __forceinline__ void epilogue_slice(const LinearParams& p, const Chai
   if (lane == 0) tma_store_wait_read();
   __syncwarp();
   CMDI_T(9);   // staging free
-  uint4 rv[8];
-  if (res_src) {
-    // fp32 residual block, 32 rows x 128 B, fetched coalesced (4 complete row segments per instruction)
-    const long long ld = p.residual ? p.ld_res : p.ld_ln;
+  const long long res_ld = p.residual ? p.ld_res : p.ld_ln;
+  if (res_src && !rv_ready) {
+    // fp32 residual block, 32 rows x 128 B, fetched coalesced (4 complete row segments per instruction).  Under this
+    // kernel's load an L2 round trip costs ~2 us, so the block of the warp's NEXT slice of the same tile is requested
+    // while this one is processed (below); only a tile's first slice pays the latency here.
 #pragma unroll
     for (int it = 0; it < 8; ++it)
-      rv[it] = ld_global_cg_v4(res_src + (long long)(warp_row0 + it * 4 + (lane >> 3)) * ld + n0 + (lane & 7) * 4);
+      rv[it] = ld_global_cg_v4(res_src + (long long)(warp_row0 + it * 4 + (lane >> 3)) * res_ld + n0 + (lane & 7) * 4);
   }
+  rv_ready = false;
   uint32_t v[32];
   tmem_ld32(tmem_acc + slice * 32, v);
   tmem_ld_wait();
@@ -173,22 +238,14 @@ __device__ __forceinline__ void epilogue_slice(const LinearParams& p, const Chai
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
   if (p.fold_stats) {
     // acc = v (W.gamma)^T  ->  rstd * (acc - mean * c[n]);  the bias added next carries W beta + b
-    const float nm = -rs.fold.x;
+    const float nm = -rs.fold.x, ck = pick(rs.c, k_in_tile);
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.fold_c + n0) + g);
-      f[g * 4 + 0] = __fmaf_rn(nm, c4.x, f[g * 4 + 0]) * rs.fold.y;
-      f[g * 4 + 1] = __fmaf_rn(nm, c4.y, f[g * 4 + 1]) * rs.fold.y;
-      f[g * 4 + 2] = __fmaf_rn(nm, c4.z, f[g * 4 + 2]) * rs.fold.y;
-      f[g * 4 + 3] = __fmaf_rn(nm, c4.w, f[g * 4 + 3]) * rs.fold.y;
-    }
+    for (int j = 0; j < 32; ++j) f[j] = __fmaf_rn(nm, __shfl_sync(0xffffffffu, ck, j), f[j]) * rs.fold.y;
   }
   if (p.bias) {
+    const float bk = pick(rs.bias, k_in_tile);
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + g);
-      f[g * 4 + 0] += b4.x; f[g * 4 + 1] += b4.y; f[g * 4 + 2] += b4.z; f[g * 4 + 3] += b4.w;
-    }
+    for (int j = 0; j < 32; ++j) f[j] += __shfl_sync(0xffffffffu, bk, j);
   }
   if (res_src) {
     // transpose through the staging tile: every thread gets its own row
@@ -198,18 +255,25 @@ __device__ __forceinline__ void epilogue_slice(const LinearParams& p, const Chai
       const int rr = it * 4 + (lane >> 3);
       st_shared_v4(stage + rr * 128 + ((c ^ (rr & 7)) << 4), rv[it].x, rv[it].y, rv[it].z, rv[it].w);
     }
+    if (next_slice >= 0 && n_blk * kBlockN + next_slice * 32 < p.N) {
+      // the registers are free again: request the residual block of this warp's next slice (same tile, same rows)
+      const int n1 = n_blk * kBlockN + next_slice * 32;
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        rv[it] = ld_global_cg_v4(res_src + (long long)(warp_row0 + it * 4 + (lane >> 3)) * res_ld + n1 + (lane & 7) * 4);
+      rv_ready = true;
+    }
     __syncwarp();
+    const float gk = pick(rs.g, k_in_tile), btk = pick(rs.b, k_in_tile);
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const uint4 u = ld_shared_v4(stage + lane * 128 + ((g ^ (lane & 7)) << 4));
       if (p.ln_src) {
         // residual = LayerNorm(ln_src) re-derived from its fp32 input, the row statistics and gamma / beta
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + n0) + g);
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + n0) + g);
-        f[g * 4 + 0] += ln_apply(__uint_as_float(u.x), rs.ln.x, rs.ln.y, g4.x, b4.x);
-        f[g * 4 + 1] += ln_apply(__uint_as_float(u.y), rs.ln.x, rs.ln.y, g4.y, b4.y);
-        f[g * 4 + 2] += ln_apply(__uint_as_float(u.z), rs.ln.x, rs.ln.y, g4.z, b4.z);
-        f[g * 4 + 3] += ln_apply(__uint_as_float(u.w), rs.ln.x, rs.ln.y, g4.w, b4.w);
+        f[g * 4 + 0] += ln_apply(__uint_as_float(u.x), rs.ln.x, rs.ln.y, __shfl_sync(0xffffffffu, gk, g * 4 + 0), __shfl_sync(0xffffffffu, btk, g * 4 + 0));
+        f[g * 4 + 1] += ln_apply(__uint_as_float(u.y), rs.ln.x, rs.ln.y, __shfl_sync(0xffffffffu, gk, g * 4 + 1), __shfl_sync(0xffffffffu, btk, g * 4 + 1));
+        f[g * 4 + 2] += ln_apply(__uint_as_float(u.z), rs.ln.x, rs.ln.y, __shfl_sync(0xffffffffu, gk, g * 4 + 2), __shfl_sync(0xffffffffu, btk, g * 4 + 2));
+        f[g * 4 + 3] += ln_apply(__uint_as_float(u.w), rs.ln.x, rs.ln.y, __shfl_sync(0xffffffffu, gk, g * 4 + 3), __shfl_sync(0xffffffffu, btk, g * 4 + 3));
       } else {
         f[g * 4 + 0] += __uint_as_float(u.x); f[g * 4 + 1] += __uint_as_float(u.y);
         f[g * 4 + 2] += __uint_as_float(u.z); f[g * 4 + 3] += __uint_as_float(u.w);
@@ -218,7 +282,8 @@ __device__ __forceinline__ void epilogue_slice(const LinearParams& p, const Chai
   }
   CMDI_T(11);  // fold + bias + residual
   if (p.stats_out) {
-    // partial LayerNorm statistics of this thread's 32 output values (two-pass in registers)
+    // LayerNorm statistics of this thread's 32 output values (two-pass in registers), merged into the running pair of
+    // the warp's earlier slices of this tile; the warp's last slice of the tile publishes the partial
     float sm = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) sm += (f[j] + f[j + 1]) + (f[j + 2] + f[j + 3]);
@@ -229,11 +294,16 @@ __device__ __forceinline__ void epilogue_slice(const LinearParams& p, const Chai
       const float a = f[j] - mean32;
       q = fmaf(a, a, q);
     }
-    p.stats_out[(size_t)row * 16 + (n0 >> 5)] = make_float2(mean32, q);
+    const float na = 32.0f * (float)k_in_tile, nb = 32.0f, nab = na + nb;
+    const float delta = mean32 - rs.run_mean;
+    rs.run_mean += delta * (nb / nab);
+    rs.run_m2 += q + delta * delta * (na * nb / nab);
+    if (k_in_tile == kSlicesPerWarp - 1)
+      p.stats_out[(size_t)row * kPartialStride + n_blk * kWarpsPerLaneGroup + warp_in_group] = make_float2(rs.run_mean, rs.run_m2);
   }
   if (p.act == 1) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+    for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
   }
   CMDI_T(12);  // statistics + activation
   if (p.out_f32) {
@@ -440,15 +510,18 @@ linear_chain_kernel(const ChainPhaseDesc* __restrict__ phases, const int num_pha
     }
     __syncwarp();
   } else {
-    // ============ epilogue: 12 warps, three per TMEM lane group, 32-column slices handed round-robin ============
+    // ============ epilogue warps: kWarpsPerLaneGroup per TMEM lane group, 32-column slices handed round-robin ============
     const int ew = warp_idx - kFirstEpiWarp;
     const int lane_group = warp_idx & 3;  // the TMEM lanes a warp may touch: 32 * (warp index % 4)
-    const int j3 = ew >> 2;               // 0..2 within the lane group
+    const int j3 = ew >> 2;               // index within the lane group
     const uint32_t epi_stage_addr = smem_u32(epi_stage + ew * kEpiStageBytes);
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(lane_group * 32) << 16);
     int ph = 0, cur_seq = -1, stored_seq = -1;
     int m_blk = 0, n_blk = 0, acc = 0;
-    RowStats rs{make_float2(0.f, 1.f), make_float2(0.f, 1.f)};
+    RowStats rs{};
+    int tile_first_slice = 0;
+    uint4 rv[8];            // residual block in flight for this warp's next slice (see epilogue_slice)
+    bool rv_ready = false;
     // everything this warp stored for tile `seq` is in memory: tell the publisher
     auto publish = [&](int seq) {
       __syncwarp();  // the other lanes' plain stores (row-mapped outputs, partial statistics) before lane 0's release
@@ -458,7 +531,7 @@ linear_chain_kernel(const ChainPhaseDesc* __restrict__ phases, const int num_pha
       }
     };
     const int total_slices = my_tiles * kSlices;
-    for (int g = j3; g < total_slices; g += 3) {
+    for (int g = j3; g < total_slices; g += kWarpsPerLaneGroup) {
       const int seq = g >> 3, slice = g & (kSlices - 1);
       const bool new_tile = seq != cur_seq;
       long long c0 = clock64(), c1 = c0, c2 = c0;
@@ -480,14 +553,19 @@ linear_chain_kernel(const ChainPhaseDesc* __restrict__ phases, const int num_pha
         cur_seq = seq;
       }
       const ChainPhaseInfo& pi = info[ph];
-      epilogue_slice(pi.p, phases[ph], tmem_lane + acc * kAccStride, m_blk, n_blk, slice, lane_group, lane, epi_stage_addr, rs, new_tile,
+      const int g_next = g + kWarpsPerLaneGroup;
+      const int next_slice = (g_next >> 3) == seq ? (g_next & (kSlices - 1)) : -1;
+      if (new_tile) { rv_ready = false; tile_first_slice = slice; }
+      epilogue_slice(pi.p, phases[ph], tmem_lane + acc * kAccStride, m_blk, n_blk, slice, (slice - tile_first_slice) / kWarpsPerLaneGroup, lane_group, lane,
+                     epi_stage_addr, rs, new_tile, rv,
+                     rv_ready, next_slice, j3,
                      (dbg_me && ew == 0 && lane == 0) ? dbg_me + ph * 16 : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_on_leader(&bars->tmem_empty[acc]);
       stored_seq = seq;
       long long c3 = clock64();
-      if (((g + 3) >> 3) != seq) {
+      if (((g + kWarpsPerLaneGroup) >> 3) != seq) {
         // last slice of this tile for this warp.  If this cluster's next tile belongs to a later phase (or does not
         // exist) it may depend on this one: publish now; otherwise at the start of the next tile.
         const int next_tile = cluster_id + (seq + 1) * num_clusters;
