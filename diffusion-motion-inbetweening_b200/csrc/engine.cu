@@ -117,7 +117,8 @@ struct cmdi_engine {
   float *et_w = nullptr, *et_b = nullptr;
   bool weights_loaded = false, temb_valid = false;
   float* temb_table = nullptr;  // [5000, 512] time_embed(pe[t]) for every ORIGINAL timestep t
-  float* temb_hidden = nullptr;
+  Planes pe_p, te_w0_p, te_w2_p, temb_h_p;  // operands of the timestep-embedding table GEMMs
+  CUtensorMap temb_st{};
   // schedule
   int T = 0;
   std::vector<double> h_sqrt_acp, h_sqrt_1m_acp;
@@ -222,19 +223,32 @@ int upload_planes(cmdi_engine* e, Planes& pl, const cmdi_tensor_desc& t, int row
   return 0;
 }
 
+int run_linear(cmdi_engine* e, const Planes& a, const Planes& w, const LinearParams& p_in, int block_n, cudaStream_t s,
+               const Planes* out_planes = nullptr, const CUtensorMap* out_f32 = nullptr);
+
 int ensure_temb(cmdi_engine* e, cudaStream_t s) {
   if (e->temb_valid) return 0;
-  // TimestepEmbedder (mdm.py:345-353) for every original timestep: time_embed(pe[t]); fp32 CUDA cores, once.
+  // TimestepEmbedder (mdm.py:345-353) for every original timestep: time_embed(pe[t]), once per weight load, as two
+  // launches of the pair GEMM (round 1 ran this table on fp32 CUDA cores: 2 x 0.65 ms on every weight load)
   const int n = 5000;
-  CK(launch_small_linear(e->pe, e->te_w0, e->te_b0, e->temb_hidden, n, kDModel, kDModel, /*SiLU*/ 2, s));
-  CK(launch_small_linear(e->temb_hidden, e->te_w2, e->te_b2, e->temb_table, n, kDModel, kDModel, 0, s));
-  e->launches += 2;
+  CK(launch_split_planes(e->pe, n, kDModel, kDModel, e->pe_p.hi, e->pe_p.lo, kDModel, s));
+  CK(launch_split_planes(e->te_w0, kDModel, kDModel, kDModel, e->te_w0_p.hi, e->te_w0_p.lo, kDModel, s));
+  CK(launch_split_planes(e->te_w2, kDModel, kDModel, kDModel, e->te_w2_p.hi, e->te_w2_p.lo, kDModel, s));
+  LinearParams t0{};
+  t0.M = n; t0.N = kDModel; t0.K = kDModel; t0.nsplit = 3; t0.nsplit_out = 3; t0.bias = e->te_b0; t0.act = 2;
+  t0.out_hi = e->temb_h_p.hi; t0.out_lo = e->temb_h_p.lo; t0.ld_bf = kDModel;
+  CKI(run_linear(e, e->pe_p, e->te_w0_p, t0, kBnNarrow, s, &e->temb_h_p));
+  LinearParams t2{};
+  t2.M = n; t2.N = kDModel; t2.K = kDModel; t2.nsplit = 3; t2.nsplit_out = 3; t2.bias = e->te_b2;
+  t2.out_f32 = e->temb_table; t2.ld_f32 = kDModel;
+  CKI(run_linear(e, e->temb_h_p, e->te_w2_p, t2, kBnNarrow, s, nullptr, &e->temb_st));
+  e->launches += 5;
   e->temb_valid = true;
   return 0;
 }
 
 int run_linear(cmdi_engine* e, const Planes& a, const Planes& w, const LinearParams& p_in, int block_n, cudaStream_t s,
-               const Planes* out_planes = nullptr, const CUtensorMap* out_f32 = nullptr) {
+               const Planes* out_planes, const CUtensorMap* out_f32) {
   LinearParams p = p_in;
   p.debug = e->debug;
   LinearStoreMaps st;
@@ -712,7 +726,11 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   A(dev_alloc(e, &e->te_w2, (size_t)kDModel * kDModel)); A(dev_alloc(e, &e->te_b2, kDModel));
   A(dev_alloc(e, &e->et_w, (size_t)kDModel * 512)); A(dev_alloc(e, &e->et_b, kDModel));
   A(dev_alloc(e, &e->temb_table, (size_t)5000 * kDModel));
-  A(dev_alloc(e, &e->temb_hidden, (size_t)5000 * kDModel));
+  A(alloc_planes(e, &e->pe_p, 5120, kDModel, kDModel, 128));
+  A(alloc_planes(e, &e->temb_h_p, 5120, kDModel, kDModel, 128));
+  A(alloc_planes(e, &e->te_w0_p, kDModel, kDModel, kDModel, kBnNarrow));
+  A(alloc_planes(e, &e->te_w2_p, kDModel, kDModel, kDModel, kBnNarrow));
+  A(make_tmap_2d(&e->temb_st, e->temb_table, 4, 5000, kDModel, kDModel, 32, 32));
   // activations
   A(dev_alloc(e, &e->x_state, (size_t)e->frame_rows_pad * e->D_pad));
   A(alloc_planes(e, &e->x_state_p, e->frame_rows_pad, e->D_pad, e->D_pad, 128));

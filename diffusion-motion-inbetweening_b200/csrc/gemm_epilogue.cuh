@@ -311,6 +311,9 @@ __device__ __forceinline__ void epilogue_tile(const LinearParams& p, const EpiSt
     if (p.act == 1) {
 #pragma unroll
       for (int j = 0; j < 64; ++j) f[j] = gelu_erf(f[j]);
+    } else if (p.act == 2) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) f[j] = f[j] / (1.0f + expf(-f[j]));  // SiLU (TimestepEmbedder, mdm.py:347)
     } else if (p.act == 3) {
 #pragma unroll
       for (int j = 0; j < 64; ++j) f[j] = mish_f(f[j]);

@@ -56,7 +56,7 @@ struct LinearParams {
   // deviations) over the 32 output columns starting at col (N must be 512); consumed by ln_partials / fold_stats
   float2* stats_out;
   const float* pos_enc;  // fp32 [L+1, N] table added per output sequence position (ROWMAP_FRAMES_TO_SEQ); or null
-  int act;               // 0 none, 1 exact erf GELU, 3 Mish (x tanh(softplus(x)), nn.Mish)
+  int act;               // 0 none, 1 exact erf GELU, 2 SiLU, 3 Mish (x tanh(softplus(x)), nn.Mish)
   int f32_pre;           // 1: out_f32 receives the value BEFORE the activation (stash for the GELU backward)
   const float* grad_aux; // fp32 [rows, ld_aux] or null: multiply by gelu'(grad_aux[row, col])  (GELU backward)
   int ld_aux;
