@@ -45,3 +45,13 @@ diff.use_graph = False
 out = diff.p_sample_loop(cfg, (B, D, 1, L), model_kwargs={"y": y}, skip_timesteps=997)
 torch.cuda.synchronize()
 print("ok", float(out.abs().mean()), float(j.abs().mean()), float(j2.abs().mean()), float(z.std()))
+# round 2: the chained transformer path (LayerNorm folded, dependency counters) and a small MDM_UNET, plain launches
+plain = C.MDM(num_layers=2).cuda()
+d2 = C.create_gaussian_diffusion(timestep_respacing="ddim50")
+d2.use_graph = False
+d2.rng = "engine"
+o1 = d2.ddim_sample_loop(plain, (3, D, 1, L), model_kwargs={"y": {}}, skip_timesteps=47)
+unet = C.MDM_UNET(dim_mults=(1, 1), keyframe_conditioned=True, zero=False).cuda()
+o2 = d2.ddim_sample_loop(unet, (B, D, 1, L), model_kwargs={"y": {}, "obs_x0": x_obs, "obs_mask": kf}, skip_timesteps=48)
+torch.cuda.synchronize()
+print("ok round 2", float(o1.abs().mean()), float(o2.abs().mean()))
