@@ -154,6 +154,7 @@ struct cmdi_engine {
   // persistent launch (gemm_chain.cu).  CMDI_CHAIN=0 selects the round-1 path (one launch per layer + LayerNorm kernels),
   // which guided steps (they stash LayerNorm inputs for the backward pass) always use.
   bool use_chain = true;
+  int chain_wide = 1;         // CMDI_CHAIN_WIDE=0: 32-column slices in the planes-only phases too (A/B)
   int chain_publish_now = 1;  // CMDI_CHAIN_PUBLISH=deferred: counter bumps deferred to the warp's next tile
   std::vector<FoldedW> f_qkv, f_w1;
   FoldedW f_out;
@@ -414,7 +415,8 @@ int get_chain_tables(cmdi_engine* e, int nseq, const ChainTables** out) {
       LinearParams& p = ph[1].info.p;
       p.bias = e->f_w1[l].d; p.fold_c = e->f_w1[l].c; p.fold_stats = e->stats1; p.act = 1;
       p.out_hi = e->ffh_p.hi; p.out_lo = e->ffh_p.lo; p.ld_bf = e->ff;
-      ph[1].o_hi = e->ffh_p.st32_hi; ph[1].o_lo = e->ffh_p.st32_lo;
+      if (e->chain_wide) { ph[1].info.wide = 1; ph[1].o_hi = e->ffh_p.st_hi; ph[1].o_lo = e->ffh_p.st_lo; }
+      else { ph[1].o_hi = e->ffh_p.st32_hi; ph[1].o_lo = e->ffh_p.st32_lo; }
       ph[1].info.wait_ctr = ctr; ph[1].info.wait_target = ph[0].info.num_n_blocks * 2;
       ph[1].info.done_ctr = ctr + e->max_m_pairs;
     }
@@ -435,7 +437,8 @@ int get_chain_tables(cmdi_engine* e, int nseq, const ChainTables** out) {
       LinearParams& p = ph[3].info.p;
       p.bias = fq.d; p.fold_c = fq.c; p.fold_stats = e->stats2;
       p.out_hi = e->qkv_p.hi; p.out_lo = e->qkv_p.lo; p.ld_bf = 3 * kDModel;
-      ph[3].o_hi = e->qkv_p.st32_hi; ph[3].o_lo = e->qkv_p.st32_lo;
+      if (e->chain_wide) { ph[3].info.wide = 1; ph[3].o_hi = e->qkv_p.st_hi; ph[3].o_lo = e->qkv_p.st_lo; }
+      else { ph[3].o_hi = e->qkv_p.st32_hi; ph[3].o_lo = e->qkv_p.st32_lo; }
     } else {
       // output head on tokens 1.. (norm2 of the last layer folded), frame-major fp32 rows
       base(ph[3], e->xseq_p, e->f_out.w.pair_hi, e->f_out.w.pair_lo, e->D_pad, kDModel, kBnWide);
@@ -682,6 +685,7 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   if (const char* g = getenv("CMDI_ATTN_PREFETCH")) e->attn_prefetch_q = atoi(g) != 0;
   if (const char* g = getenv("CMDI_ATTN_SPLIT")) e->attn_trunc_split = strcmp(g, "trunc") == 0;
   if (const char* g = getenv("CMDI_CHAIN")) e->use_chain = atoi(g) != 0;
+  if (const char* g = getenv("CMDI_CHAIN_WIDE")) e->chain_wide = atoi(g) != 0;
   if (const char* g = getenv("CMDI_CHAIN_PUBLISH")) e->chain_publish_now = strcmp(g, "deferred") != 0;
   e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount; e->nsplit = cfg->precision;
   // the chained launches spin on counters other CTA pairs bump: every pair must be resident at once

@@ -188,29 +188,92 @@ __device__ __forceinline__ float pick(const float (&a)[kSlicesPerWarp], int k) {
   return v;
 }
 
+// Start of a tile for one epilogue warp: per-column constants of its (up to) four 32-column slices and the statistics of
+// its row.  `wide`: the warp owns two 64-column pairs (slices 2q, 2q+1 for q = warp_in_group, warp_in_group + 2) instead
+// of the alternating slices warp_in_group + 2k.
+__device__ __forceinline__ int warp_slice(int k, int warp_in_group, bool wide) {
+  return wide ? 2 * (warp_in_group + kWarpsPerLaneGroup * (k >> 1)) + (k & 1) : warp_in_group + k * kWarpsPerLaneGroup;
+}
+__device__ __forceinline__ void load_tile_constants(const LinearParams& p, RowStats& rs, int row, int n_blk, int warp_in_group, bool wide, int lane) {
+#pragma unroll
+  for (int k = 0; k < kSlicesPerWarp; ++k) {
+    const int sl = warp_slice(k, warp_in_group, wide);
+    const int n = n_blk * kBlockN + sl * 32 + lane;
+    const bool ok = sl < kSlices && n < p.N;
+    rs.bias[k] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
+    rs.c[k] = (ok && p.fold_stats) ? __ldg(p.fold_c + n) : 0.f;
+    rs.g[k] = (ok && p.ln_src) ? __ldg(p.ln_gamma + n) : 0.f;
+    rs.b[k] = (ok && p.ln_src) ? __ldg(p.ln_beta + n) : 0.f;
+  }
+  if (p.fold_stats) rs.fold = combine_row_stats(p.fold_stats + (size_t)row * kPartialStride);
+  if (p.ln_partials) rs.ln = combine_row_stats(p.ln_partials + (size_t)row * kPartialStride);
+  rs.run_mean = 0.f; rs.run_m2 = 0.f;
+}
+
+// A 64-column pair of slices of a phase that writes planes only (FFN1, QKV): one accumulator read, one pass of math over
+// 64 values and two {128 B x 32 rows} plane stores -- half the per-slice synchronisation (TMEM load wait, staging-tile
+// turn-around, proxy fence) per column of the 32-column path, which needs its registers for the residual instead.
+__device__ __forceinline__ void epilogue_pair(const LinearParams& p, const ChainPhaseDesc& pd, uint32_t tmem_acc, int m_blk, int n_blk,
+                                              int pair, int k2, int lane_group, int lane, uint32_t stage, const RowStats& rs) {
+  const int n0 = n_blk * kBlockN + pair * 64;
+  if (n0 >= p.N) return;  // warp-uniform
+  const int warp_row0 = m_blk * kBlockM + lane_group * 32;
+  uint32_t v[64];
+  tmem_ld32(tmem_acc + pair * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+  tmem_ld32(tmem_acc + pair * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+  tmem_ld_wait();
+  float f[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) f[j] = __uint_as_float(v[j]);
+  if (p.fold_stats) {
+    const float nm = -rs.fold.x, c0 = pick(rs.c, 2 * k2), c1 = pick(rs.c, 2 * k2 + 1);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      f[j] = __fmaf_rn(nm, __shfl_sync(0xffffffffu, c0, j), f[j]) * rs.fold.y;
+      f[32 + j] = __fmaf_rn(nm, __shfl_sync(0xffffffffu, c1, j), f[32 + j]) * rs.fold.y;
+    }
+  }
+  if (p.bias) {
+    const float b0 = pick(rs.bias, 2 * k2), b1 = pick(rs.bias, 2 * k2 + 1);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      f[j] += __shfl_sync(0xffffffffu, b0, j);
+      f[32 + j] += __shfl_sync(0xffffffffu, b1, j);
+    }
+  }
+  if (p.act == 1) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) f[j] = gelu_fast(f[j]);
+  }
+  // hi plane first, the remainders stay in f (same arithmetic as split_bf16x2, 96 instead of 128 live registers)
+  uint32_t w[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    w[j] = *reinterpret_cast<const uint32_t*>(&h);
+    f[2 * j] -= __uint_as_float(w[j] << 16);
+    f[2 * j + 1] -= __uint_as_float(w[j] & 0xffff0000u);
+  }
+  store_block_tma(stage, lane, w, &pd.o_hi, n0, warp_row0);
+  if (p.nsplit_out == 3) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const __nv_bfloat162 l = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+      w[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    store_block_tma(stage, lane, w, &pd.o_lo, n0, warp_row0);
+  }
+}
+
 // One 32-column slice of a 128-row accumulator: TMEM -> registers -> [folded LayerNorm] -> bias -> [residual] ->
 // [partial statistics] -> [GELU] -> fp32 rows and/or bf16 hi/lo planes.
 __device__ __forceinline__ void epilogue_slice(const LinearParams& p, const ChainPhaseDesc& pd, uint32_t tmem_acc, int m_blk, int n_blk,
-                                               int slice, int k_in_tile, int lane_group, int lane, uint32_t stage, RowStats& rs, bool new_tile, uint4 (&rv)[8],
+                                               int slice, int k_in_tile, int lane_group, int lane, uint32_t stage, RowStats& rs, uint4 (&rv)[8],
                                                bool& rv_ready, int next_slice, int warp_in_group, long long* dbg) {
   long long t0 = clock64(), t1;
 #define CMDI_T(i) do { if (dbg) { t1 = clock64(); dbg[i] += t1 - t0; t0 = t1; } } while (0)
   const int warp_row0 = m_blk * kBlockM + lane_group * 32;
   const int row = warp_row0 + lane;
-  if (new_tile) {
-#pragma unroll
-    for (int k = 0; k < kSlicesPerWarp; ++k) {
-      const int n = n_blk * kBlockN + (slice + k * kWarpsPerLaneGroup) * 32 + lane;
-      const bool ok = slice + k * kWarpsPerLaneGroup < kSlices && n < p.N;
-      rs.bias[k] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
-      rs.c[k] = (ok && p.fold_stats) ? __ldg(p.fold_c + n) : 0.f;
-      rs.g[k] = (ok && p.ln_src) ? __ldg(p.ln_gamma + n) : 0.f;
-      rs.b[k] = (ok && p.ln_src) ? __ldg(p.ln_beta + n) : 0.f;
-    }
-    if (p.fold_stats) rs.fold = combine_row_stats(p.fold_stats + (size_t)row * kPartialStride);
-    if (p.ln_partials) rs.ln = combine_row_stats(p.ln_partials + (size_t)row * kPartialStride);
-    rs.run_mean = 0.f; rs.run_m2 = 0.f;
-  }
   const int n0 = n_blk * kBlockN + slice * 32;
   if (n0 >= p.N) return;  // warp-uniform: columns beyond the layer's width (output head)
   const float* res_src = p.residual ? p.residual : p.ln_src;
@@ -516,12 +579,8 @@ linear_chain_kernel(const ChainPhaseDesc* __restrict__ phases, const int num_pha
     const int j3 = ew >> 2;               // index within the lane group
     const uint32_t epi_stage_addr = smem_u32(epi_stage + ew * kEpiStageBytes);
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(lane_group * 32) << 16);
-    int ph = 0, cur_seq = -1, stored_seq = -1;
-    int m_blk = 0, n_blk = 0, acc = 0;
+    int ph = 0, stored_seq = -1;
     RowStats rs{};
-    int tile_first_slice = 0;
-    uint4 rv[8];            // residual block in flight for this warp's next slice (see epilogue_slice)
-    bool rv_ready = false;
     // everything this warp stored for tile `seq` is in memory: tell the publisher
     auto publish = [&](int seq) {
       __syncwarp();  // the other lanes' plain stores (row-mapped outputs, partial statistics) before lane 0's release
@@ -530,44 +589,57 @@ linear_chain_kernel(const ChainPhaseDesc* __restrict__ phases, const int num_pha
         mbar_arrive(&bars->publish[seq & (kPublishBars - 1)]);
       }
     };
-    const int total_slices = my_tiles * kSlices;
-    for (int g = j3; g < total_slices; g += kWarpsPerLaneGroup) {
-      const int seq = g >> 3, slice = g & (kSlices - 1);
-      const bool new_tile = seq != cur_seq;
-      long long c0 = clock64(), c1 = c0, c2 = c0;
-      if (new_tile) {
-        const int tile = cluster_id + seq * num_clusters;
-        while (tile >= info[ph].tile_end) ++ph;
-        const int local = tile - info[ph].tile_begin;
-        m_blk = 2 * (local / info[ph].num_n_blocks) + (int)cta_rank;
-        n_blk = local % info[ph].num_n_blocks;
-        acc = seq & 1;
-        mbar_wait(&bars->tmem_full[acc], (seq >> 1) & 1);
-        c1 = clock64();
-        tc_fence_after();
-        if (stored_seq >= 0) {
-          publish(stored_seq);  // deferred from the previous tile: its stores have landed while the mainloop ran
-          stored_seq = -1;
-        }
-        c2 = clock64();
-        cur_seq = seq;
-      }
+    for (int seq = 0; seq < my_tiles; ++seq) {
+      long long c0 = clock64();
+      const int tile = cluster_id + seq * num_clusters;
+      while (tile >= info[ph].tile_end) ++ph;
       const ChainPhaseInfo& pi = info[ph];
-      const int g_next = g + kWarpsPerLaneGroup;
-      const int next_slice = (g_next >> 3) == seq ? (g_next & (kSlices - 1)) : -1;
-      if (new_tile) { rv_ready = false; tile_first_slice = slice; }
-      epilogue_slice(pi.p, phases[ph], tmem_lane + acc * kAccStride, m_blk, n_blk, slice, (slice - tile_first_slice) / kWarpsPerLaneGroup, lane_group, lane,
-                     epi_stage_addr, rs, new_tile, rv,
-                     rv_ready, next_slice, j3,
-                     (dbg_me && ew == 0 && lane == 0) ? dbg_me + ph * 16 : nullptr);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_on_leader(&bars->tmem_empty[acc]);
+      const int local = tile - pi.tile_begin;
+      const int m_blk = 2 * (local / pi.num_n_blocks) + (int)cta_rank;
+      const int n_blk = local % pi.num_n_blocks;
+      const int acc = seq & 1;
+      const bool wide = pi.wide != 0;
+      mbar_wait(&bars->tmem_full[acc], (seq >> 1) & 1);
+      long long c1 = clock64();
+      tc_fence_after();
+      if (stored_seq >= 0) {
+        publish(stored_seq);  // deferred from the previous tile: its stores have landed while the mainloop ran
+        stored_seq = -1;
+      }
+      long long c2 = clock64();
+      load_tile_constants(pi.p, rs, m_blk * kBlockM + lane_group * 32 + lane, n_blk, j3, wide, lane);
+      const uint32_t tmem_acc = tmem_lane + acc * kAccStride;
+      long long* dbg_w = (dbg_me && ew == 0 && lane == 0) ? dbg_me + ph * 16 : nullptr;
+      if (wide) {
+#pragma unroll 1
+        for (int k2 = 0; k2 < kSlicesPerWarp / 2; ++k2) {
+          epilogue_pair(pi.p, phases[ph], tmem_acc, m_blk, n_blk, j3 + kWarpsPerLaneGroup * k2, k2, lane_group, lane, epi_stage_addr, rs);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {  // one arrival per 32-column slice keeps the barrier's count independent of the phase
+            mbar_arrive_on_leader(&bars->tmem_empty[acc]);
+            mbar_arrive_on_leader(&bars->tmem_empty[acc]);
+          }
+        }
+      } else {
+        uint4 rv[8];  // residual block in flight for this warp's next slice (see epilogue_slice)
+        bool rv_ready = false;
+#pragma unroll 1
+        for (int k = 0; k < kSlicesPerWarp; ++k) {
+          const int slice = j3 + k * kWarpsPerLaneGroup;
+          const int next_slice = k + 1 < kSlicesPerWarp ? slice + kWarpsPerLaneGroup : -1;
+          epilogue_slice(pi.p, phases[ph], tmem_acc, m_blk, n_blk, slice, k, lane_group, lane, epi_stage_addr, rs, rv, rv_ready,
+                         next_slice, j3, dbg_w);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_on_leader(&bars->tmem_empty[acc]);
+        }
+      }
       stored_seq = seq;
       long long c3 = clock64();
-      if (((g + kWarpsPerLaneGroup) >> 3) != seq) {
-        // last slice of this tile for this warp.  If this cluster's next tile belongs to a later phase (or does not
-        // exist) it may depend on this one: publish now; otherwise at the start of the next tile.
+      {
+        // If this cluster's next tile belongs to a later phase (or does not exist) it may depend on this one: publish
+        // now; otherwise at the start of the next tile.
         const int next_tile = cluster_id + (seq + 1) * num_clusters;
         if (next_tile >= pi.tile_end || pi.publish_now) {
           publish(seq);

@@ -103,6 +103,7 @@ struct ChainPhaseInfo {
   int wait_target;
   int* done_ctr;               // [num_m_pairs] or null: each CTA adds 1 once its half of a tile is in memory
   int publish_now;             // 1: bump done_ctr as soon as a tile's stores have landed (the warp waits for them); 0: at its next tile
+  int wide;                    // 1: planes-only phase whose epilogue works on 64-column pairs (o_hi / o_lo are {64, 32} boxes, 128 B swizzle)
 };
 struct alignas(128) ChainPhaseDesc {
   CUtensorMap a_hi, a_lo, w_hi, w_lo, o_hi, o_lo, o_f32;
