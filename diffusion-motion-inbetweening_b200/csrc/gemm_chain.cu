@@ -40,10 +40,18 @@ constexpr int kBlockM = 128;  // per CTA; 256 per pair
 constexpr int kBlockN = 256;
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
-// Epilogue warps and W-ring depth are tied through shared memory: 8 warps x 4 KB staging leave room for 3 + 3 operand
-// stages, 12 warps only for 3 + 2.  Measured at B = 64 (same box, A/B/A/B): 12 warps / 3 + 2 stages 482 steps/s,
-// 12 warps with 2 KB tiles / 3 + 3 stages 504, 8 warps / 3 + 3 stages 520 -- the FFN1 (GELU) epilogue is issue-bound, not
-// latency-bound, so more warps at 128 registers lose to fewer at 168, and the deeper W ring is worth 6 %.
+// Epilogue warps, ring depths and the L1 left beside the shared memory, measured at B = 64 (same box, A/B/A/B):
+//   12 epilogue warps (128 registers), A 3 + W 2 stages        482 steps/s
+//   12 warps with 2 KB staging tiles,  A 3 + W 3               504
+//    8 warps (168 registers),          A 3 + W 3  (224 KB)     520   <- round-2 mid-point
+//    8 warps, 64-column pairs in the planes-only phases, A 3 + W 3 (224 KB)   514-523 (another box)
+//    same, A 2 + W 3 (192 KB) or A 2 + W 2 (160 KB)            528-535
+//    same, A 2 + W 3 + a second staging tile per warp (224 KB) 514
+// The epilogue is issue- and latency-bound, not occupancy-bound (fewer warps with more registers win), and what the
+// third A stage buys the producer is less than what its 32 KB cost the epilogue as L1: the per-tile constants, the row
+// statistics and the few spilled registers around the barrier waits live there, and at 224 KB of shared memory only
+// ~25 KB of L1 remain.  A second staging tile per warp (stores never waiting for the previous store's read) bought
+// nothing at equal shared memory.
 #ifndef CMDI_CHAIN_EPI_WARPS
 #define CMDI_CHAIN_EPI_WARPS 8
 #endif
@@ -54,7 +62,10 @@ constexpr int kNumEpiWarps = CMDI_CHAIN_EPI_WARPS;
 constexpr int kWarpsPerLaneGroup = kNumEpiWarps / 4;
 constexpr int kFirstEpiWarp = 3;
 constexpr int kNumThreads = (kFirstEpiWarp + kNumEpiWarps) * 32;
-constexpr int kStagesA = 3, kStagesW = CMDI_CHAIN_STAGES_W;
+#ifndef CMDI_CHAIN_STAGES_A
+#define CMDI_CHAIN_STAGES_A 2
+#endif
+constexpr int kStagesA = CMDI_CHAIN_STAGES_A, kStagesW = CMDI_CHAIN_STAGES_W;
 constexpr int kPlaneBytes = kBlockM * kBlockK * 2;   // one bf16 plane of a 128-row x 64-column operand block = 16 KB
 constexpr int kOperandBytes = 2 * kPlaneBytes;       // hi + lo
 constexpr int kSlices = kBlockN / 32;                // 32-column slices per tile
