@@ -3,19 +3,19 @@
 //
 //   O[s, :] = softmax_j( Q[s,:] . K[j,:] / sqrt(128) ) V[j, :]
 //
-// One CTA per (sequence, head, 128-query tile).  Both contractions run on tcgen05 tensor cores:
-//   S = Q K^T   : A = Q tile (smem, K-major), B = K tile (smem, K-major), D = 128 x 208 fp32 in TMEM
-//   O = P V     : A = P (bf16, written into TMEM by the softmax warps, aliasing S), B = V (smem, MN-major),
-//                 D = 128 x 128 fp32 in TMEM
+// One CTA PAIR (cluster of 2) per (sequence, head): CTA r owns query rows [128 r, 128 r + 128).  Both contractions run
+// on tcgen05 tensor cores as cta_group::2 MMAs (M = 256):
+//   S = Q K^T   : A = Q tiles (smem, K-major), B = K (smem, K-major, keys split between the CTAs), D = 256 x 208 fp32
+//   O = P V     : A = P (bf16, written into TMEM by the softmax warps over S), B = V (smem, MN-major, head-dim columns
+//                 split between the CTAs), D = 256 x 128 fp32, double-buffered in TMEM
 // Q, K and V are read straight out of the QKV projection's [tokens, 3*H*128] bf16 planes with TMA
 // (no head-split or transpose kernels).  With nsplit = 3 every product uses the hi/lo bf16 split
 // (X_lo*Y_hi + X_hi*Y_lo + X_hi*Y_hi), P included, so the result is fp32-accurate.
 //
-// warp 0: TMA producer   warp 1: MMA issuer (+TMEM alloc)
+// warp 0: TMA producer   warp 1: MMA issuer (leader CTA; + TMEM alloc)
 // warps 2..9: softmax + output.  Two threads per query row (TMEM lane group = warp % 4, key half = (warp-2)/4):
 //   each keeps its ~104 logits in registers (one TMEM read), the halves exchange row max / row sum through
-//   shared memory, P is written back to TMEM, and O leaves through coalesced 16-byte stores staged in the
-//   (by then free) Q tile region.
+//   shared memory, P is written back to TMEM, and O leaves as bf16 hi / lo planes through TMA stores.
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include "kernels.h"
@@ -30,16 +30,10 @@ constexpr int kKeyPad = kAttnKeyPad;            // 208 = 13 * 16
 constexpr int kQBlockBytes = kQTile * 128;      // 64 dh-columns of 128 queries
 constexpr int kKVBlockBytes = kKeyPad * 128;    // 64 dh-columns of 208 keys  (26 swizzle atoms)
 constexpr int kQPlane = 2 * kQBlockBytes;       // 32768
-constexpr int kKVPlane = 2 * kKVBlockBytes;     // 53248
-constexpr int kOffQHi = 0, kOffQLo = kQPlane;
-constexpr int kOffKHi = 2 * kQPlane, kOffKLo = kOffKHi + kKVPlane;
-constexpr int kOffVHi = kOffKLo + kKVPlane;
-constexpr int kOffVLo = kOffKHi;                // V_lo reuses the K region once S is complete
-constexpr int kSmemTiles = kOffVHi + kKVPlane;  // 225280
 constexpr int kNumSoftmaxWarps = 8;
 constexpr int kThreads = 64 + kNumSoftmaxWarps * 32;
 // TMEM columns
-constexpr uint32_t kColS = 0, kColPHi = 0, kColPLo = 208, kColO = 320, kTmemCols = 512;
+constexpr uint32_t kColS = 0, kColPHi = 0, kTmemCols = 512;
 // key chunks (16 keys each) per half: half 0 -> chunks [0,7), half 1 -> chunks [7,13)
 constexpr int kChunks0 = 7, kChunks1 = 6;
 
@@ -50,7 +44,7 @@ __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
 // logits of this thread's key range -> registers, row max, exchange, probabilities -> TMEM, row sum
 template <int CHUNK0, int NCHUNKS>
 __device__ __forceinline__ float softmax_half(uint32_t trow, int S, bool split, float c_scale, float (*red_max)[128], int half,
-                                              int row, bool trunc) {
+                                              int row, bool trunc, uint32_t col_plo) {
   float s[NCHUNKS * 16];
   {
     // all TMEM reads in flight at once, one wait
@@ -86,261 +80,255 @@ __device__ __forceinline__ float softmax_half(uint32_t trow, int S, bool split, 
       if (trunc) split_bf16x2_trunc(p0, p1, ph[j], pl[j]); else split_bf16x2(p0, p1, ph[j], pl[j]);
     }
     tmem_st8(trow + kColPHi + (CHUNK0 + c) * 8, ph);
-    if (split) tmem_st8(trow + kColPLo + (CHUNK0 + c) * 8, pl);
+    if (split) tmem_st8(trow + col_plo + (CHUNK0 + c) * 8, pl);
   }
   return sum;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Persistent version: one CTA per SM walks over (sequence, head, query-tile) items w = blockIdx.x, +gridDim.x, ...
-// With 225 KB of operand tiles only one CTA fits an SM, so the one-shot kernel above serialises load -> S ->
-// softmax -> PV -> store per CTA and every wave starts with all 148 CTAs pulling 33 MB through L2 at once.
-// Here the loads of item i+1 are issued as soon as the buffers of item i drain:
-//   K region   : K_i            -> free at s_done_i  -> K_{i+1}
-//   Q region   : Q_i, V_lo_i    -> free at o_done_i  -> Q_{i+1}        (V_lo_i enters at s_done_i)
-//   V_hi region: V_hi_i, then the store staging of item i -> free at stage_free_i -> V_hi_{i+1}
-// and S_{i+1} = Q K^T is issued while the softmax warps still write out O_i.  Every barrier completes exactly once
-// per item, so the wait parity of item number i is i & 1.
+// Shared memory.  K is split by keys and V by head-dim columns between the two CTAs, so a CTA holds Q (64 KB) + half of
+// K (52 KB) + half of V (52 KB) + its store staging (32 KB) with NO region shared between operands: Q_{i+1} and K_{i+1}
+// are requested as soon as S_i is complete and V_{i+1} as soon as O_i is, all of it behind the softmax / PV / output
+// work of item i.  (Round 1's one-CTA-per-query-tile kernel needed 272 KB for the same residency: V_lo overlaid Q, so
+// Q_{i+1} could only be requested at o_done_i and its ~2 us L2 round trip sat on every item's critical path; measured
+// at 64 x 197 x 4: 44.2 -> 40.2 us per launch on the same box.)
+// Per item the tensor pipe needs ~2500 cycles for S and ~2500 for P V (3 bf16 terms each) and the softmax warps ~6000;
+// S_{i+1} cannot start before P_i V_i has retired (P overwrites S in place: two S buffers + O exceed the 512 TMEM
+// columns), so the loop softmax -> P V -> S -> softmax bounds an item at ~12 000 cycles; the output of item i-1 is
+// written under P_i V_i / S_{i+1} from the other O buffer.
 // ------------------------------------------------------------------------------------------------
-struct __align__(8) AttnBarriers2 {
-  uint64_t q_full, k_full, vhi_full, vlo_full, s_done, p_full, o_done, stage_free;
+constexpr int kKHalf = kKeyPad / 2;                     // 104 keys per CTA
+constexpr int kKHalfBlockBytes = kKHalf * 128;          // 64 dh-columns of 104 keys (13 swizzle atoms)
+constexpr int kKHalfPlane = 2 * kKHalfBlockBytes;       // 26624
+constexpr int kVHalfPlane = kKVBlockBytes;              // 64 dh-columns of 208 keys: 26624
+constexpr int kPOffQHi = 0, kPOffQLo = kQPlane;
+constexpr int kPOffKHi = 2 * kQPlane, kPOffKLo = kPOffKHi + kKHalfPlane;
+constexpr int kPOffVHi = kPOffKLo + kKHalfPlane, kPOffVLo = kPOffVHi + kVHalfPlane;
+constexpr int kPOffStage = kPOffVLo + kVHalfPlane;
+constexpr int kPairSmemTiles = kPOffStage + kNumSoftmaxWarps * kEpiStageBytes;  // 204800
+// TMEM columns of the pair kernel: P (hi | lo) overwrites S in place, O is double-buffered (the output stores of item i
+// run under the PV product of item i+1)
+constexpr uint32_t kPColPLo = 104, kPColO = 208, kPColOStride = 128;
+static_assert(kPColO + 2 * kPColOStride <= kTmemCols, "tensor memory budget");
+static_assert(kKHalfBlockBytes % 1024 == 0 && kVHalfPlane % 1024 == 0, "swizzle-atom alignment of the operand tiles");
+
+struct __align__(8) AttnPairBarriers {
+  uint64_t q_full, k_full, v_full;  // on the leader CTA: both CTAs' loads complete there
+  uint64_t s_done, o_done;          // in both CTAs (multicast commit)
+  uint64_t p_full;                  // on the leader: one arrival per softmax warp of the pair
   uint32_t tmem_base;
   uint32_t pad;
   float red_max[2][128];
   float red_sum[2][128];
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
-attention_persistent_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
-                            const __grid_constant__ CUtensorMap map_kv_hi, const __grid_constant__ CUtensorMap map_kv_lo,
-                            const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
-                            const AttnParams p, const int num_items, const int q_tiles) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+attention_pair_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
+                      const __grid_constant__ CUtensorMap map_kh_hi, const __grid_constant__ CUtensorMap map_kh_lo,
+                      const __grid_constant__ CUtensorMap map_kv_hi, const __grid_constant__ CUtensorMap map_kv_lo,
+                      const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
+                      const AttnParams p, const int num_items) {
   const long long t_entry = clock64();
-  unsigned long long ns_entry;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_entry));
-  griddep_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  AttnBarriers2* bars = reinterpret_cast<AttnBarriers2*>(smem + kSmemTiles);
+  AttnPairBarriers* bars = reinterpret_cast<AttnPairBarriers*>(smem + kPairSmemTiles);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int S = p.seq_len;
   const bool split = (p.nsplit == 3);
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&map_q_hi);
+    tma_prefetch_desc(&map_kh_hi);
     tma_prefetch_desc(&map_kv_hi);
     mbar_init(&bars->q_full, 1);
     mbar_init(&bars->k_full, 1);
-    mbar_init(&bars->vhi_full, 1);
-    mbar_init(&bars->vlo_full, 1);
+    mbar_init(&bars->v_full, 1);
     mbar_init(&bars->s_done, 1);
-    mbar_init(&bars->p_full, kNumSoftmaxWarps * 32);
     mbar_init(&bars->o_done, 1);
-    mbar_init(&bars->stage_free, kNumSoftmaxWarps);
+    mbar_init(&bars->p_full, 2 * kNumSoftmaxWarps);
     fence_barrier_init();
   }
   if (warp_idx == 1) {
-    tmem_alloc(&bars->tmem_base, kTmemCols);
-    tmem_relinquish();
+    tmem_alloc_2sm(&bars->tmem_base, kTmemCols);
+    tmem_relinquish_2sm();
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // barrier inits + TMEM allocation visible to both CTAs
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-  griddep_wait();
 
-  // item -> (sequence, head, query tile)
-  auto decode = [&](int w, int& seq, int& head, int& qtile) {
-    qtile = w % q_tiles;
-    const int sh = w / q_tiles;
-    head = sh % p.num_heads;
-    seq = sh / p.num_heads;
+  // item -> (sequence, head)
+  auto decode = [&](int w, int& seq, int& head) {
+    head = w % p.num_heads;
+    seq = w / p.num_heads;
   };
 
   if (warp_idx == 0) {
+    // ===================================== TMA producer (both CTAs) =====================================
     if (lane == 0) {
       const uint32_t planes = split ? 2 : 1;
-      auto load_q = [&](int w) {
-        int seq, head, qtile;
-        decode(w, seq, head, qtile);
-        const int row = seq * S + qtile * kQTile, col = head * kHeadDim;
-        mbar_arrive_expect_tx(&bars->q_full, planes * kQPlane);
+      auto load_q = [&](int w) {   // this CTA's 128 query rows
+        int seq, head;
+        decode(w, seq, head);
+        const int row = seq * S + (int)cta_rank * kQTile, col = head * kHeadDim;
+        if (leader) mbar_arrive_expect_tx(&bars->q_full, 2 * planes * kQPlane);
         for (int j = 0; j < 2; ++j) {
-          tma_load_2d(smem + kOffQHi + j * kQBlockBytes, &map_q_hi, &bars->q_full, col + j * 64, row);
-          if (split) tma_load_2d(smem + kOffQLo + j * kQBlockBytes, &map_q_lo, &bars->q_full, col + j * 64, row);
+          tma_load_2d_2sm(smem + kPOffQHi + j * kQBlockBytes, &map_q_hi, &bars->q_full, col + j * 64, row);
+          if (split) tma_load_2d_2sm(smem + kPOffQLo + j * kQBlockBytes, &map_q_lo, &bars->q_full, col + j * 64, row);
         }
       };
-      auto load_k = [&](int w) {
-        int seq, head, qtile;
-        decode(w, seq, head, qtile);
-        const int col = p.num_heads * kHeadDim + head * kHeadDim;
-        mbar_arrive_expect_tx(&bars->k_full, planes * kKVPlane);
+      auto load_k = [&](int w) {   // this CTA's 104 keys of K
+        int seq, head;
+        decode(w, seq, head);
+        const int row = seq * S + (int)cta_rank * kKHalf, col = p.num_heads * kHeadDim + head * kHeadDim;
+        if (leader) mbar_arrive_expect_tx(&bars->k_full, 2 * planes * kKHalfPlane);
         for (int j = 0; j < 2; ++j) {
-          tma_load_2d(smem + kOffKHi + j * kKVBlockBytes, &map_kv_hi, &bars->k_full, col + j * 64, seq * S);
-          if (split) tma_load_2d(smem + kOffKLo + j * kKVBlockBytes, &map_kv_lo, &bars->k_full, col + j * 64, seq * S);
+          tma_load_2d_2sm(smem + kPOffKHi + j * kKHalfBlockBytes, &map_kh_hi, &bars->k_full, col + j * 64, row);
+          if (split) tma_load_2d_2sm(smem + kPOffKLo + j * kKHalfBlockBytes, &map_kh_lo, &bars->k_full, col + j * 64, row);
         }
       };
-      auto load_v = [&](int w, bool lo) {
-        int seq, head, qtile;
-        decode(w, seq, head, qtile);
-        const int col = 2 * p.num_heads * kHeadDim + head * kHeadDim;
-        uint64_t* bar = lo ? &bars->vlo_full : &bars->vhi_full;
-        mbar_arrive_expect_tx(bar, kKVPlane);
-        // V_lo lives in the Q region (free once S is complete; 53 KB of its 64 KB)
-        uint8_t* dst = smem + (lo ? kOffQHi : kOffVHi);
-        for (int j = 0; j < 2; ++j) tma_load_2d(dst + j * kKVBlockBytes, lo ? &map_kv_lo : &map_kv_hi, bar, col + j * 64, seq * S);
+      auto load_v = [&](int w) {   // this CTA's 64 head-dim columns of V, all keys
+        int seq, head;
+        decode(w, seq, head);
+        const int col = 2 * p.num_heads * kHeadDim + head * kHeadDim + (int)cta_rank * 64;
+        if (leader) mbar_arrive_expect_tx(&bars->v_full, 2 * planes * kVHalfPlane);
+        tma_load_2d_2sm(smem + kPOffVHi, &map_kv_hi, &bars->v_full, col, seq * S);
+        if (split) tma_load_2d_2sm(smem + kPOffVLo, &map_kv_lo, &bars->v_full, col, seq * S);
       };
-      int w = blockIdx.x;
+      int w = cluster_id;
       if (w < num_items) {
         load_q(w);
         load_k(w);
-        load_v(w, false);
+        load_v(w);
       }
-      for (uint32_t it = 0; w < num_items; w += gridDim.x, ++it) {
+      for (uint32_t it = 0; w < num_items; w += num_clusters, ++it) {
         const uint32_t ph = it & 1;
-        const int wn = w + gridDim.x;
-        mbar_wait(&bars->s_done, ph);      // Q_i and K_i consumed
-        if (split) load_v(w, true);
-        if (wn < num_items) load_k(wn);
-        if (wn < num_items && p.prefetch_q) {
-          // Q_{i+1} can only land once V_lo_i has left the Q region; pull it into L2 meanwhile
-          int seq, head, qtile;
-          decode(wn, seq, head, qtile);
-          for (int j = 0; j < 2; ++j) {
-            tma_prefetch_2d(&map_q_hi, head * kHeadDim + j * 64, seq * S + qtile * kQTile);
-            if (split) tma_prefetch_2d(&map_q_lo, head * kHeadDim + j * 64, seq * S + qtile * kQTile);
-          }
+        const int wn = w + num_clusters;
+        mbar_wait(&bars->s_done, ph);  // Q_i and K_i consumed (in both CTAs)
+        if (wn < num_items) {
+          load_q(wn);
+          load_k(wn);
         }
-        mbar_wait(&bars->o_done, ph);      // V_lo_i and V_hi_i consumed
-        if (wn < num_items) load_q(wn);
-        mbar_wait(&bars->stage_free, ph);  // the epilogue of item i no longer reads its staging tiles (V_hi region)
-        if (wn < num_items) load_v(wn, false);
+        mbar_wait(&bars->o_done, ph);  // V_i consumed
+        if (wn < num_items) load_v(wn);
       }
     }
     __syncwarp();
   } else if (warp_idx == 1) {
-    if (lane == 0) {
+    // ====================================== MMA issuer (leader CTA only) ======================================
+    if (leader && lane == 0) {
       const uint32_t sbase = smem_u32(smem);
-      constexpr uint32_t idesc_s = make_idesc_bf16(kQTile, kKeyPad, 0);
-      constexpr uint32_t idesc_o = make_idesc_bf16(kQTile, kHeadDim, 1);
+      constexpr uint32_t idesc_s = make_idesc_bf16(2 * kQTile, kKeyPad, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(2 * kQTile, kHeadDim, 1);
       const int nterms = split ? 3 : 1;
-      uint32_t it = 0;
       long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      const long long t_loop = clock64();
-      for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
-        const uint32_t ph = it & 1;
+      auto issue_s = [&](uint32_t ph) {
         long long t0 = clock64(), t1;
-        // ---------------- S = Q K^T ----------------
         mbar_wait(&bars->q_full, ph);
         t1 = clock64(); acc[0] += t1 - t0; t0 = t1;
         mbar_wait(&bars->k_full, ph);
         t1 = clock64(); acc[1] += t1 - t0; t0 = t1;
         tc_fence_after();
         uint32_t accum = 0;
+#pragma unroll
         for (int j = 0; j < 2; ++j) {
-          for (int term = 0; term < nterms; ++term) {
-            const uint32_t qo = (split && term == 0) ? kOffQLo : kOffQHi;
-            const uint32_t ko = (split && term == 1) ? kOffKLo : kOffKHi;
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {
+            if (term >= nterms) break;
+            const uint32_t qo = (split && term == 0) ? kPOffQLo : kPOffQHi;
+            const uint32_t ko = (split && term == 1) ? kPOffKLo : kPOffKHi;
             const uint64_t da = make_desc_kmajor_sw128(sbase + qo + j * kQBlockBytes);
-            const uint64_t db = make_desc_kmajor_sw128(sbase + ko + j * kKVBlockBytes);
+            const uint64_t db = make_desc_kmajor_sw128(sbase + ko + j * kKHalfBlockBytes);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              umma_ss(tmem_base + kColS, desc_advance(da, kk * 32), desc_advance(db, kk * 32), idesc_s, accum);
+              umma_ss_2sm(tmem_base + kColS, desc_advance(da, kk * 32), desc_advance(db, kk * 32), idesc_s, accum);
               accum = 1;
             }
           }
         }
-        umma_commit(&bars->s_done);
-        t1 = clock64(); acc[2] += t1 - t0; t0 = t1;
+        umma_commit_2sm(&bars->s_done, 0x3);
+        t1 = clock64(); acc[2] += t1 - t0;
+      };
+      const long long t_loop = clock64();
+      uint32_t it = 0;
+      if (cluster_id < num_items) issue_s(0);
+      for (int w = cluster_id; w < num_items; w += num_clusters, ++it) {
+        const uint32_t ph = it & 1;
+        long long t0 = clock64(), t1;
         // ---------------- O = P V ----------------
-        // (p_full of this item also implies the softmax warps have finished reading O of the previous item)
+        // (p_full of this item also implies the softmax warps have finished reading O of item i-2, the previous user of
+        // this O buffer: they store item i-1's output after arriving here and item i-2's before)
         mbar_wait(&bars->p_full, ph);
         t1 = clock64(); acc[3] += t1 - t0; t0 = t1;
-        mbar_wait(&bars->vhi_full, ph);
+        mbar_wait(&bars->v_full, ph);
         t1 = clock64(); acc[4] += t1 - t0; t0 = t1;
         tc_fence_after();
-        const uint64_t dv_hi = make_desc_mnmajor_sw128(sbase + kOffVHi, kKVBlockBytes);
-        accum = 0;
+        const uint64_t dv_hi = make_desc_mnmajor_sw128(sbase + kPOffVHi, kKVBlockBytes);
+        const uint64_t dv_lo = make_desc_mnmajor_sw128(sbase + kPOffVLo, kKVBlockBytes);
+        const uint32_t col_o = tmem_base + kPColO + ph * kPColOStride;
+        uint32_t accum = 0;
         if (split) {
-#pragma unroll 1
+#pragma unroll
           for (int ks = 0; ks < kKeyPad / 16; ++ks) {
-            umma_ts(tmem_base + kColO, tmem_base + kColPLo + ks * 8, desc_advance(dv_hi, ks * 2048), idesc_o, accum);
+            umma_ts_2sm(col_o, tmem_base + kPColPLo + ks * 8, desc_advance(dv_hi, ks * 2048), idesc_o, accum);
             accum = 1;
           }
         }
-#pragma unroll 1
+#pragma unroll
         for (int ks = 0; ks < kKeyPad / 16; ++ks) {
-          umma_ts(tmem_base + kColO, tmem_base + kColPHi + ks * 8, desc_advance(dv_hi, ks * 2048), idesc_o, accum);
+          umma_ts_2sm(col_o, tmem_base + kColPHi + ks * 8, desc_advance(dv_hi, ks * 2048), idesc_o, accum);
           accum = 1;
         }
-        t1 = clock64(); acc[5] += t1 - t0; t0 = t1;
         if (split) {
-          mbar_wait(&bars->vlo_full, ph);
-          t1 = clock64(); acc[6] += t1 - t0; t0 = t1;
-          tc_fence_after();
-          const uint64_t dv_lo = make_desc_mnmajor_sw128(sbase + kOffQHi, kKVBlockBytes);
-#pragma unroll 1
+#pragma unroll
           for (int ks = 0; ks < kKeyPad / 16; ++ks)
-            umma_ts(tmem_base + kColO, tmem_base + kColPHi + ks * 8, desc_advance(dv_lo, ks * 2048), idesc_o, 1u);
+            umma_ts_2sm(col_o, tmem_base + kColPHi + ks * 8, desc_advance(dv_lo, ks * 2048), idesc_o, 1u);
         }
-        umma_commit(&bars->o_done);
+        umma_commit_2sm(&bars->o_done, 0x3);
+        t1 = clock64(); acc[5] += t1 - t0; t0 = t1;
+        if (w + num_clusters < num_items) {
+          // S_{i+1} overwrites the columns P_i is read from: wait until the PV MMAs have retired (the output stores of
+          // item i, ~3000 cycles, cover it)
+          mbar_wait(&bars->o_done, ph);
+          t1 = clock64(); acc[6] += t1 - t0;
+          issue_s(ph ^ 1);
+        }
         acc[7] += 1;
       }
       if (p.dbg_cycles) {
-        for (int i = 0; i < 8; ++i) p.dbg_cycles[(size_t)blockIdx.x * 16 + i] = acc[i];
-        unsigned long long ns_now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_now));
-        p.dbg_cycles[(size_t)blockIdx.x * 16 + 12] = t_loop - t_entry;
-        p.dbg_cycles[(size_t)blockIdx.x * 16 + 13] = clock64() - t_entry;
-        p.dbg_cycles[(size_t)blockIdx.x * 16 + 14] = (long long)(ns_now - ns_entry);
-        p.dbg_cycles[(size_t)blockIdx.x * 16 + 15] = (long long)ns_entry;
+        for (int i = 0; i < 8; ++i) p.dbg_cycles[(size_t)cluster_id * 16 + i] = acc[i];
+        p.dbg_cycles[(size_t)cluster_id * 16 + 12] = t_loop - t_entry;
+        p.dbg_cycles[(size_t)cluster_id * 16 + 13] = clock64() - t_entry;
       }
     }
     __syncwarp();
   } else {
-    // ---------------- softmax + output: two threads per query row ----------------
+    // ---------------- softmax + output: two threads per query row (both CTAs, each its own 128 rows) ----------------
     const int sw = warp_idx - 2;
     const int lane_group = warp_idx & 3;
     const int half = sw >> 2;
     const int row = lane_group * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(lane_group * 32) << 16);
     const float c_scale = 0.08838834764831845f * 1.4426950408889634f;  // 1/sqrt(128) * log2(e)
-    const uint32_t stage = smem_u32(smem + kOffVHi + sw * kEpiStageBytes);
+    const uint32_t stage = smem_u32(smem + kPOffStage + sw * kEpiStageBytes);
     const long long pitch = (long long)p.ld_out * 2;
-    uint32_t it = 0;
+    const int group_row0 = (int)cta_rank * kQTile + lane_group * 32;  // first query of this warp's 32 rows
     long long sacc[4] = {0, 0, 0, 0};
-    for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
-      const uint32_t ph = it & 1;
-      int seq, head, qtile;
-      decode(w, seq, head, qtile);
+    // output of one item: O (TMEM buffer `buf`) * 1 / row sum -> bf16 hi / lo planes
+    auto write_output = [&](int w, uint32_t buf, float inv) {
+      int seq, head;
+      decode(w, seq, head);
       const int row0 = seq * S;
-      long long u0 = clock64(), u1;
-      mbar_wait(&bars->s_done, ph);
-      u1 = clock64(); sacc[0] += u1 - u0; u0 = u1;
-      tc_fence_after();
-      float sum;
-      if (half == 0) {
-        sum = softmax_half<0, kChunks0>(trow, S, split, c_scale, bars->red_max, 0, row, p.trunc_split != 0);
-      } else {
-        sum = softmax_half<kChunks0, kChunks1>(trow, S, split, c_scale, bars->red_max, 1, row, p.trunc_split != 0);
-      }
-      bars->red_sum[half][row] = sum;
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&bars->p_full);
-      named_barrier_sync(1, kNumSoftmaxWarps * 32);  // red_sum of both halves visible
-      const float inv = 1.0f / (bars->red_sum[0][row] + bars->red_sum[1][row]);
-
-      u1 = clock64(); sacc[1] += u1 - u0; u0 = u1;
-      mbar_wait(&bars->o_done, ph);
-      u1 = clock64(); sacc[2] += u1 - u0; u0 = u1;
-      tc_fence_after();
-      // all MMAs of this item are complete: the V_hi region is free and becomes the store-staging area (8 x 4 KB)
       uint32_t v0[32], v1[32];
-      tmem_ld32(trow + kColO + half * 64, v0);
-      tmem_ld32(trow + kColO + half * 64 + 32, v1);
+      tmem_ld32(trow + kPColO + buf * kPColOStride + half * 64, v0);
+      tmem_ld32(trow + kPColO + buf * kPColOStride + half * 64 + 32, v1);
       tmem_ld_wait();
       uint32_t hw[32], lw[32];
 #pragma unroll
@@ -353,11 +341,9 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap map_q_hi, const 
           split_bf16x2(__uint_as_float(v1[2 * j]) * inv, __uint_as_float(v1[2 * j + 1]) * inv, hw[16 + j], lw[16 + j]);
         }
       }
-      const int group_row0 = qtile * kQTile + lane_group * 32;  // first query of this warp's 32 rows
       if (group_row0 + 32 <= S) {
         store_block_tma(stage, lane, hw, &map_o_hi, head * kHeadDim + half * 64, row0 + group_row0);
         if (p.nsplit_out == 3) store_block_tma(stage, lane, lw, &map_o_lo, head * kHeadDim + half * 64, row0 + group_row0);
-        if (lane == 0) tma_store_wait_read();
       } else if (group_row0 < S) {
         RowSlots rows;
         rows.ok = 0;
@@ -374,33 +360,68 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap map_q_hi, const 
           store_block_coalesced(stage, lane, lw, dst_lo, rows, pitch, 8, 1, 0);
         }
       }
+    };
+    // Software pipeline: softmax of item i, then -- while the pair's tensor cores run P_i V_i and S_{i+1} -- the output
+    // of item i-1 from the other O buffer.  No barrier wait is needed for that output: s_done_i, waited for above, was
+    // issued after the MMA thread saw o_done_{i-1}.
+    uint32_t it = 0;
+    int w_prev = -1;
+    float inv_prev = 0.f;
+    for (int w = cluster_id; w < num_items; w += num_clusters, ++it) {
+      const uint32_t ph = it & 1;
+      long long u0 = clock64(), u1;
+      mbar_wait(&bars->s_done, ph);
+      u1 = clock64(); sacc[0] += u1 - u0; u0 = u1;
+      tc_fence_after();
+      float sum;
+      if (half == 0) {
+        sum = softmax_half<0, kChunks0>(trow, S, split, c_scale, bars->red_max, 0, row, p.trunc_split != 0, kPColPLo);
+      } else {
+        sum = softmax_half<kChunks0, kChunks1>(trow, S, split, c_scale, bars->red_max, 1, row, p.trunc_split != 0, kPColPLo);
+      }
+      bars->red_sum[half][row] = sum;
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->stage_free);
+      if (lane == 0) mbar_arrive_on_leader(&bars->p_full);
+      named_barrier_sync(1, kNumSoftmaxWarps * 32);  // red_sum of both halves visible
+      const float inv = 1.0f / (bars->red_sum[0][row] + bars->red_sum[1][row]);
+      u1 = clock64(); sacc[1] += u1 - u0; u0 = u1;
+      if (w_prev >= 0) write_output(w_prev, ph ^ 1, inv_prev);
       u1 = clock64(); sacc[3] += u1 - u0;
+      w_prev = w;
+      inv_prev = inv;
+    }
+    if (w_prev >= 0) {
+      const uint32_t last = (it - 1) & 1;
+      long long u0 = clock64(), u1;
+      mbar_wait(&bars->o_done, last);
+      u1 = clock64(); sacc[2] += u1 - u0; u0 = u1;
+      tc_fence_after();
+      write_output(w_prev, last, inv_prev);
+      sacc[3] += clock64() - u0;
     }
     if (p.dbg_cycles && sw == 0 && lane == 0)
-      for (int i = 0; i < 4; ++i) p.dbg_cycles[(size_t)blockIdx.x * 16 + 8 + i] = sacc[i];
+      for (int i = 0; i < 4; ++i) p.dbg_cycles[(size_t)cluster_id * 16 + 8 + i] = sacc[i];
     if (lane == 0) tma_store_wait_all();  // bulk stores of the last item complete before the CTA exits
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // nobody touches the pair's TMEM / barriers after this point
   if (warp_idx == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc_2sm(tmem_base, kTmemCols);
   }
 }
 
 }  // namespace
 
 cudaError_t configure_attention_kernel() {
-  return cudaFuncSetAttribute(attention_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)(1024 + kSmemTiles + sizeof(AttnBarriers2)));
+  return cudaFuncSetAttribute(attention_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)(1024 + kPairSmemTiles + sizeof(AttnPairBarriers)));
 }
 
-cudaError_t launch_attention(const CUtensorMap& q_hi, const CUtensorMap& q_lo, const CUtensorMap& kv_hi,
-                             const CUtensorMap& kv_lo, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const AttnParams& p,
-                             cudaStream_t stream) {
+cudaError_t launch_attention(const AttnMaps& m, const AttnParams& p, cudaStream_t stream) {
   if (p.seq_len > kKeyPad || p.seq_len < 1 || (p.nsplit != 1 && p.nsplit != 3)) {
     set_last_error("launch_attention: unsupported seq_len=%d nsplit=%d", p.seq_len, p.nsplit);
     return cudaErrorInvalidValue;
@@ -411,11 +432,11 @@ cudaError_t launch_attention(const CUtensorMap& q_hi, const CUtensorMap& q_lo, c
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int q_tiles = (p.seq_len + kQTile - 1) / kQTile;
-  const int num_items = q_tiles * p.num_heads * p.num_seqs;
-  const size_t smem2 = 1024 + kSmemTiles + sizeof(AttnBarriers2);
-  return launch_kernel(attention_persistent_kernel, dim3(num_items < num_sms ? num_items : num_sms), dim3(kThreads), smem2,
-                       stream, q_hi, q_lo, kv_hi, kv_lo, o_hi, o_lo, p, num_items, q_tiles);
+  const int num_items = p.num_heads * p.num_seqs;
+  const int clusters = num_items < num_sms / 2 ? num_items : num_sms / 2;
+  const size_t smem = 1024 + kPairSmemTiles + sizeof(AttnPairBarriers);
+  return launch_kernel(attention_pair_kernel, dim3(2 * clusters), dim3(kThreads), smem, stream, *m.q_hi, *m.q_lo, *m.kh_hi, *m.kh_lo,
+                       *m.kv_hi, *m.kv_lo, *m.o_hi, *m.o_lo, p, num_items);
 }
 
 }  // namespace cmdi

@@ -163,10 +163,14 @@ extern "C" int cmdi_test_attention(const float* qkv, float* O, int num_seqs, int
   if (make_tmap_bf16_2d(&mq_lo, q_lo.p, rows_p, ld, ld, 64, 128)) return 1;
   if (make_tmap_bf16_2d(&mkv_hi, q_hi.p, rows_p, ld, ld, 64, kAttnKeyPad)) return 1;
   if (make_tmap_bf16_2d(&mkv_lo, q_lo.p, rows_p, ld, ld, 64, kAttnKeyPad)) return 1;
+  CUtensorMap mkh_hi, mkh_lo;
+  if (make_tmap_bf16_2d(&mkh_hi, q_hi.p, rows_p, ld, ld, 64, kAttnKeyPad / 2)) return 1;
+  if (make_tmap_bf16_2d(&mkh_lo, q_lo.p, rows_p, ld, ld, 64, kAttnKeyPad / 2)) return 1;
   CUtensorMap mo_hi, mo_lo;
   if (make_tmap_bf16_2d(&mo_hi, o_hi.p, rows_p, ldo, ldo, 64, 32)) return 1;
   if (make_tmap_bf16_2d(&mo_lo, o_lo.p, rows_p, ldo, ldo, 64, 32)) return 1;
   CK(configure_attention_kernel());
+  const AttnMaps am{&mq_hi, &mq_lo, &mkh_hi, &mkh_lo, &mkv_hi, &mkv_lo, &mo_hi, &mo_lo};
   AttnParams p{};
   p.num_seqs = num_seqs; p.seq_len = S; p.num_heads = H; p.nsplit = precision; p.nsplit_out = 3;
   p.out_hi = o_hi.as<__nv_bfloat16>(); p.out_lo = o_lo.as<__nv_bfloat16>(); p.ld_out = ldo;
@@ -177,36 +181,30 @@ extern "C" int cmdi_test_attention(const float* qkv, float* O, int num_seqs, int
     CK(adbg.alloc((size_t)nctas * 16 * 8));
     CK(cudaMemset(adbg.p, 0, (size_t)nctas * 16 * 8));
     p.dbg_cycles = adbg.as<long long>();
-    CK(launch_attention(mq_hi, mq_lo, mkv_hi, mkv_lo, mo_hi, mo_lo, p, stream));
+    CK(launch_attention(am, p, stream));
   }
-  CK(launch_attention(mq_hi, mq_lo, mkv_hi, mkv_lo, mo_hi, mo_lo, p, stream));
+  CK(launch_attention(am, p, stream));
   if (p.dbg_cycles) {
     std::vector<long long> h((size_t)nctas * 16);
     CK(cudaStreamSynchronize(stream));
     CK(cudaMemcpy(h.data(), adbg.p, h.size() * 8, cudaMemcpyDeviceToHost));
     double a[16] = {0};
     {
-      // persistent kernel: per-CTA sums over its items; slot 7 = item count
+      // per-CTA-pair sums over its items; slot 7 = item count
       double items = 0;
       for (int c = 0; c < nctas; ++c) items += (double)h[(size_t)c * 16 + 7];
       for (int c = 0; c < nctas; ++c) for (int k = 0; k < 12; ++k) a[k] += (double)h[(size_t)c * 16 + k] / items;
-      printf("attn2 dbg cycles (mean per item): MMA thread wait_q=%.0f wait_k=%.0f S-issue=%.0f wait_P=%.0f wait_Vhi=%.0f PV-issue=%.0f wait_Vlo=%.0f | "
-             "softmax warp: wait_S=%.0f softmax=%.0f wait_O=%.0f epilogue=%.0f (items %.0f)\n",
+      printf("attention dbg cycles (mean per item): MMA thread wait_q=%.0f wait_k=%.0f S-issue=%.0f wait_P=%.0f wait_V=%.0f PV-issue=%.0f wait_PV_retired=%.0f | "
+             "softmax warp: wait_S=%.0f softmax=%.0f last_wait_O=%.0f output=%.0f (items %.0f)\n",
              a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[8], a[9], a[10], a[11], items);
-      double pro = 0, tot_max = 0, ns_max = 0, n = 0;
-      long long first = 0, last_end = 0;
+      double pro = 0, tot_max = 0, n = 0;
       for (int c = 0; c < nctas; ++c) {
         if (h[(size_t)c * 16 + 7] == 0) continue;
         n += 1;
         pro += (double)h[(size_t)c * 16 + 12];
         if ((double)h[(size_t)c * 16 + 13] > tot_max) tot_max = (double)h[(size_t)c * 16 + 13];
-        if ((double)h[(size_t)c * 16 + 14] > ns_max) ns_max = (double)h[(size_t)c * 16 + 14];
-        const long long b = h[(size_t)c * 16 + 15], e_ = b + h[(size_t)c * 16 + 14];
-        if (first == 0 || b < first) first = b;
-        if (e_ > last_end) last_end = e_;
       }
-      printf("attn2 dbg: ctas=%.0f prologue=%.0f cycles, longest CTA (MMA thread) %.0f cycles = %.0f ns, first entry -> last MMA-thread exit %.0f ns\n",
-             n, pro / n, tot_max, ns_max, (double)(last_end - first));
+      printf("attention dbg: CTA pairs=%.0f prologue=%.0f cycles, longest pair (MMA thread) %.0f cycles\n", n, pro / n, tot_max);
       fflush(stdout);
       p.dbg_cycles = nullptr;
     }

@@ -68,7 +68,7 @@ struct LayerWT {  // transposed weight planes for dX = dY W
 };
 struct LayerStash {  // forward values the backward pass of one layer needs
   Planes qkv;
-  CUtensorMap q_hi{}, q_lo{}, kv_hi{}, kv_lo{};
+  CUtensorMap q_hi{}, q_lo{}, kv_hi{}, kv_lo{}, kh_hi{}, kh_lo{};
   float *v1 = nullptr, *v2 = nullptr, *pre = nullptr;
 };
 
@@ -101,7 +101,6 @@ struct cmdi_engine {
   int debug = 0, bn_wide = kBnWide, bn_narrow = kBnNarrow;  // CMDI_DEBUG / CMDI_BN_WIDE / CMDI_BN_NARROW (bring-up knobs)
   int steps_per_graph = 1;  // CMDI_GRAPH_STEPS: consecutive steps captured into one graph (10 and 50 measured: no gain over 1)
   bool no_graph = false;    // CMDI_NO_GRAPH=1: plain stream launches even when the caller asks for graph replay
-  int attn_prefetch_q = 1;   // CMDI_ATTN_PREFETCH=0
   int attn_trunc_split = 0;  // CMDI_ATTN_SPLIT=trunc
   float2 *ln_stats1 = nullptr, *ln_stats2 = nullptr;  // (mean, rstd) per token row published by norm1 / norm2
   bool tma_store = true;  // CMDI_EPI=stg selects the coalesced-STG epilogue everywhere
@@ -131,7 +130,7 @@ struct cmdi_engine {
   Planes x_state_p;
   float *xseq = nullptr, *x1 = nullptr, *vsum = nullptr, *model_out = nullptr, *pred_x0 = nullptr, *x_obs = nullptr;
   Planes xseq_p, x1_p, qkv_p, attn_p, ffh_p;
-  CUtensorMap q_map_hi{}, q_map_lo{}, kv_map_hi{}, kv_map_lo{};
+  CUtensorMap q_map_hi{}, q_map_lo{}, kv_map_hi{}, kv_map_lo{}, kh_map_hi{}, kh_map_lo{};  // Q {64,128}, K/V {64,208}, K half {64,104}
   CUtensorMap vsum_st{};  // fp32 TMA-store target for the pre-LayerNorm sums
   CUtensorMap xseq_st{}, x1_st{};  // fp32 TMA-store targets: xseq (backward pass), x1 (v1 of the chained forward path)
   uint8_t* obs_mask = nullptr;
@@ -320,9 +319,10 @@ int run_denoiser(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool has_cond
     // attention core
     AttnParams a{};
     a.num_seqs = nseq; a.seq_len = e->S; a.num_heads = e->H; a.nsplit = e->nsplit; a.nsplit_out = e->nsplit;
-    a.out_hi = e->attn_p.hi; a.out_lo = e->attn_p.lo; a.ld_out = kDModel; a.trunc_split = e->attn_trunc_split; a.prefetch_q = e->attn_prefetch_q;
-    for (int r_ = 0; r_ < reps; ++r_) CK(launch_attention(ls ? ls->q_hi : e->q_map_hi, ls ? ls->q_lo : e->q_map_lo, ls ? ls->kv_hi : e->kv_map_hi,
-                                                         ls ? ls->kv_lo : e->kv_map_lo, e->attn_p.st_hi, e->attn_p.st_lo, a, s));
+    a.out_hi = e->attn_p.hi; a.out_lo = e->attn_p.lo; a.ld_out = kDModel; a.trunc_split = e->attn_trunc_split;
+    const AttnMaps am = ls ? AttnMaps{&ls->q_hi, &ls->q_lo, &ls->kh_hi, &ls->kh_lo, &ls->kv_hi, &ls->kv_lo, &e->attn_p.st_hi, &e->attn_p.st_lo}
+                           : AttnMaps{&e->q_map_hi, &e->q_map_lo, &e->kh_map_hi, &e->kh_map_lo, &e->kv_map_hi, &e->kv_map_lo, &e->attn_p.st_hi, &e->attn_p.st_lo};
+    for (int r_ = 0; r_ < reps; ++r_) CK(launch_attention(am, a, s));
     CKI(mark());
     // out-proj + residual, then LayerNorm1
     {
@@ -510,10 +510,11 @@ int run_denoiser_chain(cmdi_engine* e, int B, bool dup, int n_cond_seqs, bool ha
   CKI(mark());
   AttnParams a{};
   a.num_seqs = nseq; a.seq_len = e->S; a.num_heads = e->H; a.nsplit = e->nsplit; a.nsplit_out = e->nsplit;
-  a.out_hi = e->attn_p.hi; a.out_lo = e->attn_p.lo; a.ld_out = kDModel; a.trunc_split = e->attn_trunc_split; a.prefetch_q = e->attn_prefetch_q;
+  a.out_hi = e->attn_p.hi; a.out_lo = e->attn_p.lo; a.ld_out = kDModel; a.trunc_split = e->attn_trunc_split;
+  const AttnMaps am{&e->q_map_hi, &e->q_map_lo, &e->kh_map_hi, &e->kh_map_lo, &e->kv_map_hi, &e->kv_map_lo, &e->attn_p.st_hi, &e->attn_p.st_lo};
   for (int l = 0; l < e->layers; ++l) {
     for (int r_ = 0; r_ < reps; ++r_)
-      CK(launch_attention(e->q_map_hi, e->q_map_lo, e->kv_map_hi, e->kv_map_lo, e->attn_p.st_hi, e->attn_p.st_lo, a, s));
+      CK(launch_attention(am, a, s));
     CKI(mark());
     for (int r_ = 0; r_ < reps; ++r_) {
       if (reps > 1)  // profiling repeats one launch back to back: its counters start from zero each time
@@ -540,6 +541,8 @@ int ensure_stash(cmdi_engine* e) {
     rc = rc || make_tmap_bf16_2d(&ls.q_lo, ls.qkv.lo, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, 128);
     rc = rc || make_tmap_bf16_2d(&ls.kv_hi, ls.qkv.hi, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, kAttnKeyPad);
     rc = rc || make_tmap_bf16_2d(&ls.kv_lo, ls.qkv.lo, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, kAttnKeyPad);
+    rc = rc || make_tmap_bf16_2d(&ls.kh_hi, ls.qkv.hi, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, kAttnKeyPad / 2);
+    rc = rc || make_tmap_bf16_2d(&ls.kh_lo, ls.qkv.lo, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, kAttnKeyPad / 2);
     rc = rc || dev_alloc(e, &ls.v1, (size_t)e->seq_rows_pad * kDModel);
     rc = rc || dev_alloc(e, &ls.v2, (size_t)e->seq_rows_pad * kDModel);
     rc = rc || dev_alloc(e, &ls.pre, (size_t)e->seq_rows_pad * e->ff);
@@ -682,7 +685,6 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   if (const char* g = getenv("CMDI_BN_QKV")) e->bn_qkv = atoi(g);
   if (const char* g = getenv("CMDI_NO_GRAPH")) e->no_graph = atoi(g) != 0;
   if (const char* g = getenv("CMDI_GRAPH_STEPS")) e->steps_per_graph = atoi(g) > 0 ? atoi(g) : 1;
-  if (const char* g = getenv("CMDI_ATTN_PREFETCH")) e->attn_prefetch_q = atoi(g) != 0;
   if (const char* g = getenv("CMDI_ATTN_SPLIT")) e->attn_trunc_split = strcmp(g, "trunc") == 0;
   if (const char* g = getenv("CMDI_CHAIN")) e->use_chain = atoi(g) != 0;
   if (const char* g = getenv("CMDI_CHAIN_WIDE")) e->chain_wide = atoi(g) != 0;
@@ -750,6 +752,8 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   A(make_tmap_bf16_2d(&e->q_map_lo, e->qkv_p.lo, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, 128));
   A(make_tmap_bf16_2d(&e->kv_map_hi, e->qkv_p.hi, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, kAttnKeyPad));
   A(make_tmap_bf16_2d(&e->kv_map_lo, e->qkv_p.lo, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, kAttnKeyPad));
+  A(make_tmap_bf16_2d(&e->kh_map_hi, e->qkv_p.hi, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, kAttnKeyPad / 2));
+  A(make_tmap_bf16_2d(&e->kh_map_lo, e->qkv_p.lo, e->seq_rows_pad, 3 * kDModel, 3 * kDModel, 64, kAttnKeyPad / 2));
   A(make_tmap_2d(&e->vsum_st, e->vsum, 4, e->seq_rows_pad, kDModel, kDModel, 32, 32));
   A(make_tmap_2d(&e->xseq_st, e->xseq, 4, e->seq_rows_pad, kDModel, kDModel, 32, 32));
   A(make_tmap_2d(&e->x1_st, e->x1, 4, e->seq_rows_pad, kDModel, kDModel, 32, 32));

@@ -368,10 +368,12 @@ __device__ __forceinline__ void epilogue_slice(const LinearParams& p, const Chai
       const float a = f[j] - mean32;
       q = fmaf(a, a, q);
     }
-    const float na = 32.0f * (float)k_in_tile, nb = 32.0f, nab = na + nb;
+    // Chan's update with n_a = 32 k, n_b = 32: n_b / n_ab = 1 / (k + 1), n_a n_b / n_ab = 32 k / (k + 1)
+    const float inv = k_in_tile == 0 ? 1.0f : k_in_tile == 1 ? 0.5f : k_in_tile == 2 ? (1.0f / 3.0f) : 0.25f;
+    static_assert(kSlicesPerWarp <= 4, "reciprocal table");
     const float delta = mean32 - rs.run_mean;
-    rs.run_mean += delta * (nb / nab);
-    rs.run_m2 += q + delta * delta * (na * nb / nab);
+    rs.run_mean += delta * inv;
+    rs.run_m2 += q + delta * delta * (32.0f * (float)k_in_tile * inv);
     if (k_in_tile == kSlicesPerWarp - 1)
       p.stats_out[(size_t)row * kPartialStride + n_blk * kWarpsPerLaneGroup + warp_in_group] = make_float2(rs.run_mean, rs.run_m2);
   }

@@ -127,16 +127,17 @@ struct AttnParams {
   __nv_bfloat16* out_hi;  // [num_seqs*seq_len (+pad), H*128]
   __nv_bfloat16* out_lo;
   int ld_out;
-  long long* dbg_cycles;  // bring-up only: [num_ctas][16] cycle counters or null
-  int prefetch_q;         // persistent kernel: L2-prefetch the next item's Q tile while its smem region is still occupied
+  long long* dbg_cycles;  // bring-up only: [num_clusters][16] cycle counters or null
   int trunc_split;        // 1: hi plane of P and O by truncation (split_bf16x2_trunc): half the conversions, error 2^-16 instead of 2^-17
 };
-// qkv maps: bf16 [rows, 3*H*128] row-major planes (hi, lo); box {64, 128} for Q, {64, 208} for K and V.
+// qkv maps: bf16 [rows, 3*H*128] row-major planes (hi, lo); box {64, 128} for Q, {64, 208} for V (and K in the backward
+// kernel), {64, 104} for K (each CTA of a pair holds half of the keys).
 // o maps: the output planes [rows, H*128] as TMA-store targets, box {64, 32}.
+struct AttnMaps {
+  const CUtensorMap *q_hi, *q_lo, *kh_hi, *kh_lo, *kv_hi, *kv_lo, *o_hi, *o_lo;
+};
 cudaError_t configure_attention_kernel();
-cudaError_t launch_attention(const CUtensorMap& q_hi, const CUtensorMap& q_lo, const CUtensorMap& kv_hi,
-                             const CUtensorMap& kv_lo, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const AttnParams& p,
-                             cudaStream_t stream);
+cudaError_t launch_attention(const AttnMaps& maps, const AttnParams& p, cudaStream_t stream);
 constexpr int kAttnKeyPad = 208;
 
 // ----------------------------------------------------------------------------------------------

@@ -1,6 +1,6 @@
 """Cycle counters of the chained linear kernel (CMDI_CHAIN_DBG=1), B=64."""
 import os, sys
-os.environ["CMDI_CHAIN_DBG"] = "1"
+os.environ.setdefault("CMDI_CHAIN_DBG", "1")
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import condmdi_b200 as C
