@@ -36,15 +36,19 @@ constexpr int kThreads = 64 + kNumSoftmaxWarps * 32;
 constexpr uint32_t kColS = 0, kColPHi = 0, kTmemCols = 512;
 // key chunks (16 keys each) per half: half 0 -> chunks [0,7), half 1 -> chunks [7,13)
 constexpr int kChunks0 = 7, kChunks1 = 6;
+// ... of which the first kEarly0 / kEarly1 are handed to the P V product early (see softmax_half)
+constexpr int kEarly0 = 4, kEarly1 = 3;
 
 __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // logits of this thread's key range -> registers, row max, exchange, probabilities -> TMEM, row sum
-template <int CHUNK0, int NCHUNKS>
+// `part_a`: barrier (on the pair's leader) that collects one arrival per softmax warp once the first EARLY chunks of P
+// are in tensor memory -- the P V product over those keys starts while the remaining probabilities are computed.
+template <int CHUNK0, int NCHUNKS, int EARLY>
 __device__ __forceinline__ float softmax_half(uint32_t trow, int S, bool split, float c_scale, float (*red_max)[128], int half,
-                                              int row, bool trunc, uint32_t col_plo) {
+                                              int row, bool trunc, uint32_t col_plo, uint64_t* part_a, int lane) {
   float s[NCHUNKS * 16];
   {
     // all TMEM reads in flight at once, one wait
@@ -81,6 +85,12 @@ __device__ __forceinline__ float softmax_half(uint32_t trow, int S, bool split, 
     }
     tmem_st8(trow + kColPHi + (CHUNK0 + c) * 8, ph);
     if (split) tmem_st8(trow + col_plo + (CHUNK0 + c) * 8, pl);
+    if (c == EARLY - 1) {
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_on_leader(part_a);
+    }
   }
   return sum;
 }
@@ -115,7 +125,7 @@ static_assert(kKHalfBlockBytes % 1024 == 0 && kVHalfPlane % 1024 == 0, "swizzle-
 struct __align__(8) AttnPairBarriers {
   uint64_t q_full, k_full, v_full;  // on the leader CTA: both CTAs' loads complete there
   uint64_t s_done, o_done;          // in both CTAs (multicast commit)
-  uint64_t p_full;                  // on the leader: one arrival per softmax warp of the pair
+  uint64_t p_part, p_full;          // on the leader: one arrival per softmax warp of the pair (early chunks / all of P)
   uint32_t tmem_base;
   uint32_t pad;
   float red_max[2][128];
@@ -151,6 +161,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid
     mbar_init(&bars->v_full, 1);
     mbar_init(&bars->s_done, 1);
     mbar_init(&bars->o_done, 1);
+    mbar_init(&bars->p_part, 2 * kNumSoftmaxWarps);
     mbar_init(&bars->p_full, 2 * kNumSoftmaxWarps);
     fence_barrier_init();
   }
@@ -265,7 +276,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid
         // ---------------- O = P V ----------------
         // (p_full of this item also implies the softmax warps have finished reading O of item i-2, the previous user of
         // this O buffer: they store item i-1's output after arriving here and item i-2's before)
-        mbar_wait(&bars->p_full, ph);
+        mbar_wait(&bars->p_part, ph);
         t1 = clock64(); acc[3] += t1 - t0; t0 = t1;
         mbar_wait(&bars->v_full, ph);
         t1 = clock64(); acc[4] += t1 - t0; t0 = t1;
@@ -273,24 +284,34 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid
         const uint64_t dv_hi = make_desc_mnmajor_sw128(sbase + kPOffVHi, kKVBlockBytes);
         const uint64_t dv_lo = make_desc_mnmajor_sw128(sbase + kPOffVLo, kKVBlockBytes);
         const uint32_t col_o = tmem_base + kPColO + ph * kPColOStride;
+        // one bf16 term over the key chunks [c0, c1) of half 0 and [d0, d1) of half 1 (term-major order: alternating the
+        // operand planes per chunk measured 70 % slower)
         uint32_t accum = 0;
-        if (split) {
+        auto pv_term = [&](uint32_t p_col, uint64_t dv, int c0, int c1, int d0, int d1) {
 #pragma unroll
-          for (int ks = 0; ks < kKeyPad / 16; ++ks) {
-            umma_ts_2sm(col_o, tmem_base + kPColPLo + ks * 8, desc_advance(dv_hi, ks * 2048), idesc_o, accum);
+          for (int c = 0; c < kChunks0; ++c) {
+            if (c < c0 || c >= c1) continue;
+            umma_ts_2sm(col_o, tmem_base + p_col + c * 8, desc_advance(dv, c * 2048), idesc_o, accum);
             accum = 1;
           }
-        }
 #pragma unroll
-        for (int ks = 0; ks < kKeyPad / 16; ++ks) {
-          umma_ts_2sm(col_o, tmem_base + kColPHi + ks * 8, desc_advance(dv_hi, ks * 2048), idesc_o, accum);
-          accum = 1;
-        }
-        if (split) {
-#pragma unroll
-          for (int ks = 0; ks < kKeyPad / 16; ++ks)
-            umma_ts_2sm(col_o, tmem_base + kColPHi + ks * 8, desc_advance(dv_lo, ks * 2048), idesc_o, 1u);
-        }
+          for (int c = 0; c < kChunks1; ++c) {
+            if (c < d0 || c >= d1) continue;
+            umma_ts_2sm(col_o, tmem_base + p_col + (kChunks0 + c) * 8, desc_advance(dv, (kChunks0 + c) * 2048), idesc_o, accum);
+            accum = 1;
+          }
+        };
+        // keys whose probabilities are already in tensor memory: the first kEarly0 / kEarly1 chunks of the two halves
+        if (split) pv_term(kPColPLo, dv_hi, 0, kEarly0, 0, kEarly1);
+        pv_term(kColPHi, dv_hi, 0, kEarly0, 0, kEarly1);
+        if (split) pv_term(kColPHi, dv_lo, 0, kEarly0, 0, kEarly1);
+        t1 = clock64(); acc[5] += t1 - t0; t0 = t1;
+        mbar_wait(&bars->p_full, ph);
+        t1 = clock64(); acc[3] += t1 - t0; t0 = t1;
+        tc_fence_after();
+        if (split) pv_term(kPColPLo, dv_hi, kEarly0, kChunks0, kEarly1, kChunks1);
+        pv_term(kColPHi, dv_hi, kEarly0, kChunks0, kEarly1, kChunks1);
+        if (split) pv_term(kColPHi, dv_lo, kEarly0, kChunks0, kEarly1, kChunks1);
         umma_commit_2sm(&bars->o_done, 0x3);
         t1 = clock64(); acc[5] += t1 - t0; t0 = t1;
         if (w + num_clusters < num_items) {
@@ -375,9 +396,9 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid
       tc_fence_after();
       float sum;
       if (half == 0) {
-        sum = softmax_half<0, kChunks0>(trow, S, split, c_scale, bars->red_max, 0, row, p.trunc_split != 0, kPColPLo);
+        sum = softmax_half<0, kChunks0, kEarly0>(trow, S, split, c_scale, bars->red_max, 0, row, p.trunc_split != 0, kPColPLo, &bars->p_part, lane);
       } else {
-        sum = softmax_half<kChunks0, kChunks1>(trow, S, split, c_scale, bars->red_max, 1, row, p.trunc_split != 0, kPColPLo);
+        sum = softmax_half<kChunks0, kChunks1, kEarly1>(trow, S, split, c_scale, bars->red_max, 1, row, p.trunc_split != 0, kPColPLo, &bars->p_part, lane);
       }
       bars->red_sum[half][row] = sum;
       tmem_st_wait();
