@@ -9,7 +9,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 120 -c 
   --log-file $OUT/${TAG}_launches.csv python bench.py --steps 6 --warmup 3 --skip-configs > $OUT/${TAG}_ncu_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --cache-control none --import-source on -k regex:linear_chain \
   -s 9 -c 1 -o $OUT/${TAG}_chain -f python tools/gpu_b64_steps.py 3 > $OUT/${TAG}_ncu_chain.log 2>&1
-timeout 900 ncu --set full --clock-control none --cache-control none --import-source on -k regex:attention_persistent \
+timeout 900 ncu --set full --clock-control none --cache-control none --import-source on -k regex:attention_pair \
   -s 9 -c 1 -o $OUT/${TAG}_attention -f python tools/gpu_b64_steps.py 3 > $OUT/${TAG}_ncu_attention.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
   --log-file $OUT/${TAG}_unet_launches.csv python tools/gpu_unet_step.py 2 > $OUT/${TAG}_ncu_unet.log 2>&1
