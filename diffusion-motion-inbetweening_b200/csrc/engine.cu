@@ -153,6 +153,7 @@ struct cmdi_engine {
   // persistent launch (gemm_chain.cu).  CMDI_CHAIN=0 selects the round-1 path (one launch per layer + LayerNorm kernels),
   // which guided steps (they stash LayerNorm inputs for the backward pass) always use.
   bool use_chain = true;
+  int chain_res_planes = 1;   // CMDI_CHAIN_RES=f32: residual sources kept as fp32 copies (A/B)
   int chain_wide = 1;         // CMDI_CHAIN_WIDE=0: 32-column slices in the planes-only phases too (A/B)
   int chain_publish_now = 1;  // CMDI_CHAIN_PUBLISH=deferred: counter bumps deferred to the warp's next tile
   std::vector<FoldedW> f_qkv, f_w1;
@@ -403,9 +404,13 @@ int get_chain_tables(cmdi_engine* e, int nseq, const ChainTables** out) {
       p.bias = w.bo;
       if (l == 0) { p.residual = e->xseq; p.ld_res = kDModel; }
       else {
-        p.ln_src = e->vsum; p.ld_ln = kDModel; p.ln_partials = e->stats2; p.ln_gamma = e->lw[l - 1].g2; p.ln_beta = e->lw[l - 1].be2;
+        p.ld_ln = kDModel; p.ln_partials = e->stats2; p.ln_gamma = e->lw[l - 1].g2; p.ln_beta = e->lw[l - 1].be2;
+        if (e->chain_res_planes) { p.ln_src_hi = e->xseq_p.hi; p.ln_src_lo = e->xseq_p.lo; }
+        else p.ln_src = e->vsum;
       }
-      p.out_f32 = e->x1; p.ld_f32 = kDModel; p.out_hi = e->x1_p.hi; p.out_lo = e->x1_p.lo; p.ld_bf = kDModel; p.stats_out = e->stats1;
+      // the fp32 copy of v1 is only ever read back as FFN2's residual source: not written when that reads the planes
+      if (!e->chain_res_planes) { p.out_f32 = e->x1; p.ld_f32 = kDModel; }
+      p.out_hi = e->x1_p.hi; p.out_lo = e->x1_p.lo; p.ld_bf = kDModel; p.stats_out = e->stats1;
       ph[0].o_hi = e->x1_p.st32_hi; ph[0].o_lo = e->x1_p.st32_lo; ph[0].o_f32 = e->x1_st;
       ph[0].info.done_ctr = ctr;
     }
@@ -424,8 +429,10 @@ int get_chain_tables(cmdi_engine* e, int nseq, const ChainTables** out) {
     base(ph[2], e->ffh_p, e->w2_chain[2 * l], e->w2_chain[2 * l + 1], kDModel, e->ff, kBnWide);
     {
       LinearParams& p = ph[2].info.p;
-      p.bias = w.b2; p.ln_src = e->x1; p.ld_ln = kDModel; p.ln_partials = e->stats1; p.ln_gamma = w.g1; p.ln_beta = w.be1;
-      p.out_f32 = e->vsum; p.ld_f32 = kDModel; p.out_hi = e->xseq_p.hi; p.out_lo = e->xseq_p.lo; p.ld_bf = kDModel; p.stats_out = e->stats2;
+      p.bias = w.b2; p.ld_ln = kDModel; p.ln_partials = e->stats1; p.ln_gamma = w.g1; p.ln_beta = w.be1;
+      if (e->chain_res_planes) { p.ln_src_hi = e->x1_p.hi; p.ln_src_lo = e->x1_p.lo; }
+      else { p.ln_src = e->x1; p.out_f32 = e->vsum; p.ld_f32 = kDModel; }
+      p.out_hi = e->xseq_p.hi; p.out_lo = e->xseq_p.lo; p.ld_bf = kDModel; p.stats_out = e->stats2;
       ph[2].o_hi = e->xseq_p.st32_hi; ph[2].o_lo = e->xseq_p.st32_lo; ph[2].o_f32 = e->vsum_st;
       ph[2].info.wait_ctr = ctr + e->max_m_pairs; ph[2].info.wait_target = ph[1].info.num_n_blocks * 2;
       ph[2].info.done_ctr = ctr + 2 * e->max_m_pairs;
@@ -687,6 +694,7 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   if (const char* g = getenv("CMDI_GRAPH_STEPS")) e->steps_per_graph = atoi(g) > 0 ? atoi(g) : 1;
   if (const char* g = getenv("CMDI_ATTN_SPLIT")) e->attn_trunc_split = strcmp(g, "trunc") == 0;
   if (const char* g = getenv("CMDI_CHAIN")) e->use_chain = atoi(g) != 0;
+  if (const char* g = getenv("CMDI_CHAIN_RES")) e->chain_res_planes = strcmp(g, "f32") != 0;
   if (const char* g = getenv("CMDI_CHAIN_WIDE")) e->chain_wide = atoi(g) != 0;
   if (const char* g = getenv("CMDI_CHAIN_PUBLISH")) e->chain_publish_now = strcmp(g, "deferred") != 0;
   e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount; e->nsplit = cfg->precision;

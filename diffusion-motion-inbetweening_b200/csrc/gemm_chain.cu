@@ -213,8 +213,8 @@ __device__ __forceinline__ void load_tile_constants(const LinearParams& p, RowSt
     const bool ok = sl < kSlices && n < p.N;
     rs.bias[k] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
     rs.c[k] = (ok && p.fold_stats) ? __ldg(p.fold_c + n) : 0.f;
-    rs.g[k] = (ok && p.ln_src) ? __ldg(p.ln_gamma + n) : 0.f;
-    rs.b[k] = (ok && p.ln_src) ? __ldg(p.ln_beta + n) : 0.f;
+    rs.g[k] = (ok && (p.ln_src || p.ln_src_hi)) ? __ldg(p.ln_gamma + n) : 0.f;
+    rs.b[k] = (ok && (p.ln_src || p.ln_src_hi)) ? __ldg(p.ln_beta + n) : 0.f;
   }
   if (p.fold_stats) rs.fold = combine_row_stats(p.fold_stats + (size_t)row * kPartialStride);
   if (p.ln_partials) rs.ln = combine_row_stats(p.ln_partials + (size_t)row * kPartialStride);
@@ -288,20 +288,33 @@ __device__ __forceinline__ void epilogue_slice(const LinearParams& p, const Chai
   const int n0 = n_blk * kBlockN + slice * 32;
   if (n0 >= p.N) return;  // warp-uniform: columns beyond the layer's width (output head)
   const float* res_src = p.residual ? p.residual : p.ln_src;
+  const bool res_planes = p.ln_src_hi != nullptr;  // LayerNorm's input as bf16 hi / lo planes instead of fp32 rows
+  const bool has_res = res_src || res_planes;
   // the staging tile is about to be rewritten (residual fetch or stores): the bulk store issued from it has been read out
   CMDI_T(8);   // row statistics
   if (lane == 0) tma_store_wait_read();
   __syncwarp();
   CMDI_T(9);   // staging free
   const long long res_ld = p.residual ? p.ld_res : p.ld_ln;
-  if (res_src && !rv_ready) {
-    // fp32 residual block, 32 rows x 128 B, fetched coalesced (4 complete row segments per instruction).  Under this
-    // kernel's load an L2 round trip costs ~2 us, so the block of the warp's NEXT slice of the same tile is requested
-    // while this one is processed (below); only a tile's first slice pays the latency here.
+  // Residual block of 32 rows x 32 columns, fetched coalesced into rv: fp32 rows (8 x 16 B per thread, 4 complete 128 B
+  // row segments per instruction) or the two bf16 planes (4 + 4 x 16 B, 8 complete 64 B segments per instruction).
+  // Under this kernel's load an L2 round trip costs ~2 us, so the block of the warp's NEXT slice of the same tile is
+  // requested while this one is processed (below); only a tile's first slice pays the latency here.
+  auto fetch_residual = [&](int n) {
+    if (res_planes) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it)
-      rv[it] = ld_global_cg_v4(res_src + (long long)(warp_row0 + it * 4 + (lane >> 3)) * res_ld + n0 + (lane & 7) * 4);
-  }
+      for (int it = 0; it < 4; ++it) {
+        const long long off = (long long)(warp_row0 + it * 8 + (lane >> 2)) * p.ld_ln + n + (lane & 3) * 8;
+        rv[it] = ld_global_cg_v4(p.ln_src_hi + off);
+        rv[4 + it] = ld_global_cg_v4(p.ln_src_lo + off);
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        rv[it] = ld_global_cg_v4(res_src + (long long)(warp_row0 + it * 4 + (lane >> 3)) * res_ld + n + (lane & 7) * 4);
+    }
+  };
+  if (has_res && !rv_ready) fetch_residual(n0);
   rv_ready = false;
   uint32_t v[32];
   tmem_ld32(tmem_acc + slice * 32, v);
@@ -321,36 +334,62 @@ __device__ __forceinline__ void epilogue_slice(const LinearParams& p, const Chai
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] += __shfl_sync(0xffffffffu, bk, j);
   }
-  if (res_src) {
+  if (has_res) {
     // transpose through the staging tile: every thread gets its own row
-    const int c = lane & 7;
+    if (res_planes) {
+      // hi block at +0, lo block at +2048, 64 B rows, 16 B chunk c of row r at chunk c ^ ((r >> 1) & 3)
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + (lane >> 3);
-      st_shared_v4(stage + rr * 128 + ((c ^ (rr & 7)) << 4), rv[it].x, rv[it].y, rv[it].z, rv[it].w);
+      for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + (lane >> 2);
+        const uint32_t a = stage + rr * 64 + ((((uint32_t)lane & 3u) ^ (((uint32_t)rr >> 1) & 3u)) << 4);
+        st_shared_v4(a, rv[it].x, rv[it].y, rv[it].z, rv[it].w);
+        st_shared_v4(a + 2048, rv[4 + it].x, rv[4 + it].y, rv[4 + it].z, rv[4 + it].w);
+      }
+    } else {
+      const int c = lane & 7;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + (lane >> 3);
+        st_shared_v4(stage + rr * 128 + ((c ^ (rr & 7)) << 4), rv[it].x, rv[it].y, rv[it].z, rv[it].w);
+      }
     }
     if (next_slice >= 0 && n_blk * kBlockN + next_slice * 32 < p.N) {
       // the registers are free again: request the residual block of this warp's next slice (same tile, same rows)
-      const int n1 = n_blk * kBlockN + next_slice * 32;
-#pragma unroll
-      for (int it = 0; it < 8; ++it)
-        rv[it] = ld_global_cg_v4(res_src + (long long)(warp_row0 + it * 4 + (lane >> 3)) * res_ld + n1 + (lane & 7) * 4);
+      fetch_residual(n_blk * kBlockN + next_slice * 32);
       rv_ready = true;
     }
     __syncwarp();
     const float gk = pick(rs.g, k_in_tile), btk = pick(rs.b, k_in_tile);
+    if (res_planes) {
+      const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const uint4 u = ld_shared_v4(stage + lane * 128 + ((g ^ (lane & 7)) << 4));
-      if (p.ln_src) {
-        // residual = LayerNorm(ln_src) re-derived from its fp32 input, the row statistics and gamma / beta
-        f[g * 4 + 0] += ln_apply(__uint_as_float(u.x), rs.ln.x, rs.ln.y, __shfl_sync(0xffffffffu, gk, g * 4 + 0), __shfl_sync(0xffffffffu, btk, g * 4 + 0));
-        f[g * 4 + 1] += ln_apply(__uint_as_float(u.y), rs.ln.x, rs.ln.y, __shfl_sync(0xffffffffu, gk, g * 4 + 1), __shfl_sync(0xffffffffu, btk, g * 4 + 1));
-        f[g * 4 + 2] += ln_apply(__uint_as_float(u.z), rs.ln.x, rs.ln.y, __shfl_sync(0xffffffffu, gk, g * 4 + 2), __shfl_sync(0xffffffffu, btk, g * 4 + 2));
-        f[g * 4 + 3] += ln_apply(__uint_as_float(u.w), rs.ln.x, rs.ln.y, __shfl_sync(0xffffffffu, gk, g * 4 + 3), __shfl_sync(0xffffffffu, btk, g * 4 + 3));
-      } else {
-        f[g * 4 + 0] += __uint_as_float(u.x); f[g * 4 + 1] += __uint_as_float(u.y);
-        f[g * 4 + 2] += __uint_as_float(u.z); f[g * 4 + 3] += __uint_as_float(u.w);
+      for (int c = 0; c < 4; ++c) {
+        const uint4 uh = ld_shared_v4(stage + lane * 64 + (((uint32_t)c ^ sw) << 4));
+        const uint4 ul = ld_shared_v4(stage + 2048 + lane * 64 + (((uint32_t)c ^ sw) << 4));
+        const uint32_t hw[4] = {uh.x, uh.y, uh.z, uh.w}, lw[4] = {ul.x, ul.y, ul.z, ul.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const int j = c * 8 + w * 2;
+          const float x0 = __uint_as_float(hw[w] << 16) + __uint_as_float(lw[w] << 16);
+          const float x1 = __uint_as_float(hw[w] & 0xffff0000u) + __uint_as_float(lw[w] & 0xffff0000u);
+          f[j] += ln_apply(x0, rs.ln.x, rs.ln.y, __shfl_sync(0xffffffffu, gk, j), __shfl_sync(0xffffffffu, btk, j));
+          f[j + 1] += ln_apply(x1, rs.ln.x, rs.ln.y, __shfl_sync(0xffffffffu, gk, j + 1), __shfl_sync(0xffffffffu, btk, j + 1));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint4 u = ld_shared_v4(stage + lane * 128 + ((g ^ (lane & 7)) << 4));
+        if (p.ln_src) {
+          // residual = LayerNorm(ln_src) re-derived from its fp32 input, the row statistics and gamma / beta
+          f[g * 4 + 0] += ln_apply(__uint_as_float(u.x), rs.ln.x, rs.ln.y, __shfl_sync(0xffffffffu, gk, g * 4 + 0), __shfl_sync(0xffffffffu, btk, g * 4 + 0));
+          f[g * 4 + 1] += ln_apply(__uint_as_float(u.y), rs.ln.x, rs.ln.y, __shfl_sync(0xffffffffu, gk, g * 4 + 1), __shfl_sync(0xffffffffu, btk, g * 4 + 1));
+          f[g * 4 + 2] += ln_apply(__uint_as_float(u.z), rs.ln.x, rs.ln.y, __shfl_sync(0xffffffffu, gk, g * 4 + 2), __shfl_sync(0xffffffffu, btk, g * 4 + 2));
+          f[g * 4 + 3] += ln_apply(__uint_as_float(u.w), rs.ln.x, rs.ln.y, __shfl_sync(0xffffffffu, gk, g * 4 + 3), __shfl_sync(0xffffffffu, btk, g * 4 + 3));
+        } else {
+          f[g * 4 + 0] += __uint_as_float(u.x); f[g * 4 + 1] += __uint_as_float(u.y);
+          f[g * 4 + 2] += __uint_as_float(u.z); f[g * 4 + 3] += __uint_as_float(u.w);
+        }
       }
     }
   }

@@ -45,15 +45,21 @@ struct LinearParams {
   const float* ln_gamma;
   const float* ln_beta;
   // ---- chained launches only (gemm_chain.cu) ----
-  // ... or from the 16 partial statistics per row a producer epilogue published (stats_out below) instead of ln_stats
+  // ... or from the partial statistics per row a producer epilogue published (stats_out below) instead of ln_stats
   const float2* ln_partials;
+  // ... with LayerNorm's input read back as the bf16 hi + lo planes [rows, ld_ln] the producer wrote for the next GEMM
+  // anyway (v = hi + lo to 2^-17 relative: the same quantisation the GEMMs' A operand already has), so that the
+  // producer need not store an fp32 copy as well.  Takes precedence over ln_src.
+  const __nv_bfloat16* ln_src_hi;
+  const __nv_bfloat16* ln_src_lo;
   // LayerNorm folded into THIS linear layer (the A operand is the un-normalised v, the W operand is W * gamma):
   //   LN(v) W^T = rstd * (v (W.gamma)^T - mean * c) + d,   c[n] = sum_k W[n,k] gamma[k],  d[n] = sum_k W[n,k] beta[k] + b[n]
-  // fold_stats: [rows][16] partial (mean, M2) of the A rows (16 x 32 columns); fold_c: [N]; `bias` carries d.
+  // fold_stats: [rows][16] float2 slots, the first 4 hold the partial (mean, M2) of the A row's four 128-column quarters;
+  // fold_c: [N]; `bias` carries d.
   const float2* fold_stats;
   const float* fold_c;
-  // publish the partial statistics of the OUTPUT rows: stats_out[row * 16 + (col / 32)] = (mean, sum of squared
-  // deviations) over the 32 output columns starting at col (N must be 512); consumed by ln_partials / fold_stats
+  // publish the partial statistics of the OUTPUT rows: stats_out[row * 16 + q] = (mean, sum of squared deviations) over
+  // the 128 output columns one epilogue warp owns (N must be 512); consumed by ln_partials / fold_stats
   float2* stats_out;
   const float* pos_enc;  // fp32 [L+1, N] table added per output sequence position (ROWMAP_FRAMES_TO_SEQ); or null
   int act;               // 0 none, 1 exact erf GELU, 2 SiLU, 3 Mish (x tanh(softplus(x)), nn.Mish)
