@@ -21,13 +21,14 @@
 //   consumer epilogue: ordered after the TMA lane's acquire through full[] -> MMA -> tmem_full[]; its reads of
 //                      activations written in this launch use ld.global.cg
 //
-// Epilogue (see also the note at CMDI_CHAIN_EPI_WARPS).  The first version of this kernel processed 64-column chunks
-// per warp with shuffled per-column constants and a release fence per warp: 13k .. 44k cycles of epilogue per tile against
-// a 12.3k-cycle K = 512 mainloop.  Now the accumulator tile is cut into eight 32-column slices handed round-robin to the
-// warps of a TMEM lane group (the next tile's slices start while the previous tile's are still being written); a slice
-// is one fp32 TMA store + one store of both bf16 planes through 64-byte-swizzled boxes; per-column constants come from
-// broadcast loads instead of shuffles; GELU uses a branch-free rational erf; and the release fence / counter bump lives
-// in a warp of its own.  Shared memory: A ring 3 x 32 KB, W ring 3 x 32 KB (separate barriers), 8 x 4 KB staging tiles.
+// Epilogue (see also the measurements at kNumEpiWarps).  Eight warps, two per TMEM lane group.  A tile of a phase with
+// a residual (out-proj, FFN2) is cut into eight 32-column slices, four per warp: bias, the residual LayerNorm(v)
+// re-derived from v's bf16 planes (coalesced loads transposed through the warp's 4 KB staging tile, the next slice's block
+// prefetched into registers), partial row statistics, one store of both bf16 planes through 64-byte-swizzled boxes.  A
+// tile of a planes-only phase (FFN1, QKV) is cut into four 64-column pairs, two per warp: folded-LayerNorm scale / shift,
+// bias, GELU (branch-free rational erf), hi plane then lo plane through 128-byte-swizzled boxes.  Per-column constants
+// are loaded once per tile into registers and handed out by shuffle; the release fence / counter bump lives in a warp of
+// its own.  Shared memory: A ring 2 x 32 KB, W ring 3 x 32 KB (separate barriers), 8 x 4 KB staging tiles = 192 KB.
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include "kernels.h"
@@ -52,13 +53,10 @@ constexpr int kUmmaK = 16;
 // statistics and the few spilled registers around the barrier waits live there, and at 224 KB of shared memory only
 // ~25 KB of L1 remain.  A second staging tile per warp (stores never waiting for the previous store's read) bought
 // nothing at equal shared memory.
-#ifndef CMDI_CHAIN_EPI_WARPS
-#define CMDI_CHAIN_EPI_WARPS 8
-#endif
 #ifndef CMDI_CHAIN_STAGES_W
 #define CMDI_CHAIN_STAGES_W 3
 #endif
-constexpr int kNumEpiWarps = CMDI_CHAIN_EPI_WARPS;
+constexpr int kNumEpiWarps = 8;  // the slice / pair assignment below is written for two warps per lane group
 constexpr int kWarpsPerLaneGroup = kNumEpiWarps / 4;
 constexpr int kFirstEpiWarp = 3;
 constexpr int kNumThreads = (kFirstEpiWarp + kNumEpiWarps) * 32;
