@@ -55,6 +55,8 @@ struct Planes {  // a bf16 hi/lo operand: [rows, ld] row-major, with TMA maps fo
   CUtensorMap pair_hi{}, pair_lo{};  // same planes, box height halved: W operand of the CTA-pair kernel
   CUtensorMap st_hi{}, st_lo{};      // same planes as a TMA-store target: box {64, 32}
   CUtensorMap st32_hi{}, st32_lo{};  // ... box {32, 32}, 64-byte swizzle (32-column slices of the chained epilogue)
+  CUtensorMap tap_hi{}, tap_lo{};    // A operand of a k-tap convolution: box {64, 136} (the rows of all taps at once)
+  bool has_tap = false;
 };
 
 struct LayerW {
@@ -194,6 +196,11 @@ int alloc_planes(cmdi_engine* e, Planes* pl, int rows, int cols, int ld, int box
   CKI(make_tmap_bf16_2d(&pl->st_lo, pl->lo, rows, cols, ld, 64, 32));
   CKI(make_tmap_bf16_2d(&pl->st32_hi, pl->hi, rows, cols, ld, 32, 32));
   CKI(make_tmap_bf16_2d(&pl->st32_lo, pl->lo, rows, cols, ld, 32, 32));
+  if (box_rows == 128 && rows >= 136) {
+    CKI(make_tmap_bf16_2d(&pl->tap_hi, pl->hi, rows, cols, ld, 64, 136));
+    CKI(make_tmap_bf16_2d(&pl->tap_lo, pl->lo, rows, cols, ld, 64, 136));
+    pl->has_tap = true;
+  }
   return 0;
 }
 
@@ -253,10 +260,12 @@ int run_linear(cmdi_engine* e, const Planes& a, const Planes& w, const LinearPar
   LinearParams p = p_in;
   p.debug = e->debug;
   LinearStoreMaps st;
-  if (out_planes) { st.hi = &out_planes->st_hi; st.lo = &out_planes->st_lo; }
-  st.f32 = out_f32;
-  const LinearStoreMaps* stp = (e->tma_store && (out_planes || out_f32)) ? &st : nullptr;
-  CK(launch_linear_pair(a.map_hi, a.map_lo, w.pair_hi, w.pair_lo, p, block_n, e->num_sms, s, stp));
+  if (e->tma_store) {
+    if (out_planes) { st.hi = &out_planes->st_hi; st.lo = &out_planes->st_lo; }
+    st.f32 = out_f32;
+  }
+  if (a.has_tap) { st.a_tap_hi = &a.tap_hi; st.a_tap_lo = &a.tap_lo; }
+  CK(launch_linear_pair(a.map_hi, a.map_lo, w.pair_hi, w.pair_lo, p, block_n, e->num_sms, s, &st));
   return 0;
 }
 

@@ -13,6 +13,7 @@
 //   empty[s]      per CTA, signalled by the leader's tcgen05.commit multicast to both CTAs
 //   tmem_full[a]  per CTA, same multicast commit
 //   tmem_empty[a] on the leader: epilogue warps of BOTH CTAs arrive on it (remote arrive from the peer)
+#include <cstdlib>
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include "kernels.h"
@@ -33,13 +34,23 @@ constexpr int kABytes = kBlockM * kBlockK * 2;
 struct __align__(8) PairBarriers {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
+  uint64_t full_a[2], empty_a[2];  // TAP_REUSE: the A ring
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
 
-template <int BLOCK_N>
+// TAP_REUSE (k-tap convolutions whose taps are consecutive row shifts of the same A columns): the A tile of a channel
+// block is loaded ONCE as 128 + (taps - 1) rows (box of kTapRows rows) and every tap's MMAs read it through a descriptor
+// whose start address is shifted by `tap` rows (128 B each), against that tap's own W tile: A ring of 2 tiles + W ring of `num_stages` tiles instead of
+// `num_stages` (A, W) stages.  For k = 5 that is 33 + 5 x 32 KB of operands per CTA and channel block instead of
+// 5 x 64 KB -- the mainloop of these GEMMs sits on the L2->SM operand stream.
+constexpr int kTapRows = 136;                          // 128 + 8: up to 8 further taps (whole swizzle atoms)
+constexpr int kATapBytes = kTapRows * kBlockK * 2;     // one plane of an A tile with its tap rows: 17 KB
+constexpr int kTapStagesA = 2;
+
+template <int BLOCK_N, bool TAP_REUSE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -57,8 +68,12 @@ linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int nplanes = (p.nsplit == 3) ? 2 : 1;
-  const uint32_t stage_bytes = nplanes * (kABytes + kBBytes);
-  uint8_t* epi_stage = smem + (size_t)num_stages * stage_bytes;  // kNumEpiWarps x 4 KB store-staging tiles
+  // general: num_stages x {A planes, W planes};  TAP_REUSE: kTapStagesA x {A planes with tap rows}, num_stages x {W planes}
+  const uint32_t stage_bytes = TAP_REUSE ? nplanes * kBBytes : nplanes * (kABytes + kBBytes);
+  const uint32_t a_tile_bytes = nplanes * kATapBytes;
+  uint8_t* ring_a = smem;                                                        // TAP_REUSE only
+  uint8_t* ring = TAP_REUSE ? smem + (size_t)kTapStagesA * a_tile_bytes : smem;  // stages (general) / W tiles (TAP_REUSE)
+  uint8_t* epi_stage = ring + (size_t)num_stages * stage_bytes;  // kNumEpiWarps x 4 KB store-staging tiles
   PairBarriers* bars = reinterpret_cast<PairBarriers*>(epi_stage + kNumEpiWarps * kEpiStageBytes);
 
   const int warp_idx = threadIdx.x >> 5;
@@ -81,6 +96,8 @@ linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->tmem_full[s], 1);
       mbar_init(&bars->tmem_empty[s], 2 * kNumEpiWarps);
+      mbar_init(&bars->full_a[s], 1);
+      mbar_init(&bars->empty_a[s], 1);
     }
     fence_barrier_init();
   }
@@ -99,6 +116,34 @@ linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if constexpr (TAP_REUSE) {
+        int sa_i = 0;
+        uint32_t pa = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+          const int m_blk = 2 * (tile / num_n_blocks) + (int)cta_rank;
+          const int n_blk = tile % num_n_blocks;
+          for (int cb = 0; cb < kb_per_tap; ++cb) {
+            // the A rows of all taps of this channel block: rows m_blk * 128 + tap_row[0] .. + 127 + (taps - 1)
+            mbar_wait(&bars->empty_a[sa_i], pa ^ 1);
+            uint8_t* sa = ring_a + (size_t)sa_i * a_tile_bytes;
+            if (leader) mbar_arrive_expect_tx(&bars->full_a[sa_i], 2 * a_tile_bytes);
+            tma_load_2d_2sm(sa, &map_a_hi, &bars->full_a[sa_i], p.tap_a_col[0] + cb * kBlockK, m_blk * kBlockM + p.tap_row[0]);
+            if (nplanes == 2)
+              tma_load_2d_2sm(sa + kATapBytes, &map_a_lo, &bars->full_a[sa_i], p.tap_a_col[0] + cb * kBlockK, m_blk * kBlockM + p.tap_row[0]);
+            if (++sa_i == kTapStagesA) { sa_i = 0; pa ^= 1; }
+            for (int tap = 0; tap < p.num_taps; ++tap) {
+              mbar_wait(&bars->empty[stage], phase ^ 1);
+              uint8_t* sb = ring + (size_t)stage * stage_bytes;
+              if (leader) mbar_arrive_expect_tx(&bars->full[stage], 2 * stage_bytes);
+              const int w_col = p.tap_w_col[tap] + cb * kBlockK;
+              tma_load_2d_2sm(sb, &map_w_hi, &bars->full[stage], w_col, n_blk * BLOCK_N + (int)cta_rank * kHalfN);
+              if (nplanes == 2)
+                tma_load_2d_2sm(sb + kBBytes, &map_w_lo, &bars->full[stage], w_col, n_blk * BLOCK_N + (int)cta_rank * kHalfN);
+              if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      } else {
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m_blk = 2 * (tile / num_n_blocks) + (int)cta_rank;
         const int n_blk = tile % num_n_blocks;
@@ -129,6 +174,7 @@ linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
         }
       }
+      }
     }
     __syncwarp();
   } else if (warp_idx == 1) {
@@ -139,6 +185,8 @@ linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int sa_i = 0;      // TAP_REUSE: A ring position / parity
+      uint32_t pa = 0;
       long long t_wait_empty = 0, t_wait_full = 0, t_begin = clock64();
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         long long c0 = clock64();
@@ -146,6 +194,52 @@ linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         t_wait_empty += clock64() - c0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        if constexpr (TAP_REUSE) {
+          uint32_t accum = 0;
+          for (int cb = 0; cb < kb_per_tap; ++cb) {
+            c0 = clock64();
+            mbar_wait(&bars->full_a[sa_i], pa);
+            t_wait_full += clock64() - c0;
+            const uint32_t sa = smem_u32(ring_a + (size_t)sa_i * a_tile_bytes);
+            for (int tap = 0; tap < p.num_taps; ++tap) {
+              c0 = clock64();
+              mbar_wait(&bars->full[stage], phase);
+              t_wait_full += clock64() - c0;
+              tc_fence_after();
+              const uint32_t sb = smem_u32(ring + (size_t)stage * stage_bytes);
+              // A rows shifted by `tap`: start address + tap * 128 B.  The 128-byte swizzle is a function of the absolute
+              // shared-memory address (bits 7-9 into bits 4-6) for TMA and MMA alike, so a row-shifted view needs no
+              // descriptor base offset (measured: with base offset = tap the results are wrong).
+              const uint64_t da_hi = make_desc_kmajor_sw128(sa + tap * 128);
+              const uint64_t db_hi = make_desc_kmajor_sw128(sb);
+              if (nplanes == 2) {
+                const uint64_t da_lo = make_desc_kmajor_sw128(sa + kATapBytes + tap * 128);
+                const uint64_t db_lo = make_desc_kmajor_sw128(sb + kBBytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                  umma_ss_2sm(d_tmem, desc_advance(da_lo, k * kUmmaK * 2), desc_advance(db_hi, k * kUmmaK * 2), idesc, accum);
+                  accum = 1;
+                }
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  umma_ss_2sm(d_tmem, desc_advance(da_hi, k * kUmmaK * 2), desc_advance(db_lo, k * kUmmaK * 2), idesc, 1u);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  umma_ss_2sm(d_tmem, desc_advance(da_hi, k * kUmmaK * 2), desc_advance(db_hi, k * kUmmaK * 2), idesc, 1u);
+              } else {
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                  umma_ss_2sm(d_tmem, desc_advance(da_hi, k * kUmmaK * 2), desc_advance(db_hi, k * kUmmaK * 2), idesc, accum);
+                  accum = 1;
+                }
+              }
+              umma_commit_2sm(&bars->empty[stage], 0x3);
+              if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit_2sm(&bars->empty_a[sa_i], 0x3);  // all taps of this channel block have read the A tile
+            if (++sa_i == kTapStagesA) { sa_i = 0; pa ^= 1; }
+          }
+        } else {
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           c0 = clock64();
           mbar_wait(&bars->full[stage], phase);
@@ -181,6 +275,7 @@ linear2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             stage = 0;
             phase ^= 1;
           }
+        }
         }
         umma_commit_2sm(&bars->tmem_full[acc], 0x3);  // both CTAs' epilogues may read their half of the tile
         acc ^= 1;
@@ -240,8 +335,8 @@ cudaError_t launch_impl2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const
   LinearParams p = p_in;
   p.tma_store = 0;
   CUtensorMap o_hi = a_hi, o_lo = a_hi, o_f32 = a_hi;  // placeholders when the STG epilogue is used
-  if (st && p.rowmap == ROWMAP_IDENTITY && p.dup_row_offset == 0 && (!p.out_hi || (st->hi && (p.nsplit_out != 3 || st->lo))) &&
-      (!p.out_f32 || st->f32)) {
+  if (st && (st->hi || st->f32) && p.rowmap == ROWMAP_IDENTITY && p.dup_row_offset == 0 &&
+      (!p.out_hi || (st->hi && (p.nsplit_out != 3 || st->lo))) && (!p.out_f32 || st->f32)) {
     p.tma_store = 1;
     if (st->hi) o_hi = *st->hi;
     if (st->lo) o_lo = *st->lo;
@@ -249,27 +344,43 @@ cudaError_t launch_impl2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const
   }
   constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;
   const int nplanes = (p.nsplit == 3) ? 2 : 1;
-  const int stage_bytes = nplanes * (kABytes + kBBytes);
-  int num_stages = (kSmemLimit - 1024 - kNumEpiWarps * kEpiStageBytes - (int)sizeof(PairBarriers)) / stage_bytes;
-  if (num_stages > kMaxStages) num_stages = kMaxStages;
-  const size_t smem = 1024 + (size_t)num_stages * stage_bytes + kNumEpiWarps * kEpiStageBytes + sizeof(PairBarriers);
   const int num_m_pairs = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);
   const int num_n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m_pairs * num_n_blocks;
   int clusters = num_sms / 2;
   if (clusters > num_tiles) clusters = num_tiles;
-  return launch_kernel(linear2_kernel<BLOCK_N>, dim3(2 * clusters), dim3(kNumThreads), smem, stream, a_hi, a_lo, w_hi, w_lo,
+  const int fixed = 1024 + kNumEpiWarps * kEpiStageBytes + (int)sizeof(PairBarriers);
+  // convolution whose taps are consecutive row shifts of the same A columns, and an A map with a kTapRows-row box
+  bool reuse = st && st->a_tap_hi && (nplanes == 1 || st->a_tap_lo) && p.num_taps >= 2 && p.num_taps <= kTapRows - kBlockM + 1;
+  for (int t = 1; reuse && t < p.num_taps; ++t)
+    reuse = p.tap_a_col[t] == p.tap_a_col[0] && p.tap_row[t] == p.tap_row[0] + t;
+  static const bool reuse_off = getenv("CMDI_CONV_REUSE") && atoi(getenv("CMDI_CONV_REUSE")) == 0;  // bring-up A/B
+  if (reuse && !reuse_off) {
+    const int w_bytes = nplanes * kBBytes, a_bytes = kTapStagesA * nplanes * kATapBytes;
+    int num_stages = (kSmemLimit - fixed - a_bytes) / w_bytes;
+    if (num_stages > 4) num_stages = 4;  // beyond ~200 KB the L1 left for the epilogue costs more than the depth buys
+    const size_t smem = (size_t)fixed + a_bytes + (size_t)num_stages * w_bytes;
+    return launch_kernel(linear2_kernel<BLOCK_N, true>, dim3(2 * clusters), dim3(kNumThreads), smem, stream, *st->a_tap_hi,
+                         nplanes == 2 ? *st->a_tap_lo : *st->a_tap_hi, w_hi, w_lo, o_hi, o_lo, o_f32, p, num_stages, num_m_pairs, num_n_blocks);
+  }
+  const int stage_bytes = nplanes * (kABytes + kBBytes);
+  int num_stages = (kSmemLimit - fixed) / stage_bytes;
+  if (num_stages > kMaxStages) num_stages = kMaxStages;
+  const size_t smem = (size_t)fixed + (size_t)num_stages * stage_bytes;
+  return launch_kernel(linear2_kernel<BLOCK_N, false>, dim3(2 * clusters), dim3(kNumThreads), smem, stream, a_hi, a_lo, w_hi, w_lo,
                        o_hi, o_lo, o_f32, p, num_stages, num_m_pairs, num_n_blocks);
 }
 
 }  // namespace
 
 cudaError_t configure_linear2_kernels() {
-  cudaError_t e = cudaFuncSetAttribute(linear2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(linear2_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(linear2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  cudaError_t e = cudaSuccess;
+  auto set = [&](auto kernel) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  };
+  set(linear2_kernel<128, false>); set(linear2_kernel<192, false>); set(linear2_kernel<256, false>);
+  set(linear2_kernel<128, true>); set(linear2_kernel<192, true>); set(linear2_kernel<256, true>);
+  return e;
 }
 
 // Tensor maps: A box {64, 128}; W box {64, block_n / 2}.

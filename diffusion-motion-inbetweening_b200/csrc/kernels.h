@@ -25,6 +25,9 @@ struct LinearStoreMaps {
   const CUtensorMap* hi = nullptr;
   const CUtensorMap* lo = nullptr;
   const CUtensorMap* f32 = nullptr;
+  // optional A-operand maps with a {64, 136} box: let a k-tap convolution load the A rows of all taps once (gemm2.cu)
+  const CUtensorMap* a_tap_hi = nullptr;
+  const CUtensorMap* a_tap_lo = nullptr;
 };
 
 struct LinearParams {
