@@ -31,7 +31,8 @@ sd = O.random_unet_state_dict(seed=11, text=True)
 m = C.MDM_UNET(keyframe_conditioned=True, cond_mode="text", cond_mask_prob=0.1)
 m.load_state_dict(sd, strict=False)
 m = m.to(dev)
-m.encode_text = lambda texts: gi["cond"].to(dev)
+_table = {"a": gi["cond"][0].to(dev), "b": gi["cond"][1].to(dev)}
+m.encode_text = lambda texts: torch.stack([_table[t] for t in texts])  # per-sample timesteps are evaluated in groups
 x, xo, kf = gi["x"].to(dev), gi["x_obs"].to(dev), gi["kf_mask"].to(dev)
 got = m(x, torch.tensor(g["fwd.t"]).to(dev), y={"text": ["a", "b"]}, obs_x0=xo, obs_mask=kf)
 rep(got, g["fwd.out"], "unet xl forward (text, keyframes) vs reference")
