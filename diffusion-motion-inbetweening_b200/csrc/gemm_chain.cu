@@ -203,17 +203,38 @@ __device__ __forceinline__ float pick(const float (&a)[kSlicesPerWarp], int k) {
 __device__ __forceinline__ int warp_slice(int k, int warp_in_group, bool wide) {
   return wide ? 2 * (warp_in_group + kWarpsPerLaneGroup * (k >> 1)) + (k & 1) : warp_in_group + k * kWarpsPerLaneGroup;
 }
-__device__ __forceinline__ void load_tile_constants(const LinearParams& p, RowStats& rs, int row, int n_blk, int warp_in_group, bool wide, int lane) {
+// The constants do not depend on anything computed in this launch: they are requested BEFORE the warp waits for the tile's
+// accumulator, all loads of a vector in flight together (indices clamped instead of predicated; measured before: one
+// predicated load at a time, each followed by the spill of its result, was 11 % of this kernel's stall samples).
+__device__ __forceinline__ void load_tile_constants(const LinearParams& p, RowStats& rs, int n_blk, int warp_in_group, bool wide, int lane) {
+  int idx[kSlicesPerWarp];
+  bool ok[kSlicesPerWarp];
 #pragma unroll
   for (int k = 0; k < kSlicesPerWarp; ++k) {
     const int sl = warp_slice(k, warp_in_group, wide);
     const int n = n_blk * kBlockN + sl * 32 + lane;
-    const bool ok = sl < kSlices && n < p.N;
-    rs.bias[k] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
-    rs.c[k] = (ok && p.fold_stats) ? __ldg(p.fold_c + n) : 0.f;
-    rs.g[k] = (ok && (p.ln_src || p.ln_src_hi)) ? __ldg(p.ln_gamma + n) : 0.f;
-    rs.b[k] = (ok && (p.ln_src || p.ln_src_hi)) ? __ldg(p.ln_beta + n) : 0.f;
+    ok[k] = sl < kSlices && n < p.N;
+    idx[k] = ok[k] ? n : 0;
   }
+  const bool ln = p.ln_src || p.ln_src_hi;
+  float t[4][kSlicesPerWarp];
+#pragma unroll
+  for (int k = 0; k < kSlicesPerWarp; ++k) {
+    t[0][k] = p.bias ? __ldg(p.bias + idx[k]) : 0.f;
+    t[1][k] = p.fold_stats ? __ldg(p.fold_c + idx[k]) : 0.f;
+    t[2][k] = ln ? __ldg(p.ln_gamma + idx[k]) : 0.f;
+    t[3][k] = ln ? __ldg(p.ln_beta + idx[k]) : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < kSlicesPerWarp; ++k) {
+    rs.bias[k] = ok[k] ? t[0][k] : 0.f;
+    rs.c[k] = ok[k] ? t[1][k] : 0.f;
+    rs.g[k] = ok[k] ? t[2][k] : 0.f;
+    rs.b[k] = ok[k] ? t[3][k] : 0.f;
+  }
+}
+// ... and, once the accumulator (hence the producer phase's statistics) is there, the statistics of the thread's row
+__device__ __forceinline__ void load_row_statistics(const LinearParams& p, RowStats& rs, int row) {
   if (p.fold_stats) rs.fold = combine_row_stats(p.fold_stats + (size_t)row * kPartialStride);
   if (p.ln_partials) rs.ln = combine_row_stats(p.ln_partials + (size_t)row * kPartialStride);
   rs.run_mean = 0.f; rs.run_m2 = 0.f;
@@ -533,6 +554,14 @@ linear_chain_kernel(const ChainPhaseDesc* __restrict__ phases, const int num_pha
         for (int kb = 0; kb < pi.num_k_blocks; ++kb) {
           c0 = clock64();
           mbar_wait(&bars->empty_w[sw], pw ^ 1);
+          if (pi.p.debug & 4) {
+            // bring-up decomposition (CMDI_DEBUG=4): no operand loads, only the pipeline bookkeeping
+            mbar_wait(&bars->empty_a[sa], pa ^ 1);
+            if (leader) { mbar_arrive(&bars->full_w[sw]); mbar_arrive(&bars->full_a[sa]); }
+            if (++sa == kStagesA) { sa = 0; pa ^= 1; }
+            if (++sw == kStagesW) { sw = 0; pw ^= 1; }
+            continue;
+          }
           uint8_t* dw = ring_w + (size_t)sw * kOperandBytes;
           if (leader) mbar_arrive_expect_tx(&bars->full_w[sw], tx_bytes);
           tma_load_2d_2sm(dw, &pd.w_hi, &bars->full_w[sw], kb * kBlockK, n_blk * kBlockN + (int)cta_rank * (kBlockN / 2));
@@ -577,7 +606,9 @@ linear_chain_kernel(const ChainPhaseDesc* __restrict__ phases, const int num_pha
           const uint32_t w_addr = smem_u32(ring_w + (size_t)sw * kOperandBytes);
           const uint64_t da_hi = make_desc_kmajor_sw128(a_addr);
           const uint64_t db_hi = make_desc_kmajor_sw128(w_addr);
-          if (split) {
+          if (pi.p.debug & 2) {
+            // bring-up decomposition (CMDI_DEBUG=2): no MMAs, only the pipeline bookkeeping
+          } else if (split) {
             const uint64_t da_lo = make_desc_kmajor_sw128(a_addr + kPlaneBytes);
             const uint64_t db_lo = make_desc_kmajor_sw128(w_addr + kPlaneBytes);
 #pragma unroll
@@ -649,6 +680,7 @@ linear_chain_kernel(const ChainPhaseDesc* __restrict__ phases, const int num_pha
       const int n_blk = local % pi.num_n_blocks;
       const int acc = seq & 1;
       const bool wide = pi.wide != 0;
+      load_tile_constants(pi.p, rs, n_blk, j3, wide, lane);
       mbar_wait(&bars->tmem_full[acc], (seq >> 1) & 1);
       long long c1 = clock64();
       tc_fence_after();
@@ -657,7 +689,7 @@ linear_chain_kernel(const ChainPhaseDesc* __restrict__ phases, const int num_pha
         stored_seq = -1;
       }
       long long c2 = clock64();
-      load_tile_constants(pi.p, rs, m_blk * kBlockM + lane_group * 32 + lane, n_blk, j3, wide, lane);
+      load_row_statistics(pi.p, rs, m_blk * kBlockM + lane_group * 32 + lane);
       const uint32_t tmem_acc = tmem_lane + acc * kAccStride;
       long long* dbg_w = (dbg_me && ew == 0 && lane == 0) ? dbg_me + ph * 16 : nullptr;
       if (wide) {
