@@ -184,9 +184,10 @@ constexpr int kSlicesPerWarp = (kSlices + kWarpsPerLaneGroup - 1) / kWarpsPerLan
 struct RowStats {   // per-tile cache of what this thread needs for its slices of the tile
   float2 fold, ln;                 // (mean, rstd) of its row: folded LayerNorm of the A operand / LayerNorm of the residual
   // Per-COLUMN constants (bias, folded-LN c, LayerNorm gamma / beta of the residual): lane l holds column l of the warp's
-  // k-th slice of the tile, loaded with one coalesced request per vector at the tile's first slice and handed out by
-  // shuffle.  (Fetched per use they were ~15 % of this kernel's stall samples: the tile's constants are rarely in the
-  // ~25 KB of L1 left beside 224 KB of shared memory, and an L2 round trip costs 2-3 us under this load.)
+  // k-th slice of the tile, loaded with one coalesced request per vector before the tile's accumulator wait
+  // (load_tile_constants) and handed out by shuffle.  History: fetched at the point of use they were ~15 % of this kernel's
+  // stall samples (an L2 round trip costs 2-3 us under this load); loaded per tile but one predicated load at a time, 11 %.
+  // (Per slice, one slice ahead, in 4 registers instead of 16: slower, 154.6 -> 161.6 us per launch.)
   float bias[kSlicesPerWarp], c[kSlicesPerWarp], g[kSlicesPerWarp], b[kSlicesPerWarp];
   float run_mean, run_m2;          // running statistics of this thread's output row over the warp's slices of the tile
 };
@@ -654,7 +655,7 @@ linear_chain_kernel(const ChainPhaseDesc* __restrict__ phases, const int num_pha
     }
     __syncwarp();
   } else {
-    // ============ epilogue warps: kWarpsPerLaneGroup per TMEM lane group, 32-column slices handed round-robin ============
+    // ============ epilogue warps: two per TMEM lane group; four 32-column slices or two 64-column pairs per warp and tile ============
     const int ew = warp_idx - kFirstEpiWarp;
     const int lane_group = warp_idx & 3;  // the TMEM lanes a warp may touch: 32 * (warp index % 4)
     const int j3 = ew >> 2;               // index within the lane group
