@@ -477,6 +477,12 @@ __global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ 
   }
 }
 
+// out = a + b (fp32): LayerNorm beta + the bias of the layer whose epilogue re-derives that LayerNorm as its residual
+__global__ void add_vectors_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
 __global__ void split_planes_kernel(const float* __restrict__ in, int rows, int cols, int ld_in, __nv_bfloat16* __restrict__ hi,
                                     __nv_bfloat16* __restrict__ lo, int ld_out) {
   const size_t total = (size_t)rows * ld_out;
@@ -685,6 +691,11 @@ cudaError_t launch_set_int(int* p, int v, cudaStream_t stream) {
 cudaError_t launch_fold_ln(const float* W, int N, int K, const float* gamma, const float* beta, const float* bias, float* Wf,
                            float* c, float* d, cudaStream_t stream) {
   fold_ln_kernel<<<(N + 7) / 8, 256, 0, stream>>>(W, N, K, gamma, beta, bias, Wf, c, d);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_add_vectors(const float* a, const float* b, float* out, int n, cudaStream_t stream) {
+  add_vectors_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a, b, out, n);
   return cudaGetLastError();
 }
 

@@ -161,6 +161,7 @@ struct cmdi_engine {
   int chain_publish_now = 1;  // CMDI_CHAIN_PUBLISH=deferred: counter bumps deferred to the warp's next tile
   std::vector<FoldedW> f_qkv, f_w1;
   FoldedW f_out;
+  std::vector<float*> beta_bo, beta_b2;         // [layer]: norm2_{l-1}.bias + out_proj_l.bias, norm1_l.bias + linear2_l.bias (chained epilogues)
   std::vector<CUtensorMap> wo_chain, w2_chain;  // [layer][hi, lo]: wo / w2 planes with the chain's W box
   float2 *stats1 = nullptr, *stats2 = nullptr;  // [seq_rows_pad][16] partial row statistics of v1 / v2 (32-column slices)
   int* chain_ctr = nullptr;                     // [layers][3][max_m_pairs] dependency counters, zeroed every pass
@@ -411,10 +412,10 @@ int get_chain_tables(cmdi_engine* e, int nseq, const ChainTables** out) {
     base(ph[0], e->attn_p, e->wo_chain[2 * l], e->wo_chain[2 * l + 1], kDModel, kDModel, kBnWide);
     {
       LinearParams& p = ph[0].info.p;
-      p.bias = w.bo;
-      if (l == 0) { p.residual = e->xseq; p.ld_res = kDModel; }
+      if (l == 0) { p.bias = w.bo; p.residual = e->xseq; p.ld_res = kDModel; }
       else {
-        p.ld_ln = kDModel; p.ln_partials = e->stats2; p.ln_gamma = e->lw[l - 1].g2; p.ln_beta = e->lw[l - 1].be2;
+        // bias folded into the beta of the re-derived LayerNorm residual: one vector (and 32 shuffles + adds per slice) less
+        p.ld_ln = kDModel; p.ln_partials = e->stats2; p.ln_gamma = e->lw[l - 1].g2; p.ln_beta = e->beta_bo[l];
         if (e->chain_res_planes) { p.ln_src_hi = e->xseq_p.hi; p.ln_src_lo = e->xseq_p.lo; }
         else p.ln_src = e->vsum;
       }
@@ -439,7 +440,7 @@ int get_chain_tables(cmdi_engine* e, int nseq, const ChainTables** out) {
     base(ph[2], e->ffh_p, e->w2_chain[2 * l], e->w2_chain[2 * l + 1], kDModel, e->ff, kBnWide);
     {
       LinearParams& p = ph[2].info.p;
-      p.bias = w.b2; p.ld_ln = kDModel; p.ln_partials = e->stats1; p.ln_gamma = w.g1; p.ln_beta = w.be1;
+      p.ld_ln = kDModel; p.ln_partials = e->stats1; p.ln_gamma = w.g1; p.ln_beta = e->beta_b2[l];
       if (e->chain_res_planes) { p.ln_src_hi = e->x1_p.hi; p.ln_src_lo = e->x1_p.lo; }
       else { p.ln_src = e->x1; p.out_f32 = e->vsum; p.ld_f32 = kDModel; }
       p.out_hi = e->xseq_p.hi; p.out_lo = e->xseq_p.lo; p.ld_bf = kDModel; p.stats_out = e->stats2;
@@ -799,6 +800,8 @@ extern "C" int cmdi_engine_create(const cmdi_model_cfg* cfg, int device, cmdi_en
   A(alloc_planes(e, &e->f_out.w, round_up(e->D_pad, 256), kDModel, kDModel, kBnWide));
   A(dev_alloc(e, &e->f_out.c, round_up(e->D_pad, 256))); A(dev_alloc(e, &e->f_out.d, round_up(e->D_pad, 256)));
   e->wo_chain.resize(2 * e->layers);
+  e->beta_bo.assign(e->layers, nullptr); e->beta_b2.assign(e->layers, nullptr);
+  for (int l = 0; l < e->layers; ++l) { A(dev_alloc(e, &e->beta_bo[l], kDModel)); A(dev_alloc(e, &e->beta_b2[l], kDModel)); }
   e->w2_chain.resize(2 * e->layers);
   for (int l = 0; l < e->layers && !rc; ++l) {
     const LayerW& w = e->lw[l];
@@ -955,6 +958,10 @@ extern "C" int cmdi_load_weights(cmdi_engine* e, const cmdi_tensor_desc* tensors
       rc = rc || fold(e->f_w1[l], p + "linear1.weight", e->ff, kDModel, e->lw[l].g1, e->lw[l].be1, e->lw[l].b1);
     }
     rc = rc || fold(e->f_out, "output_process.poseFinal.weight", e->D, kDModel, e->lw[e->layers - 1].g2, e->lw[e->layers - 1].be2, e->b_out);
+    for (int l = 0; l < e->layers && !rc; ++l) {
+      if (l > 0) CK(launch_add_vectors(e->lw[l - 1].be2, e->lw[l].bo, e->beta_bo[l], kDModel, s));
+      CK(launch_add_vectors(e->lw[l].be1, e->lw[l].b2, e->beta_b2[l], kDModel, s));
+    }
     cudaError_t fe = cudaStreamSynchronize(s);
     if (!rc) CK(fe);
   }

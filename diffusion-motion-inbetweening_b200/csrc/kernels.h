@@ -262,6 +262,7 @@ cudaError_t launch_fill_normal_ref(float* out, int B, size_t per_sample, unsigne
 cudaError_t launch_set_int(int* p, int v, cudaStream_t stream);
 
 // LayerNorm folded into its consumer: Wf = W * gamma (fp32 [N,K]), c[n] = sum_k Wf[n,k], d[n] = sum_k W[n,k] beta[k] + bias[n]
+cudaError_t launch_add_vectors(const float* a, const float* b, float* out, int n, cudaStream_t stream);
 cudaError_t launch_fold_ln(const float* W, int N, int K, const float* gamma, const float* beta, const float* bias, float* Wf,
                            float* c, float* d, cudaStream_t stream);
 // fp32 [rows, cols] -> bf16 planes [rows, ld] (zero padded columns)
